@@ -1,0 +1,169 @@
+"""Generate tests/golden/*.npz by running the REFERENCE ITSELF (TEST INFRASTRUCTURE).
+
+Run in the build container (needs /root/reference):   python -m oracle.make_golden
+
+Field cases: the reference's own ``ceviche/fdtd.py`` (loaded unmodified by
+oracle/ref_loader.py) is stepped in the reference's caller loop
+(ceviche/utils.py:325-331) on the seeded inputs of oracle/cases.py; we keep the probe
+series, every field at the snapshot steps (sub-sampled for the two 200x200 cases so the
+fixtures stay small) and the full-grid L2 norm of every field.
+
+Gradient cases: d(objective)/d(eps_r) by (i) torch.autograd / torch.func.jvp over the
+bit-identical torch restatement and (ii) finite differences through the reference numpy
+code -- one-sided with step 1e-6 exactly as tests/test_gradients_fdtd.py:19-20 does, and
+central.  HIPS autograd is not installed here, so (i)+(ii) stand in for the reference's AD.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import cases, ref_loader
+from .fdtd_numpy import FIELD_KEYS, pad_to_3d
+from .fdtd_torch import series_fn
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def run_reference(case, eps=None):
+    """The reference's caller loop; returns (series, {t: fields})."""
+    ref = ref_loader.load()
+    F = ref.fdtd(case["eps"] if eps is None else eps, case["dL"], case["npml"])
+    steps = case["steps"]
+    series = np.zeros((steps, len(case["probes"])))
+    snaps = {}
+    for t in range(steps):
+        J = {"x": None, "y": None, "z": None}
+        for comp, profile, wave in case["sources"]:
+            term = pad_to_3d(profile) * wave[t]
+            J[comp] = term if J[comp] is None else J[comp] + term
+        f = F.forward(Jx=J["x"], Jy=J["y"], Jz=J["z"])
+        for p, (key, mask) in enumerate(case["probes"]):
+            series[t, p] = np.sum(f[key] * pad_to_3d(mask))
+        if (t + 1) in case.get("snapshots", ()):
+            snaps[t + 1] = {k: np.array(f[k], copy=True) for k in FIELD_KEYS}
+    return series, snaps, F
+
+
+def make_field_golden(name):
+    case = cases.field_case(name)
+    series, snaps, F = run_reference(case)
+    out = {"series": series, "dt": np.float64(F.dt)}
+    stride = 5 if name.startswith("c1_") else 1
+    out["stride"] = np.int64(stride)
+    for t, fields in snaps.items():
+        for k, v in fields.items():
+            out["t%d_%s" % (t, k)] = v[::stride, ::stride, :]
+            out["t%d_%s_norm" % (t, k)] = np.float64(np.linalg.norm(v))
+    np.savez_compressed(os.path.join(OUT, "fields_%s.npz" % name), **out)
+    print("fields", name, "series norm", np.linalg.norm(series))
+
+
+def _scalar_objective(case):
+    w = cases.objective_weights(case["steps"], len(case["probes"]))
+    if case.get("ref_style", False):
+        return lambda series: series.sum()
+    return lambda series: (series ** 2 * (torch.as_tensor(w) if torch.is_tensor(series) else w)).sum()
+
+
+def make_grad_golden(name):
+    case = cases.grad_case(name)
+    shape = case["eps"].shape
+    fn = series_fn(shape, case["dL"], case["npml"], case["steps"], case["sources"], case["probes"])
+    eps0 = torch.as_tensor(case["eps"].copy())
+    out = {}
+    if name.startswith("ref_"):
+        case["ref_style"] = True
+    if case["mode"] == "rev":
+        obj = _scalar_objective(case)
+        x = eps0.clone().requires_grad_(True)
+        L = obj(fn(x))
+        (g,) = torch.autograd.grad(L, x)
+        out["value"] = np.float64(L.item())
+        out["grad_ad"] = g.numpy()
+        ref_L = lambda e: obj(run_reference(case, eps=e)[0])
+        base = ref_L(case["eps"])
+        out["value_ref"] = np.float64(base)
+        if name.startswith("ref_"):
+            cells = list(np.ndindex(shape))
+        else:
+            rng = np.random.default_rng(3)
+            cells = [tuple(int(rng.integers(0, n)) for n in shape) for _ in range(6)]
+        h = 1e-6
+        fd1, fdc = [], []
+        for idx in cells:
+            e = case["eps"].copy(); e[idx] += h
+            up = ref_L(e)
+            e = case["eps"].copy(); e[idx] -= h
+            dn = ref_L(e)
+            fd1.append((up - base) / h)
+            fdc.append((up - dn) / (2 * h))
+        out["fd_cells"] = np.array(cells)
+        out["fd_one_sided"] = np.array(fd1)
+        out["fd_central"] = np.array(fdc)
+    else:
+        # tests/test_gradients_fdtd.py:91-116: objective(c) = sum_t (F_x+F_y+F_z) with eps = c*eps0, c0 = 2
+        c0 = 2.0
+        arr_obj = lambda series_like: series_like
+        def of_c_torch(c):
+            sim_fn = _fields_sum_fn(case)
+            return sim_fn(c * eps0)
+        c = torch.tensor(c0, dtype=torch.float64)
+        val, tan = torch.func.jvp(of_c_torch, (c,), (torch.ones_like(c),))
+        out["value"] = val.numpy()
+        out["jvp_ad"] = tan.numpy()
+        ref_S = lambda cc: _fields_sum_reference(case, cc * case["eps"])
+        h = 1e-6
+        base = ref_S(c0)
+        out["value_ref"] = base
+        out["fd_one_sided"] = (ref_S(c0 + h) - base) / h
+        out["fd_central"] = (ref_S(c0 + h) - ref_S(c0 - h)) / (2 * h)
+    np.savez_compressed(os.path.join(OUT, "grad_%s.npz" % name), **out)
+    print("grad", name, {k: (np.linalg.norm(v) if np.ndim(v) else float(v)) for k, v in out.items() if k != "fd_cells"})
+
+
+def _fields_sum_fn(case):
+    """eps (torch) -> sum_t (Fx+Fy+Fz) as an array, the forward-mode objective of the reference tests."""
+    from .fdtd_torch import TorchFDTD
+    keys = [k for k, _ in case["probes"]]
+    def fn(eps):
+        sim = TorchFDTD(eps, case["dL"], case["npml"])
+        S = 0.0
+        for t in range(case["steps"]):
+            J = {"x": None, "y": None, "z": None}
+            for comp, profile, wave in case["sources"]:
+                J[comp] = torch.as_tensor(profile) * float(wave[t])
+            f = sim.step(Jx=J["x"], Jy=J["y"], Jz=J["z"])
+            S = S + f[keys[0]] + f[keys[1]] + f[keys[2]]
+        return S
+    return fn
+
+
+def _fields_sum_reference(case, eps):
+    ref = ref_loader.load()
+    F = ref.fdtd(eps, case["dL"], case["npml"])
+    keys = [k for k, _ in case["probes"]]
+    S = 0.0
+    for t in range(case["steps"]):
+        J = {"x": None, "y": None, "z": None}
+        for comp, profile, wave in case["sources"]:
+            J[comp] = profile * wave[t]
+        f = F.forward(Jx=J["x"], Jy=J["y"], Jz=J["z"])
+        S = S + f[keys[0]] + f[keys[1]] + f[keys[2]]
+    return S
+
+
+def main(argv):
+    os.makedirs(OUT, exist_ok=True)
+    which = argv[1:] or ["fields", "grads"]
+    if "fields" in which:
+        for name in cases.FIELD_CASES:
+            make_field_golden(name)
+    if "grads" in which:
+        for name in cases.GRAD_CASES:
+            make_grad_golden(name)
+
+
+if __name__ == "__main__":
+    main(sys.argv)
