@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""Benchmark of the FDTD hot path (BASELINE.json: Gcell-updates/s + % HBM roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype f64|f32] [--impl ours|reference]
+
+Workload at N = 1: BASELINE config 2 -- 3-D 256^3 dielectric waveguide splitter, npml 20, Jz sheet
+source, two arm probes.  One bench "step" = one batch of CHUNK (default 1000) FDTD time steps, so the
+default K = 10 is the config's 10 000 steps.  `value` = cells * time-steps / device time with the
+state resident in HBM; `e2e` = the same through the public API with HOST buffers (new eps_r uploaded,
+sources/probes uploaded, probe series downloaded, every step).  N > 1: x-slab decomposition of a
+(256*N) x 256 x 256 grid (weak scaling), NCCL halo exchange (see ceviche_b200/slab.py).
+
+`--impl reference`: the reference's CPU algorithm (numpy port in oracle/, pinned bit-for-bit to the
+reference) timed on the host cores on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DL = 5e-8
+NPML = [20, 20, 20]
+B_ALG_WORDS = 21          # H sweep 12w (D,1/eps,H in; H out) + D sweep 9w (H,D in; D out)
+H_KERNEL_WORDS = 12
+D_KERNEL_WORDS = 9
+
+
+# ----------------------------------------------------------------------------- workload
+def splitter_eps(shape, dtype=np.float64):
+    """Config 2 geometry: background 1.0, core 5.9536; a 10x6 (y x z) guide along x that
+    splits linearly after the midpoint into two arms ending at y = Ny/2 +- 40*(Ny/256)."""
+    Nx, Ny, Nz = shape
+    eps = np.ones(shape, dtype=dtype)
+    core = 5.9536
+    cy, cz = Ny // 2, Nz // 2
+    hy, hz = 5, 3
+    off_max = 40 * Ny // 256
+    for i in range(Nx):
+        if i < Nx // 2:
+            centres = [cy]
+        else:
+            f = min(1.0, (i - Nx // 2) / max(1, (Nx // 2 - Nx // 8)))
+            d = int(round(off_max * f))
+            centres = [cy - d, cy + d]
+        for c in centres:
+            eps[i, c - hy:c + hy, cz - hz:cz + hz] = core
+    return eps
+
+
+def workload(shape, chunk):
+    Nx, Ny, Nz = shape
+    from ceviche_b200.constants import C_0
+    dt = 0.5 * DL / (np.sqrt(3) * C_0)
+    eps = splitter_eps(shape)
+    cy, cz = Ny // 2, Nz // 2
+    prof = np.zeros(shape)
+    prof[30 * Nx // 256, cy - 5:cy + 5, cz - 3:cz + 3] = 1.0
+    t = np.arange(chunk)
+    omega = 2 * np.pi * C_0 / 2e-6
+    wave = 5 * np.exp(-(t - 2000) ** 2 / (2 * 100 ** 2)) * np.cos(omega * dt * t)
+    off = 40 * Ny // 256
+    probes = []
+    for c in (cy - off, cy + off):
+        m = np.zeros(shape)
+        m[226 * Nx // 256, c - 5:c + 5, cz - 3:cz + 3] = 1.0
+        probes.append(("Ez", m))
+    return dict(eps=eps, sources=[("z", prof, wave)], probes=probes)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def cpu_reference(shape, n_steps, warm=1):
+    """The reference's CPU algorithm (oracle port, full 3-D coefficient arrays like fdtd.py:265-316)
+    stepped on the host on the config-2 workload.  Returns (Gcell/s, seconds per time step, sample str)."""
+    from oracle.fdtd_numpy import OracleFDTD
+    wl = workload(shape, max(n_steps + warm, 8))
+    sim = OracleFDTD(wl["eps"], DL, NPML, materialize=True)
+    comp, prof, wave = wl["sources"][0]
+    for t in range(warm):
+        sim.step(Jz=prof * wave[t])
+    t0 = time.perf_counter()
+    for t in range(warm, warm + n_steps):
+        f = sim.step(Jz=prof * wave[t])
+        for key, mask in wl["probes"]:
+            np.sum(f[key] * mask)
+    dt = time.perf_counter() - t0
+    cells = shape[0] * shape[1] * shape[2]
+    return cells * n_steps / dt / 1e9, dt / n_steps, "%dx%dx%d fp64, %d time steps after %d warm-up" % (*shape, n_steps, warm)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    shape = (256, 256, 256)
+    try:
+        from oracle.fdtd_numpy import OracleFDTD
+        wl = workload(shape, 8 + args.steps + args.warmup)
+        sim = OracleFDTD(wl["eps"], DL, NPML, materialize=True)
+    except MemoryError:
+        shape = (128, 128, 128)
+        wl = workload(shape, 8 + args.steps + args.warmup)
+        sim = OracleFDTD(wl["eps"], DL, NPML, materialize=True)
+    comp, prof, wave = wl["sources"][0]
+
+    def one(t):
+        f = sim.step(Jz=prof * wave[t])
+        for key, mask in wl["probes"]:
+            np.sum(f[key] * mask)
+    for t in range(args.warmup):
+        one(t)
+    t0 = time.perf_counter()
+    for t in range(args.warmup, args.warmup + args.steps):
+        one(t)
+    el = time.perf_counter() - t0
+    cells = shape[0] * shape[1] * shape[2]
+    val = cells * args.steps / el / 1e9
+    sample = "one FDTD time step of the %dx%dx%d config-2 grid per bench step (fp64 numpy port of ceviche/fdtd.py, 1 thread)" % shape
+    line = {"impl": "reference", "metric": "Gcell-updates/s", "value": val, "unit": "Gcell/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config 2: 3-D %dx%dx%d waveguide splitter, npml 20" % shape, "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "Gcell/s", "cores": 1, "kind": "port", "sample": sample,
+                             "host_cores": os.cpu_count()},
+            "e2e": {"value": val, "unit": "Gcell/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ceviche_b200
+    from ceviche_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.float64 if args.dtype == "f64" else torch.float32
+    w = 8 if args.dtype == "f64" else 4
+    chunk = args.chunk
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+
+    if world > 1:
+        from ceviche_b200 import slab
+        return slab.bench(args, dist, dev, dtype, hbm_peak, peak_src, ClockSampler, workload)
+
+    shape = tuple(args.grid)
+    cells = shape[0] * shape[1] * shape[2]
+    wl = workload(shape, chunk)
+    F = ceviche_b200.fdtd(wl["eps"], DL, NPML, dtype=dtype, arith=args.arith)
+    srcs, probes = wl["sources"], wl["probes"]
+
+    def sync():
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput -------------------------------------------------
+    for _ in range(args.warmup):
+        F.run(chunk, srcs, probes)
+    sync()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        ev0.record()
+        for _ in range(args.steps):
+            F.run(chunk, srcs, probes)
+        ev1.record()
+        sync()
+    ms = ev0.elapsed_time(ev1)
+    ms_per_step = ms / args.steps
+    value = cells * chunk * args.steps / (ms * 1e-3) / 1e9
+    launches = args.steps * (chunk * 3 + 2)
+
+    # ---- per-kernel timing of the two half-step kernels (events on the launch stream) ----
+    import ctypes as C
+    plan = F._ensure_plan()
+    st = F._state()
+    s = F._stream()
+    reps = 50
+
+    def time_kernel(fn):
+        for _ in range(5):
+            fn()
+        sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        sync()
+        return a.elapsed_time(b) / reps
+
+    h_ms = time_kernel(lambda: _lib.check(plan.lib.cev_fdtd_step_H(plan.handle, C.byref(st), None, 0, shape[0], s)))
+    d_ms = time_kernel(lambda: _lib.check(plan.lib.cev_fdtd_step_D(plan.handle, C.byref(st), None, None, None, None,
+                                                                  0, shape[0], s)))
+    h_gbs = cells * H_KERNEL_WORDS * w / (h_ms * 1e-3) / 1e9
+    d_gbs = cells * D_KERNEL_WORDS * w / (d_ms * 1e-3) / 1e9
+    step_gbs = value * B_ALG_WORDS * w
+    traffic = None
+    prof_json = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.isfile(prof_json):
+        try:
+            traffic = json.load(open(prof_json)).get("%s_%dx%dx%d" % ((args.dtype,) + shape), {}).get("step_H_bytes")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "step_H (H half-step: D, 1/eps, H in; H out = 12 words/cell)",
+                "achieved": h_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": h_gbs / hbm_peak, "traffic": traffic,
+                "peak_source": peak_src, "ms_per_launch": h_ms,
+                "step_D": {"achieved": d_gbs, "frac": d_gbs / hbm_peak, "ms_per_launch": d_ms, "words_per_cell": D_KERNEL_WORDS},
+                "whole_step": {"bytes_per_cell_update": B_ALG_WORDS * w, "achieved": step_gbs, "frac": step_gbs / hbm_peak,
+                               "frac_of_nominal_8TBs": step_gbs / 8000.0}}
+
+    # ---- end to end through the public API with host buffers ---------------------------
+    eps_host = torch.as_tensor(wl["eps"]).to(dtype).pin_memory()
+    wave_host = torch.as_tensor(np.stack([s_[2] for s_ in srcs], 1)).pin_memory()
+    geo = [(c, p) for c, p, _ in srcs]
+    h2d = eps_host.numel() * eps_host.element_size() + wave_host.numel() * 8 + sum(p.nbytes for _, p in geo) + sum(m.nbytes for _, m in probes)
+    d2h = chunk * len(probes) * 8
+
+    def e2e_step():
+        F.eps_r = eps_host.to(dev, non_blocking=True)      # upload + Yee averaging + 1/eps + field reset
+        series = F.run(chunk, geo, probes, waveforms=wave_host.to(dev, non_blocking=True))
+        return series.cpu()
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    sync()
+    n_e2e = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        out = e2e_step()
+    sync()
+    e2e_s = (time.perf_counter() - t0) / n_e2e
+    e2e_val = cells * chunk / e2e_s / 1e9
+
+    # ---- CPU baseline: the reference algorithm on the host cores, bounded sample --------
+    cpu = None
+    if not args.no_cpu:
+        try:
+            v, sec, sample = cpu_reference((256, 256, 256) if cells >= 256 ** 3 else shape, 2)
+        except MemoryError:
+            v, sec, sample = cpu_reference((128, 128, 128), 4)
+        cpu = {"value": v, "unit": "Gcell/s", "cores": 1, "kind": "port", "sample": sample,
+               "host_cores": os.cpu_count(), "s_per_time_step": sec}
+
+    line = {"metric": "Gcell-updates/s", "value": value, "unit": "Gcell/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "config 2: 3-D %dx%dx%d dielectric waveguide splitter, npml 20, Jz sheet source, 2 arm probes" % shape,
+                       "time_steps_per_bench_step": chunk, "arith": "f64" if F.arith_f64 else "f32",
+                       "l2": "state %.0f MB >> 126 MB L2 (inputs larger than L2, no flush needed)" % (cells * w * 9 / 1e6)},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_val, "unit": "Gcell/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": int(launches), "clocks": clk.summary()}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--arith", default=None, choices=[None, "f64", "f32"])
+    ap.add_argument("--chunk", type=int, default=1000, help="FDTD time steps per bench step")
+    ap.add_argument("--grid", type=int, nargs=3, default=[256, 256, 256])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,86 @@
+"""ctypes binding of the C ABI in include/ceviche_b200.h.
+
+There is no CPU fallback: if the CUDA library cannot be loaded (and cannot be built
+because nvcc is absent) importing the compute path raises."""
+import ctypes as C
+import os
+import threading
+
+from . import build as _build
+
+_lock = threading.Lock()
+_lib = None
+
+c_void_p3 = C.c_void_p * 3
+c_double3 = C.c_double * 3
+c_dptr3 = C.POINTER(C.c_double) * 3
+
+
+class cev_state(C.Structure):
+    _fields_ = [(n, c_void_p3) for n in
+                ("H", "D", "inv_eps", "ICE", "IH", "ICH", "ID", "D_xhi", "inv_eps_xhi", "H_xlo")]
+
+
+class cev_points(C.Structure):
+    _fields_ = [("field", C.c_int32), ("n", C.c_int64), ("idx", C.c_void_p), ("cell0", C.c_int64),
+                ("weight", C.c_void_p)]
+
+
+class CevicheB200Error(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    P = C.POINTER
+    lib.cev_last_error.restype = C.c_char_p
+    lib.cev_abi_version.restype = C.c_int
+    sigs = {
+        "cev_fdtd_create": [P(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64,
+                            C.c_double, C.c_double, c_dptr3, c_dptr3],
+        "cev_fdtd_destroy": [C.c_void_p],
+        "cev_fdtd_pml_shapes": [C.c_void_p, P(C.c_int64 * 3 * 12)],
+        "cev_fdtd_step_H": [C.c_void_p, P(cev_state), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p],
+        "cev_fdtd_step_D": [C.c_void_p, P(cev_state), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                            C.c_int64, C.c_int64, C.c_void_p],
+        "cev_fdtd_compute_E": [C.c_void_p, P(cev_state), C.c_void_p, C.c_void_p],
+        "cev_fdtd_set_sources": [C.c_void_p, C.c_int, P(cev_points)],
+        "cev_fdtd_set_probes": [C.c_void_p, C.c_int, P(cev_points), P(C.c_int64)],
+        "cev_fdtd_probe_slots": [C.c_void_p, P(C.c_int32)],
+        "cev_fdtd_run": [C.c_void_p, P(cev_state), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
+    }
+    for name, argtypes in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    return sigs
+
+
+EXPORTS = ("cev_last_error", "cev_abi_version", "cev_fdtd_create", "cev_fdtd_destroy", "cev_fdtd_pml_shapes",
+           "cev_fdtd_step_H", "cev_fdtd_step_D", "cev_fdtd_compute_E", "cev_fdtd_set_sources",
+           "cev_fdtd_set_probes", "cev_fdtd_probe_slots", "cev_fdtd_run")
+
+
+def load():
+    """Load (building first if the in-tree .so is missing or older than its sources)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if _build.is_stale():
+            if _build.find_nvcc() is not None:
+                _build.build_library()
+            elif not os.path.isfile(path):
+                raise CevicheB200Error(
+                    "ceviche_b200: %s is missing and nvcc is not available to build it; "
+                    "there is no CPU fallback (run __graft_entry__.build())" % path)
+        lib = C.CDLL(path)
+        _declare(lib)
+        _lib = lib
+        return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().cev_last_error()
+        raise CevicheB200Error((msg or b"unknown error").decode())

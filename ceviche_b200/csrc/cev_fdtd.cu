@@ -1,0 +1,568 @@
+// ceviche_b200: host side of the C ABI (include/ceviche_b200.h) + kernel launches.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include "../../include/ceviche_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "step_v1.cuh"
+
+namespace {
+
+// ceviche/constants.py:7-9 -- the reference's (non-SI) values; they set dt, sigma and every coefficient.
+constexpr double EPSILON_0 = 8.85418782e-12;
+constexpr double MU_0 = 1.25663706e-6;
+
+thread_local std::string g_err;
+
+int fail(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return -1;
+}
+
+#define CUDA_TRY(expr)                                                                  \
+    do {                                                                                \
+        cudaError_t e_ = (expr);                                                        \
+        if (e_ != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+constexpr int PROBE_CHUNK = 8192;   // points per probe slot (one CTA each)
+
+struct DeviceBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int alloc(size_t n) {
+        release();
+        if (n == 0) return 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e != cudaSuccess) return fail("cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e));
+        bytes = n;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+}  // namespace
+
+struct cev_fdtd {
+    int device = 0, dtype = CEV_F64, arith64 = 1;
+    int rot = 0;                 // internal axis A <-> logical axis (A - rot) mod 3
+    int64_t Nl[3] = {0, 0, 0};   // logical extents
+    int N[3] = {0, 0, 0};        // internal extents
+    double dL = 0, dt = 0, cdt = 0;
+    int nH[3] = {0, 0, 0}, nD[3] = {0, 0, 0};   // internal compact counts
+    DeviceBuf tables;            // u/r (f32 + f64) and maps for 3 axes x {H, D}
+    const void* uH[3][2];        // [axis][0: f32, 1: f64]
+    const void* rH[3][2];
+    const void* uD[3][2];
+    const void* rD[3][2];
+    const int* mapH[3];
+    const int* mapD[3];
+    // sources
+    int nsrc = 0;
+    int64_t n_src_pts = 0;
+    DeviceBuf src_comp, src_id, src_cell, src_weight;
+    // probes
+    int nprobe = 0, n_slots = 0, n_slots_ED = 0;
+    std::vector<int32_t> slot_probe;
+    DeviceBuf pr_field, pr_wbegin, pr_ibegin, pr_cell0, pr_n, pr_idx, pr_weight;
+
+    int to_internal(int logical_axis) const { return (logical_axis + rot) % 3; }
+    int to_logical(int internal_axis) const { return (internal_axis - rot + 3) % 3; }
+};
+
+namespace {
+
+using namespace cev;
+
+template <typename T, typename AT>
+int fill_args(const cev_fdtd* p, const cev_state* st, StepArgs<T, AT>& a) {
+    memset(&a, 0, sizeof a);
+    a.Nx = p->N[0];
+    a.Ny = p->N[1];
+    a.Nz = p->N[2];
+    const int64_t plane = (int64_t)a.Ny * a.Nz;
+    constexpr int w = sizeof(AT) == 8 ? 1 : 0;
+    for (int A = 0; A < 3; ++A) {
+        const int L = p->to_logical(A);
+        a.Hin[A] = (const T*)st->H[L];
+        a.Hout[A] = (T*)st->H[L];
+        a.Din[A] = (const T*)st->D[L];
+        a.Dout[A] = (T*)st->D[L];
+        a.mE[A] = (const T*)st->inv_eps[L];
+        if (!a.Hin[A] || !a.Din[A] || !a.mE[A]) return fail("cev_state: H, D and inv_eps must be non-NULL");
+        a.ICE[A] = (T*)st->ICE[L];
+        a.IH[A] = (T*)st->IH[L];
+        a.ICH[A] = (T*)st->ICH[L];
+        a.ID[A] = (T*)st->ID[L];
+        a.Dhi[A] = st->D_xhi[L] ? (const T*)st->D_xhi[L] : a.Din[A];
+        a.mEhi[A] = st->inv_eps_xhi[L] ? (const T*)st->inv_eps_xhi[L] : a.mE[A];
+        a.Hlo[A] = st->H_xlo[L] ? (const T*)st->H_xlo[L] : a.Hin[A] + (int64_t)(a.Nx - 1) * plane;
+        a.mapH[A] = p->mapH[A];
+        a.mapD[A] = p->mapD[A];
+        a.nH[A] = p->nH[A];
+        a.nD[A] = p->nD[A];
+        a.uH[A] = (const AT*)p->uH[A][w];
+        a.rH[A] = (const AT*)p->rH[A][w];
+        a.uD[A] = (const AT*)p->uD[A][w];
+        a.rD[A] = (const AT*)p->rD[A][w];
+        a.Jscale[A] = AT(1);
+    }
+    if (p->rot != 0 && (st->D_xhi[1] || st->D_xhi[2] || st->H_xlo[1] || st->H_xlo[2]))
+        return fail("x-halo planes need Nz > 1 (no slab decomposition of a rotated 2-D/1-D grid)");
+    // PML integral arrays must exist wherever the kernels will touch them
+    for (int A = 0; A < 3; ++A) {
+        const int B = (A + 1) % 3, C = (A + 2) % 3;
+        if (p->nH[A] > 0 && !a.ICE[A]) return fail("cev_state: ICE missing for a PML axis");
+        if (p->nD[A] > 0 && !a.ICH[A]) return fail("cev_state: ICH missing for a PML axis");
+        if (p->nH[B] > 0 && p->nH[C] > 0 && !a.IH[A]) return fail("cev_state: IH missing for a PML corner");
+        if (p->nD[B] > 0 && p->nD[C] > 0 && !a.ID[A]) return fail("cev_state: ID missing for a PML corner");
+    }
+    a.cdt = (AT)p->cdt;
+    a.inv_dL = (AT)(1.0 / p->dL);
+    a.pr.n_slots = p->n_slots;
+    a.pr.slot_field = (const int32_t*)p->pr_field.p;
+    a.pr.slot_wbegin = (const int64_t*)p->pr_wbegin.p;
+    a.pr.slot_ibegin = (const int64_t*)p->pr_ibegin.p;
+    a.pr.slot_cell0 = (const int64_t*)p->pr_cell0.p;
+    a.pr.slot_n = (const int64_t*)p->pr_n.p;
+    a.pr.idx = (const int64_t*)p->pr_idx.p;
+    a.pr.weight = (const double*)p->pr_weight.p;
+    a.t_probe = -1;
+    return 0;
+}
+
+template <typename T, typename AT>
+void set_tiles_v1(StepArgs<T, AT>& a, int64_t x0, int64_t x1) {
+    a.x0 = (int)x0;
+    a.x1 = (int)x1;
+    a.ntz = (a.Nz + V1_TZ - 1) / V1_TZ;
+    a.nty = (a.Ny + V1_TY - 1) / V1_TY;
+    a.n_tiles = a.ntz * a.nty * (int)(x1 - x0);
+}
+
+// which: 0 = E/D-family slots, 1 = H-family slots
+template <typename T, typename AT>
+int attach_probes(const cev_fdtd* p, StepArgs<T, AT>& a, int which, int64_t t, double* partials) {
+    if (t < 0 || !partials || p->n_slots == 0) return 0;
+    a.aux_slot0 = which == 0 ? 0 : p->n_slots_ED;
+    a.t_probe = t;
+    a.partials = partials;
+    return which == 0 ? p->n_slots_ED : p->n_slots - p->n_slots_ED;
+}
+
+template <typename T, typename AT>
+int launch_H(cev_fdtd* p, const cev_state* st, void* const H_out[3], int64_t x0, int64_t x1,
+             int64_t probe_t, double* partials, cudaStream_t s) {
+    StepArgs<T, AT> a;
+    if (fill_args(p, st, a)) return -1;
+    if (H_out)
+        for (int A = 0; A < 3; ++A) {
+            a.Hout[A] = (T*)H_out[p->to_logical(A)];
+            if (!a.Hout[A]) return fail("H_out entries must be non-NULL");
+        }
+    set_tiles_v1(a, x0, x1);
+    const int aux = attach_probes(p, a, 0, probe_t, partials);
+    if (a.n_tiles + aux == 0) return 0;
+    k_step_H_v1<T, AT><<<a.n_tiles + aux, dim3(V1_TZ, V1_TY), 0, s>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, typename AT>
+int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const E_out[3], const void* const J[3],
+             const double J_scale[3], const double* const J_wave[3], int64_t x0, int64_t x1, int64_t probe_t,
+             double* partials, cudaStream_t s) {
+    StepArgs<T, AT> a;
+    if (fill_args(p, st, a)) return -1;
+    for (int A = 0; A < 3; ++A) {
+        const int L = p->to_logical(A);
+        if (D_out) {
+            a.Dout[A] = (T*)D_out[L];
+            if (!a.Dout[A]) return fail("D_out entries must be non-NULL");
+        }
+        if (E_out) a.Eout[A] = (T*)E_out[L];
+        if (J) a.J[A] = (const T*)J[L];
+        if (J_scale) a.Jscale[A] = (AT)J_scale[L];
+        if (J_wave) a.Jwave[A] = J_wave[L];
+    }
+    set_tiles_v1(a, x0, x1);
+    const int aux = attach_probes(p, a, 1, probe_t, partials);
+    if (a.n_tiles + aux == 0) return 0;
+    k_step_D_v1<T, AT><<<a.n_tiles + aux, dim3(V1_TZ, V1_TY), 0, s>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, typename AT>
+int launch_inject(cev_fdtd* p, const cev_state* st, const double* wave_row, cudaStream_t s) {
+    if (p->n_src_pts == 0) return 0;
+    SourceTable t;
+    t.n = p->n_src_pts;
+    t.comp = (const int32_t*)p->src_comp.p;
+    t.src = (const int32_t*)p->src_id.p;
+    t.cell = (const int64_t*)p->src_cell.p;
+    t.weight = (const double*)p->src_weight.p;
+    T* D[3];
+    for (int A = 0; A < 3; ++A) D[A] = (T*)st->D[p->to_logical(A)];
+    const int bs = 128;
+    k_inject<T, AT><<<(unsigned)((t.n + bs - 1) / bs), bs, 0, s>>>(t, D[0], D[1], D[2], wave_row);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, typename AT>
+int launch_probe_only(cev_fdtd* p, const cev_state* st, int which, int64_t t, double* partials, cudaStream_t s) {
+    StepArgs<T, AT> a;
+    if (fill_args(p, st, a)) return -1;
+    const int aux = attach_probes(p, a, which, t, partials);
+    if (aux == 0) return 0;
+    k_probe_only<T, AT><<<aux, dim3(V1_TZ, V1_TY), 0, s>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, typename AT>
+int launch_compute_E(cev_fdtd* p, const cev_state* st, void* const E_out[3], cudaStream_t s) {
+    const int64_t n = p->Nl[0] * p->Nl[1] * p->Nl[2];
+    if (n == 0) return 0;
+    for (int c = 0; c < 3; ++c) {
+        if (!E_out[c]) continue;
+        const int bs = 256;
+        const int64_t want = (n + bs - 1) / bs;
+        const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+        k_compute_E<T, AT><<<grid, bs, 0, s>>>((const T*)st->inv_eps[c], (const T*)st->D[c], (T*)E_out[c], n);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
+template <typename T, typename AT>
+int run_loop(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* waveform, double* partials,
+             cudaStream_t s) {
+    const int64_t Nx = p->N[0];
+    for (int64_t n = 0; n < nsteps; ++n) {
+        // E/D probes of step n-1 ride on the H launch of step n (D is read-only there);
+        // H probes of step n ride on its D launch (H is read-only there).
+        if (launch_H<T, AT>(p, st, nullptr, 0, Nx, n - 1, partials, s)) return -1;
+        if (launch_D<T, AT>(p, st, nullptr, nullptr, nullptr, nullptr, nullptr, 0, Nx, n, partials, s)) return -1;
+        if (waveform && launch_inject<T, AT>(p, st, waveform + n * p->nsrc, s)) return -1;
+    }
+    if (nsteps > 0 && launch_probe_only<T, AT>(p, st, 0, nsteps - 1, partials, s)) return -1;
+    return 0;
+}
+
+#define DISPATCH(plan, fn, ...)                                                       \
+    ((plan)->dtype == CEV_F64 ? fn<double, double>(__VA_ARGS__)                       \
+                              : ((plan)->arith64 ? fn<float, double>(__VA_ARGS__)     \
+                                                 : fn<float, float>(__VA_ARGS__)))
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int check_range(const cev_fdtd* p, int64_t x0, int64_t x1) {
+    // ranges are over the LOGICAL x axis = internal axis `rot`; only unrotated plans may sub-range
+    const int64_t nx = p->Nl[0];
+    if (x0 < 0 || x1 > nx || x0 > x1) return fail("x-range [%lld,%lld) outside [0,%lld)", (long long)x0, (long long)x1, (long long)nx);
+    if (p->rot != 0 && !(x0 == 0 && x1 == nx)) return fail("partial x-ranges need Nz > 1");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cev_last_error(void) { return g_err.c_str(); }
+int cev_abi_version(void) { return CEV_ABI_VERSION; }
+
+int cev_fdtd_create(cev_fdtd** out, int device, int dtype, int arith_f64, int64_t nx, int64_t Ny, int64_t Nz, double dL,
+                    double dt, const double* sH[3], const double* sD[3]) {
+    if (!out) return fail("plan out-pointer is NULL");
+    *out = nullptr;
+    if (dtype != CEV_F32 && dtype != CEV_F64) return fail("dtype must be 0 (fp32) or 1 (fp64)");
+    if (nx < 1 || Ny < 1 || Nz < 1) return fail("grid extents must be >= 1");
+    if (nx * Ny * Nz >= (int64_t)1 << 31) return fail("grid too large for 32-bit cell indexing inside a slab");
+    if (!(dL > 0) || !(dt > 0)) return fail("dL and dt must be positive");
+    if (!sH || !sD) return fail("sigma profiles are NULL");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail("device %d out of range (%d visible)", device, ndev);
+    DeviceGuard guard(device);
+
+    cev_fdtd* p = new cev_fdtd();
+    p->device = device;
+    p->dtype = dtype;
+    p->arith64 = (dtype == CEV_F64) ? 1 : (arith_f64 ? 1 : 0);
+    p->Nl[0] = nx;
+    p->Nl[1] = Ny;
+    p->Nl[2] = Nz;
+    p->dL = dL;
+    p->dt = dt;
+    p->cdt = (1.0 / std::sqrt(EPSILON_0 * MU_0)) * dt;
+    // make the last internal axis the contiguous one with extent > 1 (cyclic relabelling keeps the curl)
+    p->rot = (Nz > 1) ? 0 : (Ny > 1 ? 1 : (nx > 1 ? 2 : 0));
+    for (int A = 0; A < 3; ++A) p->N[A] = (int)p->Nl[p->to_logical(A)];
+
+    // tables: per internal axis, for H and D sampling: u (f32,f64), r (f32,f64), map (int)
+    size_t total = 0;
+    for (int A = 0; A < 3; ++A) total += (size_t)p->N[A] * 2 * (4 + 8 + 4 + 8 + 4) + 2 * 64;   // + alignment slack
+    std::vector<unsigned char> host(total);
+    if (p->tables.alloc(total)) {
+        delete p;
+        return -1;
+    }
+    size_t off = 0;
+    auto put = [&](const void* src, size_t bytes) -> const void* {
+        memcpy(host.data() + off, src, bytes);
+        const void* dev = (const unsigned char*)p->tables.p + off;
+        off += bytes;
+        return dev;
+    };
+    for (int A = 0; A < 3; ++A) {
+        const int L = p->to_logical(A);
+        const int n = p->N[A];
+        for (int kind = 0; kind < 2; ++kind) {
+            const double* sig = kind == 0 ? sH[L] : sD[L];
+            if (!sig) {
+                delete p;
+                return fail("sigma profile for axis %d is NULL", L);
+            }
+            std::vector<double> u(n), r(n);
+            std::vector<float> uf(n), rf(n);
+            std::vector<int> map(n);
+            int cnt = 0;
+            for (int q = 0; q < n; ++q) {
+                if (!(sig[q] >= 0) || !std::isfinite(sig[q])) {
+                    delete p;
+                    return fail("sigma profile must be finite and >= 0");
+                }
+                u[q] = sig[q] * dt / (2 * EPSILON_0);
+                r[q] = 1.0 / (1.0 + u[q]);
+                uf[q] = (float)u[q];
+                rf[q] = (float)r[q];
+                map[q] = (sig[q] != 0.0) ? cnt++ : -1;
+            }
+            const void* duf = put(uf.data(), n * 4);
+            // keep 8-byte alignment for the doubles
+            if (off % 8) off += 8 - off % 8;
+            const void* dud = put(u.data(), n * 8);
+            const void* drf = put(rf.data(), n * 4);
+            if (off % 8) off += 8 - off % 8;
+            const void* drd = put(r.data(), n * 8);
+            const void* dmap = put(map.data(), n * 4);
+            if (off % 8) off += 8 - off % 8;
+            if (kind == 0) {
+                p->uH[A][0] = duf; p->uH[A][1] = dud; p->rH[A][0] = drf; p->rH[A][1] = drd;
+                p->mapH[A] = (const int*)dmap; p->nH[A] = cnt;
+            } else {
+                p->uD[A][0] = duf; p->uD[A][1] = dud; p->rD[A][0] = drf; p->rD[A][1] = drd;
+                p->mapD[A] = (const int*)dmap; p->nD[A] = cnt;
+            }
+        }
+    }
+    if (off > total) {
+        delete p;
+        return fail("internal: table overflow");
+    }
+    cudaError_t e = cudaMemcpy(p->tables.p, host.data(), off, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        p->tables.release();
+        delete p;
+        return fail("table upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return 0;
+}
+
+int cev_fdtd_destroy(cev_fdtd* p) {
+    if (!p) return 0;
+    DeviceGuard guard(p->device);
+    p->tables.release();
+    p->src_comp.release(); p->src_id.release(); p->src_cell.release(); p->src_weight.release();
+    p->pr_field.release(); p->pr_wbegin.release(); p->pr_ibegin.release(); p->pr_cell0.release();
+    p->pr_n.release(); p->pr_idx.release(); p->pr_weight.release();
+    delete p;
+    return 0;
+}
+
+int cev_fdtd_pml_shapes(const cev_fdtd* p, int64_t shapes[12][3]) {
+    if (!p || !shapes) return fail("NULL argument");
+    for (int fam = 0; fam < 4; ++fam) {
+        const bool isH = fam < 2;
+        const bool self = (fam == 1 || fam == 3);   // IH / ID: compact on the two OTHER axes
+        for (int c = 0; c < 3; ++c) {
+            for (int ax = 0; ax < 3; ++ax) {
+                const int cnt = isH ? p->nH[p->to_internal(ax)] : p->nD[p->to_internal(ax)];
+                const bool compact = self ? (ax != c) : (ax == c);
+                shapes[fam * 3 + c][ax] = compact ? cnt : p->Nl[ax];
+            }
+        }
+    }
+    return 0;
+}
+
+int cev_fdtd_step_H(cev_fdtd* p, const cev_state* st, void* const H_out[3], int64_t x0, int64_t x1, void* stream) {
+    if (!p || !st) return fail("NULL argument");
+    if (check_range(p, x0, x1)) return -1;
+    DeviceGuard guard(p->device);
+    const int64_t a0 = p->rot ? 0 : x0, a1 = p->rot ? p->N[0] : x1;
+    return DISPATCH(p, launch_H, p, st, H_out, a0, a1, (int64_t)-1, (double*)nullptr, (cudaStream_t)stream);
+}
+
+int cev_fdtd_step_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const E_out[3], const void* const J[3],
+                    const double J_scale[3], int64_t x0, int64_t x1, void* stream) {
+    if (!p || !st) return fail("NULL argument");
+    if (check_range(p, x0, x1)) return -1;
+    DeviceGuard guard(p->device);
+    const int64_t a0 = p->rot ? 0 : x0, a1 = p->rot ? p->N[0] : x1;
+    return DISPATCH(p, launch_D, p, st, D_out, E_out, J, J_scale, (const double* const*)nullptr, a0, a1, (int64_t)-1,
+                    (double*)nullptr, (cudaStream_t)stream);
+}
+
+int cev_fdtd_compute_E(cev_fdtd* p, const cev_state* st, void* const E_out[3], void* stream) {
+    if (!p || !st || !E_out) return fail("NULL argument");
+    DeviceGuard guard(p->device);
+    return DISPATCH(p, launch_compute_E, p, st, E_out, (cudaStream_t)stream);
+}
+
+int cev_fdtd_set_sources(cev_fdtd* p, int nsrc, const cev_points* src) {
+    if (!p || nsrc < 0 || (nsrc > 0 && !src)) return fail("bad source arguments");
+    DeviceGuard guard(p->device);
+    const int64_t ncell = p->Nl[0] * p->Nl[1] * p->Nl[2];
+    int64_t total = 0;
+    for (int s = 0; s < nsrc; ++s) {
+        if (src[s].field < CEV_FIELD_D || src[s].field >= CEV_FIELD_D + 3) return fail("source %d: field must be a D component (3..5)", s);
+        if (src[s].n < 0 || (src[s].n > 0 && (!src[s].idx || !src[s].weight))) return fail("source %d: needs idx and weight arrays", s);
+        if (src[s].n > ncell) return fail("source %d: more points than cells", s);
+        total += src[s].n;
+    }
+    p->nsrc = nsrc;
+    p->n_src_pts = total;
+    if (p->src_comp.alloc(total * 4) || p->src_id.alloc(total * 4) || p->src_cell.alloc(total * 8) || p->src_weight.alloc(total * 8)) return -1;
+    std::vector<int32_t> comp(total), id(total);
+    int64_t off = 0;
+    for (int s = 0; s < nsrc; ++s) {
+        for (int64_t q = 0; q < src[s].n; ++q) {
+            comp[off + q] = p->to_internal(src[s].field - CEV_FIELD_D);
+            id[off + q] = s;
+        }
+        if (src[s].n) {
+            CUDA_TRY(cudaMemcpy((int64_t*)p->src_cell.p + off, src[s].idx, src[s].n * 8, cudaMemcpyDeviceToDevice));
+            CUDA_TRY(cudaMemcpy((double*)p->src_weight.p + off, src[s].weight, src[s].n * 8, cudaMemcpyDeviceToDevice));
+        }
+        off += src[s].n;
+    }
+    if (total) {
+        CUDA_TRY(cudaMemcpy(p->src_comp.p, comp.data(), total * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(p->src_id.p, id.data(), total * 4, cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+int cev_fdtd_set_probes(cev_fdtd* p, int nprobe, const cev_points* probe, int64_t* n_slots_out) {
+    if (!p || nprobe < 0 || (nprobe > 0 && !probe)) return fail("bad probe arguments");
+    DeviceGuard guard(p->device);
+    const int64_t ncell = p->Nl[0] * p->Nl[1] * p->Nl[2];
+    std::vector<int32_t> field, owner;
+    std::vector<int64_t> wbegin, ibegin, cell0, cnt;
+    int64_t wtotal = 0, itotal = 0;
+    std::vector<int64_t> woff(nprobe), ioff(nprobe);
+    for (int q = 0; q < nprobe; ++q) {
+        const cev_points& P = probe[q];
+        if (P.field < 0 || P.field > 8) return fail("probe %d: field code must be 0..8", q);
+        if (P.n < 0 || (P.n > 0 && !P.weight)) return fail("probe %d: needs a weight array", q);
+        if (!P.idx && (P.cell0 < 0 || P.cell0 + P.n > ncell)) return fail("probe %d: dense range outside the grid", q);
+        woff[q] = wtotal;
+        ioff[q] = P.idx ? itotal : -1;
+        wtotal += P.n;
+        if (P.idx) itotal += P.n;
+    }
+    // E/D-family slots first, then H-family: each family is sampled by a different launch
+    int nED = 0;
+    for (int fam = 0; fam < 2; ++fam) {
+        for (int q = 0; q < nprobe; ++q) {
+            const cev_points& P = probe[q];
+            const bool isH = P.field >= CEV_FIELD_H;
+            if ((fam == 0) == isH) continue;
+            const int fcode = (P.field / 3) * 3 + p->to_internal(P.field % 3);
+            int64_t done = 0;
+            do {   // at least one slot per probe so that every series column is written
+                const int64_t m = (P.n - done < PROBE_CHUNK) ? (P.n - done) : PROBE_CHUNK;
+                field.push_back(fcode);
+                owner.push_back(q);
+                wbegin.push_back(woff[q] + done);
+                ibegin.push_back(P.idx ? ioff[q] + done : -1);
+                cell0.push_back(P.idx ? 0 : P.cell0 + done);
+                cnt.push_back(m);
+                done += m;
+            } while (done < P.n);
+        }
+        if (fam == 0) nED = (int)field.size();
+    }
+    const int ns = (int)field.size();
+    if (p->pr_field.alloc(ns * 4) || p->pr_wbegin.alloc(ns * 8) || p->pr_ibegin.alloc(ns * 8) || p->pr_cell0.alloc(ns * 8) ||
+        p->pr_n.alloc(ns * 8) || p->pr_idx.alloc(itotal * 8) || p->pr_weight.alloc(wtotal * 8))
+        return -1;
+    if (ns) {
+        CUDA_TRY(cudaMemcpy(p->pr_field.p, field.data(), ns * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(p->pr_wbegin.p, wbegin.data(), ns * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(p->pr_ibegin.p, ibegin.data(), ns * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(p->pr_cell0.p, cell0.data(), ns * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(p->pr_n.p, cnt.data(), ns * 8, cudaMemcpyHostToDevice));
+    }
+    for (int q = 0; q < nprobe; ++q) {
+        const cev_points& P = probe[q];
+        if (P.n == 0) continue;
+        CUDA_TRY(cudaMemcpy((double*)p->pr_weight.p + woff[q], P.weight, P.n * 8, cudaMemcpyDeviceToDevice));
+        if (P.idx) CUDA_TRY(cudaMemcpy((int64_t*)p->pr_idx.p + ioff[q], P.idx, P.n * 8, cudaMemcpyDeviceToDevice));
+    }
+    p->nprobe = nprobe;
+    p->n_slots = ns;
+    p->n_slots_ED = nED;
+    p->slot_probe = owner;
+    if (n_slots_out) *n_slots_out = ns;
+    return 0;
+}
+
+int cev_fdtd_probe_slots(const cev_fdtd* p, int32_t* slot_probe) {
+    if (!p || !slot_probe) return fail("NULL argument");
+    for (int s = 0; s < p->n_slots; ++s) slot_probe[s] = p->slot_probe[s];
+    return 0;
+}
+
+int cev_fdtd_run(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* waveform, double* partials, void* stream) {
+    if (!p || !st) return fail("NULL argument");
+    if (nsteps < 0) return fail("nsteps must be >= 0");
+    if (p->n_src_pts > 0 && !waveform) return fail("plan has sources but waveform is NULL");
+    if (p->n_slots > 0 && !partials) return fail("plan has probes but partials is NULL");
+    if (st->D_xhi[1] || st->D_xhi[2] || st->H_xlo[1] || st->H_xlo[2]) return fail("cev_fdtd_run steps a whole (periodic) grid; slabs are driven per half-step");
+    DeviceGuard guard(p->device);
+    return DISPATCH(p, run_loop, p, st, nsteps, p->n_src_pts > 0 ? waveform : nullptr, partials, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,121 @@
+// Shared device-side definitions for the FDTD kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cev {
+
+// Sampling of probe point sets: one CTA per "slot" (a chunk of one probe's points) does a
+// fixed-order reduction and writes ONE partial sum -> deterministic series, no atomics.
+struct ProbeTable {
+    int            n_slots;
+    const int32_t* slot_field;   // CEV_FIELD_* + component
+    const int64_t* slot_wbegin;  // offset into weight[]
+    const int64_t* slot_ibegin;  // offset into idx[], <0 => dense
+    const int64_t* slot_cell0;   // dense: first cell
+    const int64_t* slot_n;       // points in the slot
+    const int64_t* idx;
+    const double*  weight;
+};
+
+// Everything a half-step kernel needs.  Axes/components are in the plan's INTERNAL order
+// (a cyclic relabelling of x,y,z chosen so that the last internal axis is the contiguous
+// one with extent > 1; see cev_fdtd.cu).  T = storage type, AT = arithmetic type.
+template <typename T, typename AT>
+struct StepArgs {
+    int Nx, Ny, Nz;
+    int x0, x1;
+    const T* Hin[3];
+    T*       Hout[3];
+    const T* Din[3];
+    T*       Dout[3];
+    const T* mE[3];
+    T*       Eout[3];
+    const T* Dhi[3];    // plane (Ny*Nz) standing for i = Nx   (wrap: plane 0; slab: halo buffer)
+    const T* mEhi[3];
+    const T* Hlo[3];    // plane standing for i = -1            (wrap: plane Nx-1; slab: halo buffer)
+    T* ICE[3];
+    T* IH[3];
+    T* ICH[3];
+    T* ID[3];
+    const int* mapH[3];
+    const int* mapD[3];
+    int nH[3], nD[3];
+    const AT* uH[3];    // u = sigma*dt/(2 eps0) per axis (H sampling / D sampling)
+    const AT* rH[3];    // r = 1/(1+u)
+    const AT* uD[3];
+    const AT* rD[3];
+    AT cdt;             // C_0 * dt
+    AT inv_dL;
+    const T* J[3];      // dense source per component (nullable)
+    AT       Jscale[3];
+    const double* Jwave[3];   // nullable device scalar overriding Jscale (waveform entry)
+    // tiling + auxiliary probe CTAs appended to the grid
+    int n_tiles, ntz, nty;
+    ProbeTable pr;
+    int        aux_slot0;     // first slot handled by the aux CTAs of this launch
+    int64_t    t_probe;       // row of partials[] they write
+    double*    partials;
+};
+
+template <typename T, typename AT>
+__device__ __forceinline__ AT probe_value(const StepArgs<T, AT>& a, int field, int64_t cell) {
+    const int c = field % 3;
+    if (field < 3) return (AT)a.mE[c][cell] * (AT)a.Din[c][cell];
+    if (field < 6) return (AT)a.Din[c][cell];
+    return (AT)a.Hin[c][cell];
+}
+
+// One CTA reduces one slot.  blockDim.x*blockDim.y threads, power of two <= 1024.
+template <typename T, typename AT>
+__device__ void probe_block(const StepArgs<T, AT>& a, int slot) {
+    __shared__ double red[1024];
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int nth = blockDim.x * blockDim.y;
+    const int field = a.pr.slot_field[slot];
+    const int64_t n = a.pr.slot_n[slot];
+    const int64_t wb = a.pr.slot_wbegin[slot];
+    const int64_t ib = a.pr.slot_ibegin[slot];
+    const int64_t c0 = a.pr.slot_cell0[slot];
+    double acc = 0.0;
+    for (int64_t q = tid; q < n; q += nth) {
+        const int64_t cell = (ib < 0) ? (c0 + q) : a.pr.idx[ib + q];
+        acc += (double)probe_value<T, AT>(a, field, cell) * a.pr.weight[wb + q];
+    }
+    red[tid] = acc;
+    __syncthreads();
+    for (int s = nth >> 1; s > 0; s >>= 1) {
+        if (tid < s) red[tid] += red[tid + s];
+        __syncthreads();
+    }
+    if (tid == 0) a.partials[a.t_probe * a.pr.n_slots + slot] = red[0];
+}
+
+// One field component of one half-step (fdtd.py:85-97 for H, :110-122 for D):
+//   I_curl += curl ; I_self += old ; new = m1*old + m2*curl + m3*I_curl + m4*I_self
+// with the coefficients of fdtd.py:272-311 rewritten division-free from the per-axis tables
+//   m0*dt = (1+ua)(1+ub),  1/m0 = dt*ra*rb
+//   m1 = (1-ua-ub-ua*ub) ra rb,  m2 = s*C0*dt ra rb,  m3 = s*C0*dt*2uc ra rb,  m4 = -4 ua ub ra rb
+// (s = -1 for H, +1 for D; (ua,ub) = the two other axes, uc = the component's own axis).
+// The integral arrays exist only where their coefficient is non-zero (index < 0: skip).
+template <typename T, typename AT>
+__device__ __forceinline__ AT update_component(AT old, AT curl, AT ua, AT ra, AT ub, AT rb, AT uc, AT scdt,
+                                               T* Icurl, int64_t icurl, T* Iself, int64_t iself) {
+    const AT rr = ra * rb;
+    const AT m1 = (AT(1) - ua - ub - ua * ub) * rr;
+    const AT m2 = scdt * rr;
+    AT v = m1 * old + m2 * curl;
+    if (icurl >= 0) {
+        const AT I = (AT)Icurl[icurl] + curl;
+        Icurl[icurl] = (T)I;
+        v += (scdt * (uc + uc) * rr) * I;
+    }
+    if (iself >= 0) {
+        const AT I = (AT)Iself[iself] + old;
+        Iself[iself] = (T)I;
+        v += (AT(-4) * ua * ub * rr) * I;
+    }
+    return v;
+}
+
+}  // namespace cev

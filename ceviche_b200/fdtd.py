@@ -1,0 +1,397 @@
+"""The `fdtd` simulator object: a drop-in for ceviche.fdtd (reference ceviche/fdtd.py:10-316)
+whose arrays are torch CUDA tensors and whose time step runs in hand-written sm_100a kernels
+behind the C ABI of include/ceviche_b200.h.
+
+Same constructor, properties (with the reference's side effects), `forward(Jx, Jy, Jz)` returning
+the nine-field dict, `initialize_fields()`, and attributes (`dt`, `t_index`, `Nx/Ny/Nz`,
+`grid_shape`, `N`, `eps_arr`, `eps_xx/yy/zz`, `Hx..`, `Dx..`, `Ex..`).  Additions are keyword-only
+(`dtype`, `device`, `arith`) plus the fused `run()` entry (the caller loop of
+ceviche/utils.py:316-332 executed on the device with in-kernel sources and probes).
+
+Host-side set-up (dt, the six 1-D sigma profiles) is fp64 numpy following the reference
+formulas; the 30 full-grid coefficient arrays of fdtd.py:265-311 are never built.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .constants import C_0, EPSILON_0
+
+FIELD_KEYS = ("Ex", "Ey", "Ez", "Dx", "Dy", "Dz", "Hx", "Hy", "Hz")
+_FIELD_CODE = {k: i for i, k in enumerate(FIELD_KEYS)}
+_COMP = {"x": 0, "y": 1, "z": 2, "Jx": 0, "Jy": 1, "Jz": 2, 0: 0, 1: 1, 2: 2}
+_DTYPES = {torch.float64: 1, torch.float32: 0}
+_PML_FAMILIES = ("ICE", "IH", "ICH", "ID")
+
+
+def reshape_to_ND(arr, N):
+    """ceviche/utils.py:206-214: trailing singleton axes up to N dims, ValueError beyond."""
+    ND = len(arr.shape)
+    if ND > N:
+        raise ValueError("array is larger than {} dimensional, given shape {}".format(N, tuple(arr.shape)))
+    return arr.reshape(tuple(arr.shape) + (N - ND) * (1,))
+
+
+def sigma_profiles(shape, npml, dt):
+    """The six 1-D PML profiles equivalent to fdtd._compute_sigmas (fdtd.py:224-263).
+
+    Each reference sigma array varies along its own axis only; on the doubled grid of axis a
+    (2*N_a samples) the cubic grading sits at indices 2p-n+1 (low side) and 2N_a-2p+n (high
+    side) for n = 0..2p-1; H samples the odd entries, D the even ones."""
+    sH, sD = [], []
+    for n_cells, p in zip(shape, npml):
+        p = int(p)
+        s2 = np.zeros(2 * n_cells)
+        for n in range(2 * p):
+            val = (0.5 * EPSILON_0 / dt) * (n / 2 / p) ** 3
+            s2[2 * p - n + 1] = val
+            s2[2 * n_cells - 2 * p + n] = val
+        sH.append(np.ascontiguousarray(s2[1::2]))
+        sD.append(np.ascontiguousarray(s2[0::2]))
+    return sH, sD
+
+
+def _ptr(t):
+    return None if t is None or t.numel() == 0 else t.data_ptr()
+
+
+def _ptr3(ts):
+    return _lib.c_void_p3(*[_ptr(t) for t in ts])
+
+
+class _Plan:
+    """Owner of one C-side plan handle."""
+
+    def __init__(self, device, dtype, arith_f64, shape, dL, dt, sH, sD):
+        self.lib = _lib.load()
+        self.handle = C.c_void_p()
+        self._keep = [np.ascontiguousarray(a, dtype=np.float64) for a in list(sH) + list(sD)]
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        cH = _lib.c_dptr3(*[dp(a) for a in self._keep[:3]])
+        cD = _lib.c_dptr3(*[dp(a) for a in self._keep[3:]])
+        _lib.check(self.lib.cev_fdtd_create(C.byref(self.handle), device.index, _DTYPES[dtype], int(arith_f64),
+                                            shape[0], shape[1], shape[2], float(dL), float(dt), cH, cD))
+        shapes = (C.c_int64 * 3 * 12)()
+        _lib.check(self.lib.cev_fdtd_pml_shapes(self.handle, C.byref(shapes)))
+        self.pml_shapes = [tuple(int(v) for v in shapes[q]) for q in range(12)]
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.cev_fdtd_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass
+
+
+class fdtd:
+
+    def __init__(self, eps_r, dL, npml, *, dtype=torch.float64, device=None, arith=None):
+        """ Makes an FDTD object (signature of ceviche/fdtd.py:12)
+                eps_r: relative permittivity, 1-/2-/3-D numpy array or torch tensor
+                dL: the grid size (scalar, as the reference: fdtd.py:219)
+                npml: the number of PML cells on each axis (3 ints, 0 = periodic axis)
+            keyword-only: dtype (torch.float64 | torch.float32 storage), device, arith
+            ('f64' | 'f32': arithmetic of the fp32 path; fp64 storage always computes in fp64).
+        """
+        if dtype not in _DTYPES:
+            raise ValueError("dtype must be torch.float64 or torch.float32")
+        if not torch.cuda.is_available():
+            raise _lib.CevicheB200Error("ceviche_b200 needs a CUDA device: there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.CevicheB200Error("ceviche_b200 runs on CUDA devices only")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.dtype = dtype
+        self.arith_f64 = True if dtype == torch.float64 else (arith in (None, "f64", torch.float64))
+        self._plan = None
+
+        eps_r = self._as_eps(eps_r, pad=True)
+        self.Nx, self.Ny, self.Nz = self.grid_shape = tuple(eps_r.shape)
+
+        self.dL = dL
+        self.npml = npml
+        self.eps_r = eps_r
+
+    def __repr__(self):
+        return "FDTD(eps_r.shape={}, dL={}, NPML={})".format(self.grid_shape, self.dL, self.npml)
+
+    def __str__(self):
+        return "FDTD object:\n\tdomain size = {}\n\tdL = {}\n\tNPML = {}".format(self.grid_shape, self.dL, self.npml)
+
+    # ------------------------------------------------------------------ properties
+    @property
+    def dL(self):
+        return self.__dL
+
+    @dL.setter
+    def dL(self, new_dL):
+        """Resets the time step (only: sigma is NOT recomputed -- the reference's behaviour, fdtd.py:41-45)."""
+        self.__dL = new_dL
+        self._set_time_step()
+        self._plan = None
+
+    @property
+    def npml(self):
+        return self.__npml
+
+    @npml.setter
+    def npml(self, new_npml):
+        self.__npml = new_npml
+        self._compute_sigmas()
+        self._plan = None
+
+    @property
+    def eps_r(self):
+        return self.__eps_r
+
+    @eps_r.setter
+    def eps_r(self, new_eps):
+        """New permittivity => new Yee averages and 1/eps, and a FIELD RESET (fdtd.py:63-72)."""
+        new_eps = self._as_eps(new_eps, pad=False)
+        if tuple(new_eps.shape) != tuple(self.grid_shape):
+            self._plan = None
+        self.__eps_r = new_eps
+        e64 = new_eps.to(torch.float64)
+        # ceviche/utils.py:153-176 (grid_center_to_xyz): mean with the previous cell, periodic
+        self.eps_xx, self.eps_yy, self.eps_zz = [(e64 + torch.roll(e64, 1, a)) / 2 for a in range(3)]
+        self.eps_arr = new_eps.flatten()
+        self.N = self.eps_arr.numel()
+        self.grid_shape = self.Nx, self.Ny, self.Nz = tuple(new_eps.shape)
+        self._compute_update_parameters()
+        self.initialize_fields()
+
+    def _as_eps(self, eps, pad):
+        if not torch.is_tensor(eps):
+            eps = torch.as_tensor(np.asarray(eps, dtype=np.float64))
+        if pad:
+            eps = reshape_to_ND(eps, N=3)
+        elif eps.dim() != 3:
+            raise ValueError("eps_r must be 3-dimensional when assigned, given shape {}".format(tuple(eps.shape)))
+        return eps.to(self.device)
+
+    # ------------------------------------------------------------------ set-up
+    def _set_time_step(self, stability_factor=0.5):
+        """fdtd.py:213-222: always the 3-D Courant bound."""
+        dL_sum = 3 / self.dL ** 2
+        dL_avg = 1 / np.sqrt(dL_sum)
+        courant_stability = dL_avg / C_0
+        self.dt = courant_stability * stability_factor
+
+    def _compute_sigmas(self):
+        npml = list(self.npml)
+        if len(npml) != 3:
+            raise IndexError("npml needs 3 entries (fdtd.py:249 indexes npml[2])")
+        self.sigH, self.sigD = sigma_profiles(self.grid_shape, npml, self.dt)
+
+    def _compute_update_parameters(self, mu_r=1.0):
+        """Only the D->E coefficients are arrays (fdtd.py:314-316); everything else lives in the
+        plan's 1-D tables."""
+        self._mE64 = [1 / e for e in (self.eps_xx, self.eps_yy, self.eps_zz)]
+        self._mE = [m.to(self.dtype).contiguous() for m in self._mE64]
+        self.mEx1, self.mEy1, self.mEz1 = self._mE
+
+    def _ensure_plan(self):
+        if self._plan is None:
+            self._plan = _Plan(self.device, self.dtype, self.arith_f64, self.grid_shape, self.dL, self.dt,
+                               self.sigH, self.sigD)
+            self._alloc_pml()
+            self._src_key = self._probe_key = None
+        return self._plan
+
+    def _alloc_pml(self):
+        shapes = self._plan.pml_shapes
+        z = lambda s: torch.zeros(s, dtype=self.dtype, device=self.device)
+        self._pml = {fam: [z(shapes[f * 3 + c]) for c in range(3)] for f, fam in enumerate(_PML_FAMILIES)}
+
+    def initialize_fields(self):
+        """fdtd.py:147-211: zero state, t_index = 0, a NEW fields dict."""
+        self.t_index = 0
+        z = lambda: [torch.zeros(self.grid_shape, dtype=self.dtype, device=self.device) for _ in range(3)]
+        self._H, self._D, self._E = z(), z(), z()
+        if self._plan is not None:
+            self._alloc_pml()
+        else:
+            self._pml = None
+        self.fields = {}
+        self._publish()
+
+    def _publish(self):
+        self._published = True   # these tensors are now in the caller's hands: never mutate them
+        for c, n in enumerate("xyz"):
+            self.fields["E" + n] = self._E[c]
+            self.fields["D" + n] = self._D[c]
+            self.fields["H" + n] = self._H[c]
+
+    def __getattr__(self, name):
+        # Hx.., Dx.., Ex.., ICEx.. attribute surface of the reference (fdtd.py:157-199)
+        if len(name) >= 2 and name[-1] in "xyz" and not name.startswith("_"):
+            c = "xyz".index(name[-1])
+            fam = name[:-1]
+            d = self.__dict__
+            if fam in ("H", "D", "E") and "_" + fam in d:
+                return d["_" + fam][c]
+            if fam in _PML_FAMILIES and d.get("_pml") is not None:
+                return d["_pml"][fam][c]
+            if fam in ("sigH", "sigD") and fam in d:
+                view = [1, 1, 1]
+                view[c] = -1
+                return np.broadcast_to(d[fam][c].reshape(view), d["grid_shape"])
+        raise AttributeError(name)
+
+    # ------------------------------------------------------------------ C-ABI state
+    def _state(self, H=None, D=None, mE=None):
+        st = _lib.cev_state()
+        st.H = _ptr3(H or self._H)
+        st.D = _ptr3(D or self._D)
+        st.inv_eps = _ptr3(mE or self._mE)
+        for fam in _PML_FAMILIES:
+            setattr(st, fam, _ptr3(self._pml[fam]))
+        return st
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _as_J(self, J):
+        if J is None:
+            return None
+        if not torch.is_tensor(J):
+            J = torch.as_tensor(np.asarray(J))
+        if J.is_complex():
+            raise NotImplementedError("complex J is not supported by the CUDA path")
+        J = J.to(device=self.device, dtype=self.dtype)
+        if J.dim() < 3:
+            J = J.reshape(tuple(J.shape) + (1,) * (3 - J.dim())) if J.dim() > 0 else J
+        return J.expand(self.grid_shape).contiguous()
+
+    # ------------------------------------------------------------------ one time step
+    def forward(self, Jx=None, Jy=None, Jz=None):
+        """ one time step of FDTD (fdtd.py:74-144).  Returns the (same) `fields` dict holding nine
+        FRESH tensors, like the reference hands out fresh arrays each step. """
+        from . import autodiff
+        plan = self._ensure_plan()
+        self.t_index += 1
+        J = [self._as_J(j) for j in (Jx, Jy, Jz)]
+        if autodiff.needs_grad(self, J):
+            self._H, self._D, self._E, self._pml = autodiff.step(self, J)
+            self._publish()
+            return self.fields
+        with torch.cuda.device(self.device):
+            Hn = [torch.empty_like(t) for t in self._H]
+            Dn = [torch.empty_like(t) for t in self._D]
+            En = [torch.empty_like(t) for t in self._E]
+            lib, h, s = plan.lib, plan.handle, self._stream()
+            st = self._state()
+            _lib.check(lib.cev_fdtd_step_H(h, C.byref(st), _ptr3(Hn), 0, self.Nx, s))
+            st.H = _ptr3(Hn)
+            _lib.check(lib.cev_fdtd_step_D(h, C.byref(st), _ptr3(Dn), _ptr3(En), _ptr3(J),
+                                           _lib.c_double3(1.0, 1.0, 1.0), 0, self.Nx, s))
+        self._H, self._D, self._E = Hn, Dn, En
+        self._publish()
+        return self.fields
+
+    # ------------------------------------------------------------------ fused caller loop
+    def _point_set(self, field_code, arr, keep, dense_ok):
+        """profile / mask array -> cev_points (+ tensors kept alive in `keep`)."""
+        if not torch.is_tensor(arr):
+            arr = torch.as_tensor(np.asarray(arr, dtype=np.float64))
+        arr = arr.to(device=self.device, dtype=torch.float64)
+        arr = reshape_to_ND(arr, 3).expand(self.grid_shape).reshape(-1)
+        pts = _lib.cev_points()
+        pts.field = field_code
+        nz = torch.nonzero(arr).reshape(-1)
+        if dense_ok and nz.numel() * 2 > arr.numel():
+            w = arr.contiguous()
+            pts.n, pts.idx, pts.cell0, pts.weight = w.numel(), None, 0, w.data_ptr()
+            keep.append(w)
+        else:
+            w = arr[nz].contiguous()
+            pts.n, pts.idx, pts.cell0, pts.weight = nz.numel(), _ptr(nz), 0, _ptr(w)
+            keep += [nz, w]
+        return pts
+
+    def set_sources(self, sources):
+        """sources: [(component 'x'|'y'|'z', profile array)].  J(t) = sum_s profile_s * waveform[t, s]."""
+        plan = self._ensure_plan()
+        keep = []
+        pts = (_lib.cev_points * max(1, len(sources)))()
+        for s, (comp, profile) in enumerate(sources):
+            pts[s] = self._point_set(3 + _COMP[comp], profile, keep, dense_ok=False)
+        with torch.cuda.device(self.device):
+            _lib.check(plan.lib.cev_fdtd_set_sources(plan.handle, len(sources), pts))
+        self._n_sources = len(sources)
+
+    def set_probes(self, probes):
+        """probes: [(field key 'Ex'..'Hz', mask array)].  series[t, p] = sum(field_p * mask_p)."""
+        plan = self._ensure_plan()
+        keep = []
+        pts = (_lib.cev_points * max(1, len(probes)))()
+        for p, (key, mask) in enumerate(probes):
+            pts[p] = self._point_set(_FIELD_CODE[key], mask, keep, dense_ok=True)
+        n_slots = C.c_int64()
+        with torch.cuda.device(self.device):
+            _lib.check(plan.lib.cev_fdtd_set_probes(plan.handle, len(probes), pts, C.byref(n_slots)))
+        owner = (C.c_int32 * max(1, n_slots.value))()
+        _lib.check(plan.lib.cev_fdtd_probe_slots(plan.handle, owner))
+        fold = torch.zeros((n_slots.value, len(probes)), dtype=torch.float64)
+        for s in range(n_slots.value):
+            fold[s, owner[s]] = 1.0
+        self._slot_fold = fold.to(self.device)
+        self._n_probes = len(probes)
+        self._n_slots = n_slots.value
+
+    def run(self, steps, sources=(), probes=(), waveforms=None):
+        """`steps` fused time steps: the loop of ceviche/utils.py:325-331 on the device.
+
+        sources: [(component, profile, waveform[steps])]  (or (component, profile) with
+                 `waveforms` a [steps, n_sources] array/tensor)
+        probes:  [(field key, mask)]
+        Returns series[steps, n_probes] (float64 tensor on the device).  State advances in place;
+        `fields` is refreshed at the end."""
+        from . import autodiff
+        steps = int(steps)
+        src_geo = [(s[0], s[1]) for s in sources]
+        if waveforms is None:
+            if len(sources):
+                waveforms = np.stack([np.asarray(s[2], dtype=np.float64)[:steps] for s in sources], axis=1)
+            else:
+                waveforms = np.zeros((steps, 0))
+        if not torch.is_tensor(waveforms):
+            waveforms = torch.as_tensor(np.ascontiguousarray(waveforms, dtype=np.float64))
+        waveforms = waveforms.to(device=self.device, dtype=torch.float64).contiguous()
+        if waveforms.shape != (steps, len(sources)):
+            raise ValueError("waveforms must have shape (steps, n_sources) = {}".format((steps, len(sources))))
+        self.set_sources(src_geo)
+        self.set_probes(list(probes))
+        if autodiff.needs_grad(self, []):
+            return autodiff.run(self, steps, waveforms)
+        return self._run_raw(steps, waveforms)
+
+    def _run_raw(self, steps, waveforms, refresh=True):
+        plan = self._ensure_plan()
+        with torch.cuda.device(self.device):
+            if self._published:   # the in-place loop must not touch tensors handed out earlier
+                self._H = [t.clone() for t in self._H]
+                self._D = [t.clone() for t in self._D]
+                self._published = False
+            partials = torch.zeros((steps, self._n_slots), dtype=torch.float64, device=self.device)
+            st = self._state()
+            _lib.check(plan.lib.cev_fdtd_run(plan.handle, C.byref(st), steps, _ptr(waveforms), _ptr(partials),
+                                             self._stream()))
+            self.t_index += steps
+            if refresh:
+                self._refresh_E()
+            if self._n_probes == 0:
+                return torch.zeros((steps, 0), dtype=torch.float64, device=self.device)
+            return partials @ self._slot_fold
+
+    def _refresh_E(self):
+        plan = self._ensure_plan()
+        En = [torch.empty_like(t) for t in self._D]
+        st = self._state()
+        _lib.check(plan.lib.cev_fdtd_compute_E(plan.handle, C.byref(st), _ptr3(En), self._stream()))
+        self._E = En
+        self._publish()

@@ -1,0 +1,118 @@
+/* ceviche_b200 -- C ABI of the B200-native FDTD time-stepping engine.
+ *
+ * Drop-in boundary for ONE path of fancompute/ceviche: the body of
+ * ceviche.fdtd.forward() (reference ceviche/fdtd.py:74-144: curl_E / curl_H of
+ * ceviche/derivatives.py:16-30, the sigma-PML update of fdtd.py:85-122, the J
+ * injection of fdtd.py:125-127 and E = D/eps of fdtd.py:135-137), its caller loop
+ * (ceviche/utils.py:316-332) and its derivatives with respect to eps_r.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no C++/torch types.
+ *  - every function returns 0 on success, <0 on error; cev_last_error() gives the
+ *    message of the last failure on the calling thread.  No exception crosses the ABI.
+ *  - all FIELD pointers are DEVICE pointers borrowed from the caller (torch tensors in
+ *    the Python host layer); the library never allocates, frees or retains field
+ *    memory.  The opaque plan owns only small tables (1-D PML profiles, index maps,
+ *    source / probe point sets).
+ *  - every compute call is asynchronous and ordered on the caller's cudaStream_t
+ *    (passed as void*); a plan is bound to one device and is not thread-safe.
+ *  - arrays are C-order (Nx, Ny, Nz), z contiguous, exactly like the reference's
+ *    numpy arrays; vector arguments are indexed [0]=x, [1]=y, [2]=z.
+ *  - dtype: 0 = fp32 storage, 1 = fp64 storage (the reference is fp64).
+ */
+#ifndef CEVICHE_B200_H
+#define CEVICHE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CEV_ABI_VERSION 1
+#define CEV_F32 0
+#define CEV_F64 1
+
+/* field codes used by probes / seeds: E=0..2, D=3..5, H=6..8 (x,y,z) */
+#define CEV_FIELD_E 0
+#define CEV_FIELD_D 3
+#define CEV_FIELD_H 6
+
+typedef struct cev_fdtd cev_fdtd;
+
+/* State of one simulation (or one x-slab of it).  Replaces the attribute soup of
+ * fdtd.initialize_fields() (fdtd.py:147-211): H*, D*, and the four PML integral families
+ * ICE*, IH*, ICH*, ID*.  E is NOT state: E = inv_eps * D is formed on the fly by the H
+ * half-step (bit-identical to fdtd.py:135-137) and only materialised on request.
+ * The PML integrals are stored compactly, only where their coefficient is non-zero
+ * (shapes from cev_fdtd_pml_shapes).  *_xhi / *_xlo are the x-halo planes (Ny*Nz
+ * contiguous) a slab reads beyond its last / before its first x-plane; NULL means
+ * "wrap inside this array" (single-slab np.roll semantics, derivatives.py:16-30). */
+typedef struct cev_state {
+    void*       H[3];
+    void*       D[3];
+    const void* inv_eps[3];      /* mE{x,y,z}1 = 1/eps_{xx,yy,zz}, fdtd.py:314-316 */
+    void*       ICE[3];
+    void*       IH[3];
+    void*       ICH[3];
+    void*       ID[3];
+    const void* D_xhi[3];        /* D planes at local i = nx (from the right neighbour); [0] unused */
+    const void* inv_eps_xhi[3];
+    const void* H_xlo[3];        /* H planes at local i = -1 (from the left neighbour); [0] unused */
+} cev_state;
+
+/* Sparse (or dense) point sets for sources, probes and adjoint seeds.  All arrays are
+ * device pointers.  A set with idx == NULL is dense: point q is cell (cell0 + q). */
+typedef struct cev_points {
+    int32_t        field;        /* CEV_FIELD_* + component (sources: D component 3..5) */
+    int64_t        n;
+    const int64_t* idx;          /* flat C-order cell index, or NULL */
+    int64_t        cell0;
+    const double*  weight;       /* n weights (profile / mask values) */
+} cev_points;
+
+const char* cev_last_error(void);
+int         cev_abi_version(void);
+
+/* Plan = geometry + PML tables.  Replaces fdtd._set_time_step (fdtd.py:213-222, dt is
+ * computed by the host layer and passed in), fdtd._compute_sigmas (fdtd.py:224-263, the
+ * six 1-D profiles sH{x,y,z}, sD{x,y,z} on the HOST, lengths nx, Ny, Nz) and
+ * fdtd._compute_update_parameters (fdtd.py:265-316): the 30 coefficient arrays are never
+ * built; the kernels evaluate them from the profiles.  nx is the number of local x-planes. */
+int cev_fdtd_create(cev_fdtd** plan, int device, int dtype, int arith_f64,
+                    int64_t nx, int64_t Ny, int64_t Nz, double dL, double dt,
+                    const double* sH[3], const double* sD[3]);
+int cev_fdtd_destroy(cev_fdtd* plan);
+
+/* Logical shapes of the 12 compact PML integral arrays, order ICE[3], IH[3], ICH[3], ID[3]. */
+int cev_fdtd_pml_shapes(const cev_fdtd* plan, int64_t shapes[12][3]);
+
+/* H half-step, fdtd.py:80-97, on local x-planes [x0, x1).  H_out == NULL: in place. */
+int cev_fdtd_step_H(cev_fdtd* plan, const cev_state* st, void* const H_out[3],
+                    int64_t x0, int64_t x1, void* stream);
+/* D/E half-step, fdtd.py:105-137.  D_out == NULL: in place.  E_out nullable (each entry).
+ * J[c] nullable dense source added after the update, scaled by J_scale[c] (fdtd.py:125-127). */
+int cev_fdtd_step_D(cev_fdtd* plan, const cev_state* st, void* const D_out[3], void* const E_out[3],
+                    const void* const J[3], const double J_scale[3],
+                    int64_t x0, int64_t x1, void* stream);
+/* E = inv_eps * D (fdtd.py:135-137) into E_out. */
+int cev_fdtd_compute_E(cev_fdtd* plan, const cev_state* st, void* const E_out[3], void* stream);
+
+/* Sources and probes of the caller loop (utils.py:316-332): J(t) = sum_s profile_s * waveform[t, s],
+ * series[t, p] = sum(field_p * mask_p).  Point sets are copied into the plan. */
+int cev_fdtd_set_sources(cev_fdtd* plan, int nsrc, const cev_points* src);
+int cev_fdtd_set_probes(cev_fdtd* plan, int nprobe, const cev_points* probe, int64_t* n_slots);
+/* slot -> probe map (host array of n_slots ints) so the caller can fold partial sums. */
+int cev_fdtd_probe_slots(const cev_fdtd* plan, int32_t* slot_probe);
+
+/* nsteps fused leap-frog steps with in-kernel source injection and probe sampling.
+ * waveform: device double [nsteps, nsrc]; partials: device double [nsteps, n_slots]
+ * (series[t, p] = sum of the slots of p, in slot order: deterministic). */
+int cev_fdtd_run(cev_fdtd* plan, const cev_state* st, int64_t nsteps,
+                 const double* waveform, double* partials, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CEVICHE_B200_H */

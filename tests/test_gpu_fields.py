@@ -1,0 +1,152 @@
+"""Parity of the CUDA path (through the Python boundary -> C ABI) against the numpy oracle and
+the committed golden vectors.  Tolerances: rel-L2 <= 1e-10 (fp64), <= 1e-5 (fp32), as north_star."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases
+from oracle.fdtd_numpy import FIELD_KEYS, OracleFDTD, pad_to_3d, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float64: 1e-10, torch.float32: 1e-5}
+
+
+def _run_cuda(case, dtype, fused, arith=None):
+    import ceviche_b200
+    F = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"], dtype=dtype, arith=arith)
+    steps = case["steps"]
+    snaps = {}
+    if fused:
+        series = []
+        t0 = 0
+        for t1 in sorted(set(case["snapshots"]) | {steps}):
+            srcs = [(c, p, w[t0:t1]) for c, p, w in case["sources"]]
+            series.append(F.run(t1 - t0, srcs, case["probes"]))
+            if t1 in case["snapshots"]:
+                snaps[t1] = {k: F.fields[k].cpu().numpy() for k in FIELD_KEYS}
+            t0 = t1
+        series = torch.cat(series).cpu().numpy()
+    else:
+        series = np.zeros((steps, len(case["probes"])))
+        masks = [torch.as_tensor(pad_to_3d(m)).cuda() for _, m in case["probes"]]
+        profs = [(c, torch.as_tensor(pad_to_3d(p)).cuda()) for c, p, _ in case["sources"]]
+        for t in range(steps):
+            J = {"x": None, "y": None, "z": None}
+            for (c, p), (_, _, w) in zip(profs, case["sources"]):
+                term = p * float(w[t])
+                J[c] = term if J[c] is None else J[c] + term
+            f = F.forward(Jx=J["x"], Jy=J["y"], Jz=J["z"])
+            for q, (key, _) in enumerate(case["probes"]):
+                series[t, q] = float(torch.sum(f[key].double() * masks[q]))
+            if (t + 1) in case["snapshots"]:
+                snaps[t + 1] = {k: f[k].cpu().numpy() for k in FIELD_KEYS}
+    return F, series, snaps
+
+
+def _check(case, series, snaps, o_series, o_snaps, tol):
+    worst = 0.0
+    for t in case["snapshots"]:
+        for k in FIELD_KEYS:
+            e = rel_l2(snaps[t][k], o_snaps[t][k])
+            assert e <= tol, (t, k, e)
+            worst = max(worst, e)
+        allk = np.concatenate([snaps[t][k].ravel() for k in FIELD_KEYS])
+        allo = np.concatenate([o_snaps[t][k].ravel() for k in FIELD_KEYS])
+        assert rel_l2(allk, allo) <= tol
+    for p in range(series.shape[1]):
+        e = rel_l2(series[:, p], o_series[:, p])
+        assert e <= tol, ("series", p, e)
+    return worst
+
+
+@pytest.mark.parametrize("fused", [True, False], ids=["run", "forward"])
+@pytest.mark.parametrize("name", cases.SMALL_FIELD_CASES)
+def test_small_cases_fp64(name, fused):
+    case = cases.field_case(name)
+    O = OracleFDTD(case["eps"], case["dL"], case["npml"])
+    o_series, o_snaps = O.run(case["steps"], case["sources"], case["probes"], case["snapshots"])
+    F, series, snaps = _run_cuda(case, torch.float64, fused)
+    assert F.dt == O.dt
+    _check(case, series, snaps, o_series, o_snaps, TOL[torch.float64])
+
+
+@pytest.mark.parametrize("arith", ["f32", "f64"])
+@pytest.mark.parametrize("name", ["pml3d", "odd2d", "tall_z"])
+def test_small_cases_fp32(name, arith):
+    case = cases.field_case(name)
+    O = OracleFDTD(case["eps"], case["dL"], case["npml"])
+    o_series, o_snaps = O.run(case["steps"], case["sources"], case["probes"], case["snapshots"])
+    _, series, snaps = _run_cuda(case, torch.float32, True, arith=arith)
+    _check(case, series, snaps, o_series, o_snaps, TOL[torch.float32])
+
+
+@pytest.mark.parametrize("name", ["c1_tm", "c1_te"])
+def test_config1_against_golden(name, golden_dir):
+    """BASELINE config 1 (2-D 200x200, npml 20, dipole, 1000 steps, fp64) against vectors produced
+    by the reference itself; zero fields must stay exactly zero."""
+    case = cases.field_case(name)
+    gold = np.load(os.path.join(golden_dir, "fields_%s.npz" % name))
+    F, series, snaps = _run_cuda(case, torch.float64, True)
+    assert F.dt == float(gold["dt"])
+    s = int(gold["stride"])
+    for p in range(series.shape[1]):
+        assert rel_l2(series[:, p], gold["series"][:, p]) <= 1e-10
+    for t in case["snapshots"]:
+        for k in FIELD_KEYS:
+            g = gold["t%d_%s" % (t, k)]
+            assert rel_l2(snaps[t][k][::s, ::s, :], g) <= 1e-10, (t, k)
+            gn = float(gold["t%d_%s_norm" % (t, k)])
+            n = float(np.linalg.norm(snaps[t][k]))
+            assert (n == 0.0) if gn == 0.0 else abs(n - gn) <= 1e-10 * gn, (t, k)
+
+
+def test_config1_fp32_within_tolerance(golden_dir):
+    case = cases.field_case("c1_tm")
+    gold = np.load(os.path.join(golden_dir, "fields_c1_tm.npz"))
+    for arith in ("f32", "f64"):
+        _, series, snaps = _run_cuda(case, torch.float32, True, arith=arith)
+        s = int(gold["stride"])
+        for k in ("Ez", "Hx", "Hy"):
+            e = rel_l2(snaps[1000][k][::s, ::s, :], gold["t1000_%s" % k])
+            assert e <= 1e-5, (arith, k, e)
+        assert rel_l2(series[:, 0], gold["series"][:, 0]) <= 1e-5
+
+
+def test_forward_and_run_agree_bitwise():
+    case = cases.field_case("pml3d")
+    _, s_run, f_run = _run_cuda(case, torch.float64, True)
+    _, s_fwd, f_fwd = _run_cuda(case, torch.float64, False)
+    t = case["steps"]
+    for k in FIELD_KEYS:
+        assert np.array_equal(f_run[t][k], f_fwd[t][k]), k
+
+
+def test_reference_api_quirks():
+    import ceviche_b200
+    eps = 1 + np.random.default_rng(3).random((10, 9))
+    F = ceviche_b200.fdtd(eps, 5e-8, [2, 2, 0])
+    assert F.grid_shape == (10, 9, 1) and F.N == 90 and F.t_index == 0
+    d0 = F.fields
+    f1 = F.forward(Jz=2.0)                      # scalar J adds to every cell
+    assert f1 is d0 and F.t_index == 1
+    assert torch.all(f1["Dz"] == 2.0)
+    held = f1["Ez"]
+    held_copy = held.clone()
+    F.forward(Jz=np.ones((10, 9, 1)))
+    assert torch.equal(held, held_copy)         # previously returned arrays stay valid
+    assert F.fields["Ez"] is not held
+    F.run(3)
+    assert torch.equal(held, held_copy) and F.t_index == 5
+    F.eps_r = torch.as_tensor(eps.reshape(10, 9, 1) * 2)   # setter resets fields and t_index
+    assert F.t_index == 0 and float(F.fields["Ez"].abs().max()) == 0.0
+    assert F.fields is not d0
+    with pytest.raises(ValueError):
+        F.eps_r = eps                            # 2-D through the setter is an error in the reference too
+    with pytest.raises(ValueError):
+        ceviche_b200.fdtd(np.ones((2, 2, 2, 2)), 5e-8, [0, 0, 0])
+    O = OracleFDTD(eps, 5e-8, [2, 2, 0])
+    assert np.array_equal(F.eps_xx.cpu().numpy() / 2, O.eps_yee[0])
+    assert repr(F) == "FDTD(eps_r.shape=(10, 9, 1), dL=5e-08, NPML=[2, 2, 0])"

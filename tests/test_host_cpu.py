@@ -1,0 +1,67 @@
+"""CPU-only checks of the host layer and of the C-ABI library's export table (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import fdtd_numpy as onp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_constants_match_reference_digits():
+    from ceviche_b200 import constants as c
+    assert c.EPSILON_0 == 8.85418782e-12 and c.MU_0 == 1.25663706e-6
+    assert c.C_0 == onp.C_0 == 299792458.13099605
+
+
+@pytest.mark.parametrize("shape,npml", [((12, 7, 9), (3, 2, 0)), ((200, 200, 1), (20, 20, 0)), ((5, 6, 40), (0, 1, 9))])
+def test_host_sigma_profiles_equal_oracle(shape, npml):
+    from ceviche_b200.fdtd import sigma_profiles
+    dt = onp.time_step(5e-8)
+    sH, sD = sigma_profiles(shape, npml, dt)
+    oH, oD = onp.sigma_profiles(shape, npml, dt)
+    for a in range(3):
+        assert np.array_equal(sH[a], oH[a]) and np.array_equal(sD[a], oD[a])
+
+
+def test_reshape_to_nd_raises_beyond_3d():
+    from ceviche_b200.fdtd import reshape_to_ND
+    assert reshape_to_ND(np.ones((4, 5)), 3).shape == (4, 5, 1)
+    with pytest.raises(ValueError):
+        reshape_to_ND(np.ones((2, 2, 2, 2)), 3)
+
+
+def test_library_exports_every_declared_symbol():
+    """Every function declared in include/ceviche_b200.h is exported by the built .so."""
+    from ceviche_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "ceviche_b200.h")).read()
+    declared = set(re.findall(r"\b(cev_[a-z_A-Z0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert set(_lib.EXPORTS) == declared
+    assert lib.cev_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import ceviche_b200
+    from ceviche_b200._lib import CevicheB200Error
+    with pytest.raises(CevicheB200Error):
+        ceviche_b200.fdtd(np.ones((4, 4)), 5e-8, [1, 1, 0])
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under ceviche_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "ceviche_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
