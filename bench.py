@@ -223,14 +223,16 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident throughput -------------------------------------------------
+    wave_dev = torch.as_tensor(np.stack([s_[2] for s_ in srcs], 1)).to(dev)
+    F.prepare(srcs, probes)        # profiles / masks uploaded once: inputs resident in HBM
     for _ in range(args.warmup):
-        F.run(chunk, srcs, probes)
+        F.run(chunk, waveforms=wave_dev)
     sync()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         ev0.record()
         for _ in range(args.steps):
-            F.run(chunk, srcs, probes)
+            F.run(chunk, waveforms=wave_dev)
         ev1.record()
         sync()
     ms = ev0.elapsed_time(ev1)

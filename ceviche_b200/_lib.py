@@ -39,6 +39,7 @@ def _declare(lib):
                             C.c_double, C.c_double, c_dptr3, c_dptr3],
         "cev_fdtd_destroy": [C.c_void_p],
         "cev_fdtd_pml_shapes": [C.c_void_p, P(C.c_int64 * 3 * 12)],
+        "cev_fdtd_set_option": [C.c_void_p, C.c_char_p, C.c_int64],
         "cev_fdtd_step_H": [C.c_void_p, P(cev_state), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p],
         "cev_fdtd_step_D": [C.c_void_p, P(cev_state), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                             C.c_int64, C.c_int64, C.c_void_p],
@@ -56,6 +57,7 @@ def _declare(lib):
 
 
 EXPORTS = ("cev_last_error", "cev_abi_version", "cev_fdtd_create", "cev_fdtd_destroy", "cev_fdtd_pml_shapes",
+           "cev_fdtd_set_option",
            "cev_fdtd_step_H", "cev_fdtd_step_D", "cev_fdtd_compute_E", "cev_fdtd_set_sources",
            "cev_fdtd_set_probes", "cev_fdtd_probe_slots", "cev_fdtd_run")
 

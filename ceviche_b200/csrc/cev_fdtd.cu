@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "step_v1.cuh"
+#include "step_v2.cuh"
 
 namespace {
 
@@ -67,6 +68,8 @@ struct cev_fdtd {
     int N[3] = {0, 0, 0};        // internal extents
     double dL = 0, dt = 0, cdt = 0;
     int nH[3] = {0, 0, 0}, nD[3] = {0, 0, 0};   // internal compact counts
+    int variant = 0;             // 0 auto, 1 force baseline kernels, 2 force marching kernels
+    int xchunk = 0;              // 0 auto
     DeviceBuf tables;            // u/r (f32 + f64) and maps for 3 axes x {H, D}
     const void* uH[3][2];        // [axis][0: f32, 1: f64]
     const void* rH[3][2];
@@ -152,9 +155,54 @@ template <typename T, typename AT>
 void set_tiles_v1(StepArgs<T, AT>& a, int64_t x0, int64_t x1) {
     a.x0 = (int)x0;
     a.x1 = (int)x1;
+    a.xchunk = 1;
     a.ntz = (a.Nz + V1_TZ - 1) / V1_TZ;
     a.nty = (a.Ny + V1_TY - 1) / V1_TY;
     a.n_tiles = a.ntz * a.nty * (int)(x1 - x0);
+}
+
+template <typename T>
+constexpr int vec_width() {
+    return 16 / (int)sizeof(T);
+}
+
+// The marching kernels need 16-byte vectors along z: Nz a multiple of the vector width and every
+// array 16-byte aligned (torch allocations are; odd Nz falls back to the baseline kernels).
+template <typename T, typename AT>
+bool can_march(const cev_fdtd* p, const StepArgs<T, AT>& a, bool isH) {
+    if (p->variant == 1) return false;
+    constexpr int V = vec_width<T>();
+    if (a.Nz % V != 0) return false;
+    auto ok = [](const void* q) { return q == nullptr || ((uintptr_t)q % 16) == 0; };
+    for (int c = 0; c < 3; ++c) {
+        if (!ok(a.Hin[c]) || !ok(a.Hout[c]) || !ok(a.Din[c]) || !ok(a.Dout[c]) || !ok(a.mE[c]) || !ok(a.Eout[c]) ||
+            !ok(a.Dhi[c]) || !ok(a.mEhi[c]) || !ok(a.Hlo[c]) || !ok(a.J[c]))
+            return false;
+    }
+    (void)isH;
+    return p->variant == 2 || a.Nz >= 2 * V;
+}
+
+template <typename T, typename AT>
+void set_tiles_v2(const cev_fdtd* p, StepArgs<T, AT>& a, int64_t x0, int64_t x1) {
+    constexpr int V = vec_width<T>();
+    a.x0 = (int)x0;
+    a.x1 = (int)x1;
+    a.ntz = (a.Nz + 32 * V - 1) / (32 * V);
+    a.nty = (a.Ny + V2_BY - 1) / V2_BY;
+    const int nx = (int)(x1 - x0);
+    const int cols = a.ntz * a.nty;
+    int chunk = p->xchunk;
+    if (chunk <= 0) {
+        const int target = 148 * 24;                   // ~6 waves of 128-thread CTAs on 148 SMs
+        int nchunks = (target + cols - 1) / cols;
+        if (nchunks < 1) nchunks = 1;
+        if (nchunks > nx) nchunks = nx > 0 ? nx : 1;
+        chunk = (nx + nchunks - 1) / nchunks;
+        if (chunk < 8) chunk = nx < 8 ? (nx > 0 ? nx : 1) : 8;
+    }
+    a.xchunk = chunk;
+    a.n_tiles = nx > 0 ? cols * ((nx + chunk - 1) / chunk) : 0;
 }
 
 // which: 0 = E/D-family slots, 1 = H-family slots
@@ -177,10 +225,13 @@ int launch_H(cev_fdtd* p, const cev_state* st, void* const H_out[3], int64_t x0,
             a.Hout[A] = (T*)H_out[p->to_logical(A)];
             if (!a.Hout[A]) return fail("H_out entries must be non-NULL");
         }
-    set_tiles_v1(a, x0, x1);
+    const bool march = can_march(p, a, true);
+    if (march) set_tiles_v2(p, a, x0, x1);
+    else set_tiles_v1(a, x0, x1);
     const int aux = attach_probes(p, a, 0, probe_t, partials);
     if (a.n_tiles + aux == 0) return 0;
-    k_step_H_v1<T, AT><<<a.n_tiles + aux, dim3(V1_TZ, V1_TY), 0, s>>>(a);
+    if (march) k_step_H_v2<T, AT, vec_width<T>()><<<a.n_tiles + aux, dim3(32, V2_BY), 0, s>>>(a);
+    else k_step_H_v1<T, AT><<<a.n_tiles + aux, dim3(V1_TZ, V1_TY), 0, s>>>(a);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -202,10 +253,15 @@ int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const
         if (J_scale) a.Jscale[A] = (AT)J_scale[L];
         if (J_wave) a.Jwave[A] = J_wave[L];
     }
-    set_tiles_v1(a, x0, x1);
+    const bool march = can_march(p, a, false);
+    if (march) set_tiles_v2(p, a, x0, x1);
+    else set_tiles_v1(a, x0, x1);
     const int aux = attach_probes(p, a, 1, probe_t, partials);
     if (a.n_tiles + aux == 0) return 0;
-    k_step_D_v1<T, AT><<<a.n_tiles + aux, dim3(V1_TZ, V1_TY), 0, s>>>(a);
+    const bool extras = a.J[0] || a.J[1] || a.J[2] || a.Eout[0] || a.Eout[1] || a.Eout[2];
+    if (march && extras) k_step_D_v2<T, AT, vec_width<T>(), true><<<a.n_tiles + aux, dim3(32, V2_BY), 0, s>>>(a);
+    else if (march) k_step_D_v2<T, AT, vec_width<T>(), false><<<a.n_tiles + aux, dim3(32, V2_BY), 0, s>>>(a);
+    else k_step_D_v1<T, AT><<<a.n_tiles + aux, dim3(V1_TZ, V1_TY), 0, s>>>(a);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -407,6 +463,20 @@ int cev_fdtd_destroy(cev_fdtd* p) {
     p->pr_field.release(); p->pr_wbegin.release(); p->pr_ibegin.release(); p->pr_cell0.release();
     p->pr_n.release(); p->pr_idx.release(); p->pr_weight.release();
     delete p;
+    return 0;
+}
+
+int cev_fdtd_set_option(cev_fdtd* p, const char* name, int64_t value) {
+    if (!p || !name) return fail("NULL argument");
+    if (!strcmp(name, "kernel_variant")) {
+        if (value < 0 || value > 2) return fail("kernel_variant must be 0 (auto), 1 (baseline) or 2 (marching)");
+        p->variant = (int)value;
+    } else if (!strcmp(name, "xchunk")) {
+        if (value < 0) return fail("xchunk must be >= 0");
+        p->xchunk = (int)value;
+    } else {
+        return fail("unknown option '%s'", name);
+    }
     return 0;
 }
 

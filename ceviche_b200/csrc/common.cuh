@@ -51,7 +51,7 @@ struct StepArgs {
     AT       Jscale[3];
     const double* Jwave[3];   // nullable device scalar overriding Jscale (waveform entry)
     // tiling + auxiliary probe CTAs appended to the grid
-    int n_tiles, ntz, nty;
+    int n_tiles, ntz, nty, xchunk;
     ProbeTable pr;
     int        aux_slot0;     // first slot handled by the aux CTAs of this launch
     int64_t    t_probe;       // row of partials[] they write
@@ -61,7 +61,7 @@ struct StepArgs {
 template <typename T, typename AT>
 __device__ __forceinline__ AT probe_value(const StepArgs<T, AT>& a, int field, int64_t cell) {
     const int c = field % 3;
-    if (field < 3) return (AT)a.mE[c][cell] * (AT)a.Din[c][cell];
+    if (field < 3) return (AT)a.mE[c][cell] * (AT)a.Din[c][cell];   // feeds a double product: no contraction issue
     if (field < 6) return (AT)a.Din[c][cell];
     return (AT)a.Hin[c][cell];
 }
@@ -91,31 +91,58 @@ __device__ void probe_block(const StepArgs<T, AT>& a, int slot) {
     if (tid == 0) a.partials[a.t_probe * a.pr.n_slots + slot] = red[0];
 }
 
-// One field component of one half-step (fdtd.py:85-97 for H, :110-122 for D):
-//   I_curl += curl ; I_self += old ; new = m1*old + m2*curl + m3*I_curl + m4*I_self
-// with the coefficients of fdtd.py:272-311 rewritten division-free from the per-axis tables
-//   m0*dt = (1+ua)(1+ub),  1/m0 = dt*ra*rb
+// Explicitly rounded arithmetic: no FMA contraction, so that (i) every kernel variant produces
+// bit-identical results and (ii) the rounding sequence is the reference's numpy one (each product
+// and each sum rounded separately, fdtd.py:95-97 / derivatives.py:18).
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+
+// (a1-a0)/dL - (b1-b0)/dL, both quotients rounded before the subtraction (derivatives.py:16-30)
+template <typename AT>
+__device__ __forceinline__ AT curl2(AT a1, AT a0, AT b1, AT b0, AT inv) {
+    return add_rn(mul_rn(a1 - a0, inv), -mul_rn(b1 - b0, inv));
+}
+
+// Coefficients of fdtd.py:272-311 rewritten division-free from the per-axis tables
+//   u = sigma*dt/(2 eps0), r = 1/(1+u):   m0*dt = (1+ua)(1+ub),  1/m0 = dt*ra*rb
 //   m1 = (1-ua-ub-ua*ub) ra rb,  m2 = s*C0*dt ra rb,  m3 = s*C0*dt*2uc ra rb,  m4 = -4 ua ub ra rb
 // (s = -1 for H, +1 for D; (ua,ub) = the two other axes, uc = the component's own axis).
-// The integral arrays exist only where their coefficient is non-zero (index < 0: skip).
+template <typename AT>
+__device__ __forceinline__ void coef12(AT ua, AT ra, AT ub, AT rb, AT scdt, AT& m1, AT& m2) {
+    const AT rr = mul_rn(ra, rb);
+    m1 = mul_rn(AT(1) - ua - ub - mul_rn(ua, ub), rr);
+    m2 = mul_rn(scdt, rr);
+}
+
+// One field component of one half-step (fdtd.py:85-97 for H, :110-122 for D):
+//   I_curl += curl ; I_self += old ; new = m1*old + m2*curl + m3*I_curl + m4*I_self
+// The integral arrays exist only where their coefficient is non-zero (index < 0: skip); m3 / m4
+// are only evaluated there.
 template <typename T, typename AT>
-__device__ __forceinline__ AT update_component(AT old, AT curl, AT ua, AT ra, AT ub, AT rb, AT uc, AT scdt,
-                                               T* Icurl, int64_t icurl, T* Iself, int64_t iself) {
-    const AT rr = ra * rb;
-    const AT m1 = (AT(1) - ua - ub - ua * ub) * rr;
-    const AT m2 = scdt * rr;
-    AT v = m1 * old + m2 * curl;
+__device__ __forceinline__ AT update_cell(AT old, AT curl, AT m1, AT m2, AT ua, AT ra, AT ub, AT rb, AT uc, AT scdt,
+                                          T* Icurl, int64_t icurl, T* Iself, int64_t iself) {
+    AT v = add_rn(mul_rn(m1, old), mul_rn(m2, curl));
     if (icurl >= 0) {
         const AT I = (AT)Icurl[icurl] + curl;
         Icurl[icurl] = (T)I;
-        v += (scdt * (uc + uc) * rr) * I;
+        v = add_rn(v, mul_rn(mul_rn(mul_rn(scdt, uc + uc), mul_rn(ra, rb)), I));
     }
     if (iself >= 0) {
         const AT I = (AT)Iself[iself] + old;
         Iself[iself] = (T)I;
-        v += (AT(-4) * ua * ub * rr) * I;
+        v = add_rn(v, mul_rn(mul_rn(mul_rn(mul_rn(AT(-4), ua), ub), mul_rn(ra, rb)), I));
     }
     return v;
+}
+
+template <typename T, typename AT>
+__device__ __forceinline__ AT update_component(AT old, AT curl, AT ua, AT ra, AT ub, AT rb, AT uc, AT scdt,
+                                               T* Icurl, int64_t icurl, T* Iself, int64_t iself) {
+    AT m1, m2;
+    coef12<AT>(ua, ra, ub, rb, scdt, m1, m2);
+    return update_cell<T, AT>(old, curl, m1, m2, ua, ra, ub, rb, uc, scdt, Icurl, icurl, Iself, iself);
 }
 
 }  // namespace cev

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(V1_TZ* V1_TY) k_step_H_v1(const StepArgs<T, AT
     const int64_t o_kp = i * plane + (int64_t)j * a.Nz + kp;
     const bool last = (i + 1 == a.Nx);
 
-#define E_AT(c, off) ((AT)a.mE[c][off] * (AT)a.Din[c][off])
+#define E_AT(c, off) mul_rn((AT)a.mE[c][off], (AT)a.Din[c][off])
     const AT Ex = E_AT(0, o), Ey = E_AT(1, o), Ez = E_AT(2, o);
     const AT Ex_jp = E_AT(0, o_jp), Ez_jp = E_AT(2, o_jp);
     const AT Ex_kp = E_AT(0, o_kp), Ey_kp = E_AT(1, o_kp);
@@ -46,14 +46,14 @@ __global__ void __launch_bounds__(V1_TZ* V1_TY) k_step_H_v1(const StepArgs<T, AT
         Ey_ip = E_AT(1, o + plane);
         Ez_ip = E_AT(2, o + plane);
     } else {
-        Ey_ip = (AT)a.mEhi[1][o_in] * (AT)a.Dhi[1][o_in];
-        Ez_ip = (AT)a.mEhi[2][o_in] * (AT)a.Dhi[2][o_in];
+        Ey_ip = mul_rn((AT)a.mEhi[1][o_in], (AT)a.Dhi[1][o_in]);
+        Ez_ip = mul_rn((AT)a.mEhi[2][o_in], (AT)a.Dhi[2][o_in]);
     }
 #undef E_AT
     const AT inv = a.inv_dL;
-    const AT CEx = (Ez_jp - Ez) * inv - (Ey_kp - Ey) * inv;
-    const AT CEy = (Ex_kp - Ex) * inv - (Ez_ip - Ez) * inv;
-    const AT CEz = (Ey_ip - Ey) * inv - (Ex_jp - Ex) * inv;
+    const AT CEx = curl2<AT>(Ez_jp, Ez, Ey_kp, Ey, inv);
+    const AT CEy = curl2<AT>(Ex_kp, Ex, Ez_ip, Ez, inv);
+    const AT CEz = curl2<AT>(Ey_ip, Ey, Ex_jp, Ex, inv);
 
     const AT ux = a.uH[0][i], uy = a.uH[1][j], uz = a.uH[2][k];
     const AT rx = a.rH[0][i], ry = a.rH[1][j], rz = a.rH[2][k];
@@ -117,9 +117,9 @@ __global__ void __launch_bounds__(V1_TZ* V1_TY) k_step_D_v1(const StepArgs<T, AT
         Hz_im = (AT)a.Hlo[2][o_in];
     }
     const AT inv = a.inv_dL;
-    const AT CHx = (Hz - Hz_jm) * inv - (Hy - Hy_km) * inv;
-    const AT CHy = (Hx - Hx_km) * inv - (Hz - Hz_im) * inv;
-    const AT CHz = (Hy - Hy_im) * inv - (Hx - Hx_jm) * inv;
+    const AT CHx = curl2<AT>(Hz, Hz_jm, Hy, Hy_km, inv);
+    const AT CHy = curl2<AT>(Hx, Hx_km, Hz, Hz_im, inv);
+    const AT CHz = curl2<AT>(Hy, Hy_im, Hx, Hx_jm, inv);
 
     const AT ux = a.uD[0][i], uy = a.uD[1][j], uz = a.uD[2][k];
     const AT rx = a.rD[0][i], ry = a.rD[1][j], rz = a.rD[2][k];
@@ -146,10 +146,10 @@ __global__ void __launch_bounds__(V1_TZ* V1_TY) k_step_D_v1(const StepArgs<T, AT
         AT d = Dn[c];
         if (a.J[c]) {
             const AT sc = a.Jwave[c] ? (AT)(*a.Jwave[c]) : a.Jscale[c];
-            d += (AT)a.J[c][o] * sc;
+            d = add_rn(d, mul_rn((AT)a.J[c][o], sc));
         }
         a.Dout[c][o] = (T)d;
-        if (a.Eout[c]) a.Eout[c][o] = (T)((AT)a.mE[c][o] * (AT)(T)d);  // E from the STORED D, as fdtd.py:135
+        if (a.Eout[c]) a.Eout[c][o] = (T)mul_rn((AT)a.mE[c][o], (AT)(T)d);  // E from the STORED D, as fdtd.py:135
     }
 }
 
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(V1_TZ* V1_TY) k_step_D_v1(const StepArgs<T, AT
 template <typename T, typename AT>
 __global__ void k_compute_E(const T* __restrict__ mE, const T* __restrict__ D, T* __restrict__ E, int64_t n) {
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x)
-        E[q] = (T)((AT)mE[q] * (AT)D[q]);
+        E[q] = (T)mul_rn((AT)mE[q], (AT)D[q]);
 }
 
 // Sparse J injection: D[field][cell] += weight * waveform[src]   (fdtd.py:125-127 for

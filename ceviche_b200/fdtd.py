@@ -106,7 +106,9 @@ class fdtd:
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         self.dtype = dtype
-        self.arith_f64 = True if dtype == torch.float64 else (arith in (None, "f64", torch.float64))
+        # fp32 storage computes in fp32 by default (meets the 1e-5 bar at <= 1000 steps)
+        self.arith_f64 = True if dtype == torch.float64 else (arith in ("f64", torch.float64))
+        self._options = {}
         self._plan = None
 
         eps_r = self._as_eps(eps_r, pad=True)
@@ -199,8 +201,17 @@ class fdtd:
             self._plan = _Plan(self.device, self.dtype, self.arith_f64, self.grid_shape, self.dL, self.dt,
                                self.sigH, self.sigD)
             self._alloc_pml()
-            self._src_key = self._probe_key = None
+            for name, value in self._options.items():
+                _lib.check(self._plan.lib.cev_fdtd_set_option(self._plan.handle, name.encode(), int(value)))
+            self._n_sources = self._n_probes = self._n_slots = 0
+            self._slot_fold = None
         return self._plan
+
+    def set_option(self, name, value):
+        """Kernel tuning / test knobs of the C ABI ('kernel_variant', 'xchunk'); results do not change."""
+        self._options[name] = int(value)
+        if self._plan is not None:
+            _lib.check(self._plan.lib.cev_fdtd_set_option(self._plan.handle, name.encode(), int(value)))
 
     def _alloc_pml(self):
         shapes = self._plan.pml_shapes
@@ -343,17 +354,36 @@ class fdtd:
         self._n_probes = len(probes)
         self._n_slots = n_slots.value
 
-    def run(self, steps, sources=(), probes=(), waveforms=None):
+    def prepare(self, sources=(), probes=()):
+        """Upload source profiles [(component, profile)] and probe masks [(field key, mask)] once;
+        later `run(steps, waveforms=...)` calls with sources=None reuse them."""
+        self.set_sources([(s[0], s[1]) for s in sources])
+        self.set_probes(list(probes))
+
+    def run(self, steps, sources=None, probes=None, waveforms=None):
         """`steps` fused time steps: the loop of ceviche/utils.py:325-331 on the device.
 
         sources: [(component, profile, waveform[steps])]  (or (component, profile) with
-                 `waveforms` a [steps, n_sources] array/tensor)
-        probes:  [(field key, mask)]
+                 `waveforms` a [steps, n_sources] array/tensor); None = keep the prepared ones
+        probes:  [(field key, mask)]; None = keep the prepared ones
         Returns series[steps, n_probes] (float64 tensor on the device).  State advances in place;
         `fields` is refreshed at the end."""
         from . import autodiff
         steps = int(steps)
-        src_geo = [(s[0], s[1]) for s in sources]
+        self._ensure_plan()
+        if sources is None and probes is None and waveforms is None and self._n_sources == 0:
+            sources = ()
+        if sources is None:
+            if waveforms is None:
+                raise ValueError("run(): prepared sources need `waveforms` [steps, n_sources]")
+            n_src = self._n_sources
+        else:
+            n_src = len(sources)
+            self.set_sources([(s[0], s[1]) for s in sources])
+        if probes is not None:
+            self.set_probes(list(probes))
+        elif self._slot_fold is None:
+            self.set_probes([])
         if waveforms is None:
             if len(sources):
                 waveforms = np.stack([np.asarray(s[2], dtype=np.float64)[:steps] for s in sources], axis=1)
@@ -362,10 +392,8 @@ class fdtd:
         if not torch.is_tensor(waveforms):
             waveforms = torch.as_tensor(np.ascontiguousarray(waveforms, dtype=np.float64))
         waveforms = waveforms.to(device=self.device, dtype=torch.float64).contiguous()
-        if waveforms.shape != (steps, len(sources)):
-            raise ValueError("waveforms must have shape (steps, n_sources) = {}".format((steps, len(sources))))
-        self.set_sources(src_geo)
-        self.set_probes(list(probes))
+        if tuple(waveforms.shape) != (steps, n_src):
+            raise ValueError("waveforms must have shape (steps, n_sources) = {}".format((steps, n_src)))
         if autodiff.needs_grad(self, []):
             return autodiff.run(self, steps, waveforms)
         return self._run_raw(steps, waveforms)

@@ -85,6 +85,10 @@ int cev_fdtd_create(cev_fdtd** plan, int device, int dtype, int arith_f64,
                     const double* sH[3], const double* sD[3]);
 int cev_fdtd_destroy(cev_fdtd* plan);
 
+/* Tuning / test knobs: "kernel_variant" 0 auto | 1 baseline (one thread per cell) | 2 marching;
+ * "xchunk" x-planes per CTA of the marching kernels (0 = auto).  Results do not depend on them. */
+int cev_fdtd_set_option(cev_fdtd* plan, const char* name, int64_t value);
+
 /* Logical shapes of the 12 compact PML integral arrays, order ICE[3], IH[3], ICH[3], ID[3]. */
 int cev_fdtd_pml_shapes(const cev_fdtd* plan, int64_t shapes[12][3]);
 

@@ -1,0 +1,82 @@
+"""The tuned marching kernels (step_v2.cuh) against the baseline one-thread-per-cell kernels
+(step_v1.cuh): bit-identical fields, PML integrals and probe series, for every x-chunking."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases
+from oracle.fdtd_numpy import FIELD_KEYS, OracleFDTD, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(shape, npml, steps, seed):
+    rng = np.random.default_rng(seed)
+    eps = 1 + 3 * rng.random(shape)
+    src = [("z", rng.random(shape) * (rng.random(shape) < 0.02), cases.modulated(steps, steps / 3, steps / 8, 11.0, 2.0)),
+           ("x", cases.one_hot(shape, (shape[0] // 2, shape[1] // 3, shape[2] // 2)), cases.gaussian(steps, steps / 4, steps / 10)),
+           ("y", cases.one_hot(shape, (0, 0, shape[2] - 1)), cases.gaussian(steps, steps / 5, steps / 10))]
+    probes = [("Ez", rng.random(shape)), ("Hx", rng.random(shape) * (rng.random(shape) < 0.2)),
+              ("Dy", cases.one_hot(shape, (shape[0] - 1, shape[1] - 1, 0)))]
+    return dict(eps=eps, dL=cases.DL, npml=list(npml), steps=steps, sources=src, probes=probes)
+
+
+def _run(case, dtype, variant, xchunk=0, per_step=False):
+    import ceviche_b200
+    F = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"], dtype=dtype)
+    F.set_option("kernel_variant", variant)
+    F.set_option("xchunk", xchunk)
+    if per_step:
+        profs = [(c, torch.as_tensor(p).cuda()) for c, p, _ in case["sources"]]
+        for t in range(case["steps"]):
+            J = {c: p * float(w[t]) for (c, p), (_, _, w) in zip(profs, case["sources"])}
+            F.forward(Jx=J.get("x"), Jy=J.get("y"), Jz=J.get("z"))
+        series = None
+    else:
+        series = F.run(case["steps"], case["sources"], case["probes"]).cpu().numpy()
+    fields = {k: F.fields[k].cpu().numpy() for k in FIELD_KEYS}
+    pml = [t.cpu().numpy() for fam in ("ICE", "IH", "ICH", "ID") for t in F._pml[fam]]
+    return series, fields, pml
+
+
+SHAPES = [((20, 18, 136), (4, 3, 6)), ((9, 7, 64), (2, 0, 5)), ((3, 5, 24), (0, 2, 2)), ((33, 40, 1), (5, 6, 0)),
+          ((6, 10, 260), (2, 3, 20))]
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("shape,npml", SHAPES)
+def test_marching_equals_baseline_bitwise(shape, npml, dtype):
+    case = _case(shape, npml, 40, 7)
+    s1, f1, p1 = _run(case, dtype, 1)
+    for xchunk in (0, 1, 3, 1000):
+        s2, f2, p2 = _run(case, dtype, 2, xchunk)
+        for k in FIELD_KEYS:
+            assert np.array_equal(f1[k], f2[k]), (k, xchunk)
+        for a, b in zip(p1, p2):
+            assert np.array_equal(a, b), xchunk
+        assert np.array_equal(s1, s2)
+
+
+def test_marching_forward_api_with_dense_J_and_E_output():
+    case = _case((10, 12, 40), (2, 3, 4), 25, 9)
+    _, f1, _ = _run(case, torch.float64, 1, per_step=True)
+    _, f2, _ = _run(case, torch.float64, 2, xchunk=4, per_step=True)
+    _, f3, _ = _run(case, torch.float64, 2)
+    for k in FIELD_KEYS:
+        assert np.array_equal(f1[k], f2[k]), k
+        assert np.array_equal(f1[k], f3[k]), k
+
+
+def test_marching_against_oracle_midsize():
+    """A grid large enough for several CTAs per axis and several x-chunks, against the numpy oracle."""
+    case = _case((40, 36, 136), (6, 5, 8), 60, 3)
+    O = OracleFDTD(case["eps"], case["dL"], case["npml"])
+    o_series, _ = O.run(case["steps"], case["sources"], case["probes"])
+    series, fields, _ = _run(case, torch.float64, 2, xchunk=7)
+    for k in FIELD_KEYS:
+        assert rel_l2(fields[k], O.fields()[k]) <= 1e-10, k
+    for p in range(series.shape[1]):
+        assert rel_l2(series[:, p], o_series[:, p]) <= 1e-10
+    series32, fields32, _ = _run(case, torch.float32, 2)
+    for k in FIELD_KEYS:
+        assert rel_l2(fields32[k], O.fields()[k]) <= 1e-5, k
