@@ -217,6 +217,9 @@ def run_ours(args):
     cells = shape[0] * shape[1] * shape[2]
     wl = workload(shape, chunk)
     F = ceviche_b200.fdtd(wl["eps"], DL, NPML, dtype=dtype, arith=args.arith)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        F.set_option(k, int(v))
     srcs, probes = wl["sources"], wl["probes"]
 
     def sync():
@@ -290,16 +293,19 @@ def run_ours(args):
         F.eps_r = eps_host.to(dev, non_blocking=True)      # upload + Yee averaging + 1/eps + field reset
         series = F.run(chunk, geo, probes, waveforms=wave_host.to(dev, non_blocking=True))
         return series.cpu()
-    for _ in range(max(1, args.warmup // 2)):
-        e2e_step()
-    sync()
-    n_e2e = max(1, min(args.steps, 3))
-    t0 = time.perf_counter()
-    for _ in range(n_e2e):
-        out = e2e_step()
-    sync()
-    e2e_s = (time.perf_counter() - t0) / n_e2e
-    e2e_val = cells * chunk / e2e_s / 1e9
+    if args.no_e2e:
+        e2e_s, e2e_val = float("nan"), None
+    else:
+        for _ in range(max(1, args.warmup // 2)):
+            e2e_step()
+        sync()
+        n_e2e = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            out = e2e_step()
+        sync()
+        e2e_s = (time.perf_counter() - t0) / n_e2e
+        e2e_val = cells * chunk / e2e_s / 1e9
 
     # ---- CPU baseline: the reference algorithm on the host cores, bounded sample --------
     cpu = None
@@ -335,6 +341,8 @@ def main():
     ap.add_argument("--chunk", type=int, default=1000, help="FDTD time steps per bench step")
     ap.add_argument("--grid", type=int, nargs=3, default=[256, 256, 256])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel tuning runs)")
+    ap.add_argument("--opt", action="append", default=[], help="plan option name=value (repeatable)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

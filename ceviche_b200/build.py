@@ -7,7 +7,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(HERE, "libceviche_b200.so")
+LIB_PATH = os.environ.get("CEV_LIB_PATH") or os.path.join(HERE, "libceviche_b200.so")
 HEADER = os.path.join(ROOT, "include", "ceviche_b200.h")
 
 NVCC_FLAGS = [
@@ -49,6 +49,7 @@ def build_library(force=False, verbose=False, extra_flags=()):
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build %s" % LIB_PATH)
     tmp = LIB_PATH + ".tmp%d" % os.getpid()
+    extra_flags = list(extra_flags) + os.environ.get("CEV_NVCC_EXTRA", "").split()
     cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-I", os.path.join(ROOT, "include"), "-o", tmp] + sources()
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

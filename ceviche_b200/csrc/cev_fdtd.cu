@@ -70,6 +70,8 @@ struct cev_fdtd {
     int nH[3] = {0, 0, 0}, nD[3] = {0, 0, 0};   // internal compact counts
     int variant = 0;             // 0 auto, 1 force baseline kernels, 2 force marching kernels
     int xchunk = 0;              // 0 auto
+    int pf_dist = 1;             // L2 prefetch distance of the marching kernels (planes)
+    int lz = 8;                  // lanes of a warp along z in the marching kernels (8, 16 or 32)
     DeviceBuf tables;            // u/r (f32 + f64) and maps for 3 axes x {H, D}
     const void* uH[3][2];        // [axis][0: f32, 1: f64]
     const void* rH[3][2];
@@ -188,20 +190,20 @@ void set_tiles_v2(const cev_fdtd* p, StepArgs<T, AT>& a, int64_t x0, int64_t x1)
     constexpr int V = vec_width<T>();
     a.x0 = (int)x0;
     a.x1 = (int)x1;
-    a.ntz = (a.Nz + 32 * V - 1) / (32 * V);
-    a.nty = (a.Ny + V2_BY - 1) / V2_BY;
+    const int LZ = p->lz, rows = V2_BY * (32 / LZ);
+    a.ntz = (a.Nz + LZ * V - 1) / (LZ * V);
+    a.nty = (a.Ny + rows - 1) / rows;
     const int nx = (int)(x1 - x0);
     const int cols = a.ntz * a.nty;
     int chunk = p->xchunk;
     if (chunk <= 0) {
-        const int target = 148 * 24;                   // ~6 waves of 128-thread CTAs on 148 SMs
-        int nchunks = (target + cols - 1) / cols;
-        if (nchunks < 1) nchunks = 1;
-        if (nchunks > nx) nchunks = nx > 0 ? nx : 1;
-        chunk = (nx + nchunks - 1) / nchunks;
-        if (chunk < 8) chunk = nx < 8 ? (nx > 0 ? nx : 1) : 8;
+        // short chunks keep the concurrently-active working set (CTAs x streams x planes) inside L2
+        // and give the scheduler many CTAs to balance; tuned on B200 (scripts/tune.py)
+        chunk = cols >= 512 ? 8 : 4;
+        if (chunk > nx) chunk = nx > 0 ? nx : 1;
     }
     a.xchunk = chunk;
+    a.pf_dist = p->pf_dist;
     a.n_tiles = nx > 0 ? cols * ((nx + chunk - 1) / chunk) : 0;
 }
 
@@ -230,7 +232,14 @@ int launch_H(cev_fdtd* p, const cev_state* st, void* const H_out[3], int64_t x0,
     else set_tiles_v1(a, x0, x1);
     const int aux = attach_probes(p, a, 0, probe_t, partials);
     if (a.n_tiles + aux == 0) return 0;
-    if (march) k_step_H_v2<T, AT, vec_width<T>()><<<a.n_tiles + aux, dim3(32, V2_BY), 0, s>>>(a);
+    if (march) {
+        constexpr int V = vec_width<T>();
+        const dim3 blk(32, V2_BY);
+        const int g = a.n_tiles + aux;
+        if (p->lz == 8) k_step_H_v2<T, AT, V, 8><<<g, blk, 0, s>>>(a);
+        else if (p->lz == 16) k_step_H_v2<T, AT, V, 16><<<g, blk, 0, s>>>(a);
+        else k_step_H_v2<T, AT, V, 32><<<g, blk, 0, s>>>(a);
+    }
     else k_step_H_v1<T, AT><<<a.n_tiles + aux, dim3(V1_TZ, V1_TY), 0, s>>>(a);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -259,8 +268,20 @@ int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const
     const int aux = attach_probes(p, a, 1, probe_t, partials);
     if (a.n_tiles + aux == 0) return 0;
     const bool extras = a.J[0] || a.J[1] || a.J[2] || a.Eout[0] || a.Eout[1] || a.Eout[2];
-    if (march && extras) k_step_D_v2<T, AT, vec_width<T>(), true><<<a.n_tiles + aux, dim3(32, V2_BY), 0, s>>>(a);
-    else if (march) k_step_D_v2<T, AT, vec_width<T>(), false><<<a.n_tiles + aux, dim3(32, V2_BY), 0, s>>>(a);
+    if (march) {
+        constexpr int V = vec_width<T>();
+        const dim3 blk(32, V2_BY);
+        const int g = a.n_tiles + aux;
+        if (extras) {   // per-step forward() API: one shape is enough
+            p->lz == 8 ? k_step_D_v2<T, AT, V, 8, true><<<g, blk, 0, s>>>(a)
+                       : (p->lz == 16 ? k_step_D_v2<T, AT, V, 16, true><<<g, blk, 0, s>>>(a)
+                                      : k_step_D_v2<T, AT, V, 32, true><<<g, blk, 0, s>>>(a));
+        } else {
+            p->lz == 8 ? k_step_D_v2<T, AT, V, 8, false><<<g, blk, 0, s>>>(a)
+                       : (p->lz == 16 ? k_step_D_v2<T, AT, V, 16, false><<<g, blk, 0, s>>>(a)
+                                      : k_step_D_v2<T, AT, V, 32, false><<<g, blk, 0, s>>>(a));
+        }
+    }
     else k_step_D_v1<T, AT><<<a.n_tiles + aux, dim3(V1_TZ, V1_TY), 0, s>>>(a);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -471,6 +492,12 @@ int cev_fdtd_set_option(cev_fdtd* p, const char* name, int64_t value) {
     if (!strcmp(name, "kernel_variant")) {
         if (value < 0 || value > 2) return fail("kernel_variant must be 0 (auto), 1 (baseline) or 2 (marching)");
         p->variant = (int)value;
+    } else if (!strcmp(name, "prefetch_planes")) {
+        if (value < 0 || value > 64) return fail("prefetch_planes must be in [0, 64]");
+        p->pf_dist = (int)value;
+    } else if (!strcmp(name, "lanes_z")) {
+        if (value != 8 && value != 16 && value != 32) return fail("lanes_z must be 8, 16 or 32");
+        p->lz = (int)value;
     } else if (!strcmp(name, "xchunk")) {
         if (value < 0) return fail("xchunk must be >= 0");
         p->xchunk = (int)value;

@@ -52,6 +52,7 @@ struct StepArgs {
     const double* Jwave[3];   // nullable device scalar overriding Jscale (waveform entry)
     // tiling + auxiliary probe CTAs appended to the grid
     int n_tiles, ntz, nty, xchunk;
+    int pf_dist;              // L2 prefetch distance in x-planes (0 = off)
     ProbeTable pr;
     int        aux_slot0;     // first slot handled by the aux CTAs of this launch
     int64_t    t_probe;       // row of partials[] they write
@@ -66,12 +67,15 @@ __device__ __forceinline__ AT probe_value(const StepArgs<T, AT>& a, int field, i
     return (AT)a.Hin[c][cell];
 }
 
-// One CTA reduces one slot.  blockDim.x*blockDim.y threads, power of two <= 1024.
+// One CTA reduces one slot with its first PROBE_THREADS threads, whatever the CTA shape of the
+// kernel it rides on: the summation order (hence the series, bit for bit) is the same everywhere.
+constexpr int PROBE_THREADS = 128;
 template <typename T, typename AT>
 __device__ void probe_block(const StepArgs<T, AT>& a, int slot) {
-    __shared__ double red[1024];
+    __shared__ double red[PROBE_THREADS];
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-    const int nth = blockDim.x * blockDim.y;
+    if (tid >= PROBE_THREADS) return;       // CTAs have >= 128 threads; the rest sit out (no later barrier for them)
+    const int nth = PROBE_THREADS;
     const int field = a.pr.slot_field[slot];
     const int64_t n = a.pr.slot_n[slot];
     const int64_t wb = a.pr.slot_wbegin[slot];
@@ -83,10 +87,11 @@ __device__ void probe_block(const StepArgs<T, AT>& a, int slot) {
         acc += (double)probe_value<T, AT>(a, field, cell) * a.pr.weight[wb + q];
     }
     red[tid] = acc;
-    __syncthreads();
+    // named barrier over exactly the participating threads
+    asm volatile("bar.sync 1, %0;" ::"n"(PROBE_THREADS));
     for (int s = nth >> 1; s > 0; s >>= 1) {
         if (tid < s) red[tid] += red[tid + s];
-        __syncthreads();
+        asm volatile("bar.sync 1, %0;" ::"n"(PROBE_THREADS));
     }
     if (tid == 0) a.partials[a.t_probe * a.pr.n_slots + slot] = red[0];
 }

@@ -4,11 +4,16 @@
 // of row j and marches over a chunk of x-planes.  The x-neighbour plane (i+1 for the H half-step,
 // i-1 for the D half-step) is carried in registers from one iteration to the next, so every
 // plane of D / 1/eps / H is fetched from L2 once per chunk; the y-neighbour row is a second,
-// L1-resident vector load; the z-neighbour comes from the adjacent lane by warp shuffle (one
-// scalar load on the last / first lane of a warp).  All 9 (H) / 8 (D) vector loads of an
-// iteration are independent, which is what keeps enough bytes in flight to cover HBM latency.
-// PML: coefficients come from the per-axis tables; the cell-invariant parts are hoisted out of
-// the marching loop and the general formula only runs on x-PML planes (a CTA-uniform branch).
+// L1/L2-resident vector load; the z-neighbour comes from the adjacent lane by warp shuffle (one
+// scalar load on the last / first lane of a warp).  All vector loads of an iteration are
+// independent and issued up front.
+//
+// Register diet (occupancy is what buys HBM bandwidth here -- scripts/microbench/streams.cu shows
+// the same 12-stream marching pattern reaching ~7 TB/s when the kernel is lean): nothing PML-related
+// is carried across iterations.  A thread knows three flags (its row is in the y-PML, any of its
+// cells is in the z-PML, the current plane is in the x-PML); when none is set -- the bulk of the
+// grid -- the update is the vacuum one (m1 = 1, m2 = -+C0 dt); otherwise the general path re-reads
+// the tiny per-axis tables (L1-resident) for that cell.
 // Results are bit-identical to step_v1.cuh (same rounding sequence), which the tests assert.
 #pragma once
 #include "common.cuh"
@@ -29,59 +34,87 @@ __device__ __forceinline__ void stv(T* p, const Vec<T, V>& x) {
     *reinterpret_cast<Vec<T, V>*>(p) = x;
 }
 
-constexpr int V2_BY = 4;        // rows per CTA (one warp per row)
-constexpr int V2_MIN_CTAS = 4;  // register cap: 65536 / (4 * 128) = 128 per thread
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
-template <typename T, typename AT, int V>
-__global__ void __launch_bounds__(32 * V2_BY, V2_MIN_CTAS) k_step_H_v2(const StepArgs<T, AT> a) {
+constexpr int V2_BY = 4;        // warps per CTA; a warp covers LZ lanes along z times 32/LZ rows
+// register caps = 65536 / (MIN_CTAS * 128) per thread; tuned on B200 (scripts/tune.py): the H kernel
+// carries more state and prefers fewer, fatter CTAs; the D kernel prefers occupancy
+#ifndef V2_H_MIN_CTAS
+#define V2_H_MIN_CTAS 4
+#endif
+#ifndef V2_D_MIN_CTAS
+#define V2_D_MIN_CTAS 8
+#endif
+
+// General (PML) update of the three components of one cell.  IS_H selects the H or the D tables at
+// compile time (no address of the parameter struct is taken: it stays in the constant bank).
+template <typename T, typename AT, bool IS_H>
+__device__ __forceinline__ void pml_cell(const StepArgs<T, AT>& a, int i, int j, int k, AT s, const AT* old,
+                                         const AT* curl, AT* out) {
+#define TAB(name, ax) (IS_H ? a.name##H[ax] : a.name##D[ax])
+    const AT ux = TAB(u, 0)[i], uy = TAB(u, 1)[j], uz = TAB(u, 2)[k];
+    const AT rx = TAB(r, 0)[i], ry = TAB(r, 1)[j], rz = TAB(r, 2)[k];
+    const int mx = TAB(map, 0)[i], my = TAB(map, 1)[j], mz = TAB(map, 2)[k];
+    const int n1 = IS_H ? a.nH[1] : a.nD[1], n2 = IS_H ? a.nH[2] : a.nD[2];
+#undef TAB
+    T* const Ic0 = IS_H ? a.ICE[0] : a.ICH[0];
+    T* const Ic1 = IS_H ? a.ICE[1] : a.ICH[1];
+    T* const Ic2 = IS_H ? a.ICE[2] : a.ICH[2];
+    T* const Is0 = IS_H ? a.IH[0] : a.ID[0];
+    T* const Is1 = IS_H ? a.IH[1] : a.ID[1];
+    T* const Is2 = IS_H ? a.IH[2] : a.ID[2];
+    // x: (a,b) = (y,z), own x.   Icurl_x (nCx,Ny,Nz), Iself_x (Nx,nCy,nCz)
+    out[0] = update_component<T, AT>(old[0], curl[0], uy, ry, uz, rz, ux, s, Ic0,
+                                     mx >= 0 ? (int64_t)((mx * a.Ny + j) * a.Nz + k) : -1, Is0,
+                                     (my >= 0 && mz >= 0) ? (int64_t)((i * n1 + my) * n2 + mz) : -1);
+    // y: (a,b) = (x,z), own y.   Icurl_y (Nx,nCy,Nz), Iself_y (nCx,Ny,nCz)
+    out[1] = update_component<T, AT>(old[1], curl[1], ux, rx, uz, rz, uy, s, Ic1,
+                                     my >= 0 ? (int64_t)((i * n1 + my) * a.Nz + k) : -1, Is1,
+                                     (mx >= 0 && mz >= 0) ? (int64_t)((mx * a.Ny + j) * n2 + mz) : -1);
+    // z: (a,b) = (x,y), own z.   Icurl_z (Nx,Ny,nCz), Iself_z (nCx,nCy,Nz)
+    out[2] = update_component<T, AT>(old[2], curl[2], ux, rx, uy, ry, uz, s, Ic2,
+                                     mz >= 0 ? (int64_t)((i * a.Ny + j) * n2 + mz) : -1, Is2,
+                                     (mx >= 0 && my >= 0) ? (int64_t)((mx * n1 + my) * a.Nz + k) : -1);
+}
+
+template <typename T, typename AT, int V, int LZ>
+__global__ void __launch_bounds__(32 * V2_BY, V2_H_MIN_CTAS) k_step_H_v2(const StepArgs<T, AT> a) {
     const int bid = blockIdx.x;
     if (bid >= a.n_tiles) {
         probe_block<T, AT>(a, a.aux_slot0 + (bid - a.n_tiles));
         return;
     }
+    constexpr int RW = 32 / LZ;                  // rows per warp
     const int lane = threadIdx.x;
+    const int lz = lane % LZ, ly = lane / LZ;
     const int tz = bid % a.ntz;
     const int rest = bid / a.ntz;
     const int ty = rest % a.nty;
     const int xc = rest / a.nty;
-    const int j = ty * V2_BY + threadIdx.y;
-    if (j >= a.Ny) return;                       // warp-uniform
-    const int k0raw = (tz * 32 + lane) * V;
-    const bool active = k0raw < a.Nz;
-    const int k0 = active ? k0raw : 0;           // inactive lanes shadow cell 0 (loads only)
+    const int jraw = (ty * V2_BY + threadIdx.y) * RW + ly;
+    if (jraw - ly >= a.Ny) return;               // warp-uniform: the whole warp is below the grid
+    const int k0raw = (tz * LZ + lz) * V;
+    const bool active = k0raw < a.Nz && jraw < a.Ny;
+    const int j = jraw < a.Ny ? jraw : a.Ny - 1; // inactive lanes shadow a valid cell (loads only)
+    const int k0 = k0raw < a.Nz ? k0raw : 0;
     const int xs = a.x0 + xc * a.xchunk;
     const int xe = min(xs + a.xchunk, a.x1);
 
     const int plane = a.Ny * a.Nz;
     const int jp = (j + 1 == a.Ny) ? 0 : j + 1;
-    const bool z_edge = (lane == 31) || (k0 + V >= a.Nz);   // +1 neighbour not in lane+1
+    const bool z_edge = (lz == LZ - 1) || (k0 + V >= a.Nz);   // +1 neighbour not in lane+1
     const int kp = (k0 + V >= a.Nz) ? 0 : k0 + V;
     const int orow = j * a.Nz + k0;
     const int orow_jp = jp * a.Nz + k0;
     const int okp = j * a.Nz + kp;
 
-    // cell-invariant PML data
-    const AT uy = a.uH[1][j], ry = a.rH[1][j];
-    const int my = a.mapH[1][j];
-    AT uz[V], rz[V];
-    int mz[V];
+    bool yz_pml = a.mapH[1][j] >= 0;
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-        uz[e] = a.uH[2][k0 + e];
-        rz[e] = a.rH[2][k0 + e];
-        mz[e] = a.mapH[2][k0 + e];
-    }
+    for (int e = 0; e < V; ++e) yz_pml |= a.mapH[2][k0 + e] >= 0;
     const AT s = -a.cdt;
-    const AT zero = AT(0), one = AT(1);
-    // coefficients off the x-PML (ux = 0): hoisted
-    // m1, m2 off the x-PML (ux = 0, rx = 1): hoisted out of the marching loop
-    AT m1x[V], m2x[V], m1y0[V], m2y0[V], m1z0, m2z0;
-#pragma unroll
-    for (int e = 0; e < V; ++e) {
-        coef12<AT>(uy, ry, uz[e], rz[e], s, m1x[e], m2x[e]);
-        coef12<AT>(zero, one, uz[e], rz[e], s, m1y0[e], m2y0[e]);
-    }
-    coef12<AT>(zero, one, uy, ry, s, m1z0, m2z0);
+    const AT inv = a.inv_dL;
 
     // E = mE*D of the current plane (own cells)
     AT Ecur[3][V];
@@ -98,7 +131,7 @@ __global__ void __launch_bounds__(32 * V2_BY, V2_MIN_CTAS) k_step_H_v2(const Ste
     for (int i = xs; i < xe; ++i) {
         const int pbase = i * plane;
         const bool last = (i + 1 == a.Nx);
-        // ---- issue every load of this iteration up front
+        // ---- every load of this iteration, up front
         Vec<T, V> dn[3], mn[3], h[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -116,16 +149,21 @@ __global__ void __launch_bounds__(32 * V2_BY, V2_MIN_CTAS) k_step_H_v2(const Ste
             ex_kp = mul_rn((AT)a.mE[0][pbase + okp], (AT)a.Din[0][pbase + okp]);
             ey_kp = mul_rn((AT)a.mE[1][pbase + okp], (AT)a.Din[1][pbase + okp]);
         }
-        const AT ux = a.uH[0][i], rx = a.rH[0][i];
-        const int mx = a.mapH[0][i];
-
-        AT Enext[3][V];
+        if (a.pf_dist > 0 && (lz & 7) == 0 && i + a.pf_dist < xe) {   // one lane per 128-byte line
+            const int po = (i + a.pf_dist) * plane + orow;
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int e = 0; e < V; ++e) Enext[c][e] = mul_rn((AT)mn[c].v[e], (AT)dn[c].v[e]);
+            for (int c = 0; c < 3; ++c) {
+                prefetch_l2(a.Hin[c] + po);
+                if (i + a.pf_dist + 1 < a.Nx) {
+                    prefetch_l2(a.Din[c] + po + plane);
+                    prefetch_l2(a.mE[c] + po + plane);
+                }
+            }
+        }
+        const bool pml = yz_pml || (a.mapH[0][i] >= 0);
 
-        Vec<T, V> out[3];
+        // ---- curls (consume the neighbour loads); E of the next plane becomes current
+        AT CE[3][V];
 #pragma unroll
         for (int e = 0; e < V; ++e) {
             const AT Ex = Ecur[0][e], Ey = Ecur[1][e], Ez = Ecur[2][e];
@@ -133,94 +171,84 @@ __global__ void __launch_bounds__(32 * V2_BY, V2_MIN_CTAS) k_step_H_v2(const Ste
             const AT Ez_jp = mul_rn((AT)mzj.v[e], (AT)dzj.v[e]);
             const AT Ex_kp = (e + 1 < V) ? Ecur[0][(e + 1) % V] : ex_kp;
             const AT Ey_kp = (e + 1 < V) ? Ecur[1][(e + 1) % V] : ey_kp;
-            const AT CEx = curl2<AT>(Ez_jp, Ez, Ey_kp, Ey, a.inv_dL);
-            const AT CEy = curl2<AT>(Ex_kp, Ex, Enext[2][e], Ez, a.inv_dL);
-            const AT CEz = curl2<AT>(Enext[1][e], Ey, Ex_jp, Ex, a.inv_dL);
-            const int k = k0 + e;
-            AT m1y = m1y0[e], m2y = m2y0[e], m1z = m1z0, m2z = m2z0;
-            int ic0 = -1, is0 = -1, ic1 = -1, is1 = -1, ic2 = -1, is2 = -1;
-            if (mx >= 0) {   // x-PML plane: CTA-uniform
-                coef12<AT>(ux, rx, uz[e], rz[e], s, m1y, m2y);
-                coef12<AT>(ux, rx, uy, ry, s, m1z, m2z);
-                ic0 = (mx * a.Ny + j) * a.Nz + k;
-                if (mz[e] >= 0) is1 = (mx * a.Ny + j) * a.nH[2] + mz[e];
-                if (my >= 0) is2 = (mx * a.nH[1] + my) * a.Nz + k;
-            }
-            if (my >= 0) {
-                ic1 = (i * a.nH[1] + my) * a.Nz + k;
-                if (mz[e] >= 0) is0 = (i * a.nH[1] + my) * a.nH[2] + mz[e];
-            }
-            if (mz[e] >= 0) ic2 = (i * a.Ny + j) * a.nH[2] + mz[e];
-            if (active) {
-                out[0].v[e] = (T)update_cell<T, AT>((AT)h[0].v[e], CEx, m1x[e], m2x[e], uy, ry, uz[e], rz[e], ux, s,
-                                                    a.ICE[0], ic0, a.IH[0], is0);
-                out[1].v[e] = (T)update_cell<T, AT>((AT)h[1].v[e], CEy, m1y, m2y, ux, rx, uz[e], rz[e], uy, s,
-                                                    a.ICE[1], ic1, a.IH[1], is1);
-                out[2].v[e] = (T)update_cell<T, AT>((AT)h[2].v[e], CEz, m1z, m2z, ux, rx, uy, ry, uz[e], s,
-                                                    a.ICE[2], ic2, a.IH[2], is2);
-            }
+            const AT Ey_ip = mul_rn((AT)mn[1].v[e], (AT)dn[1].v[e]);
+            const AT Ez_ip = mul_rn((AT)mn[2].v[e], (AT)dn[2].v[e]);
+            CE[0][e] = curl2<AT>(Ez_jp, Ez, Ey_kp, Ey, inv);
+            CE[1][e] = curl2<AT>(Ex_kp, Ex, Ez_ip, Ez, inv);
+            CE[2][e] = curl2<AT>(Ey_ip, Ey, Ex_jp, Ex, inv);
         }
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            Ecur[0][e] = mul_rn((AT)mn[0].v[e], (AT)dn[0].v[e]);
+            Ecur[1][e] = mul_rn((AT)mn[1].v[e], (AT)dn[1].v[e]);
+            Ecur[2][e] = mul_rn((AT)mn[2].v[e], (AT)dn[2].v[e]);
+        }
+
+        // ---- update
         if (active) {
+            Vec<T, V> out[3];
+            if (!pml) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int e = 0; e < V; ++e)   // m1 = 1, m2 = -C0 dt: exactly what the general formula gives off the PML
+                        out[c].v[e] = (T)add_rn((AT)h[c].v[e], mul_rn(s, CE[c][e]));
+            } else {
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    AT old[3] = {(AT)h[0].v[e], (AT)h[1].v[e], (AT)h[2].v[e]};
+                    AT curl[3] = {CE[0][e], CE[1][e], CE[2][e]};
+                    AT o3[3];
+                    pml_cell<T, AT, true>(a, i, j, k0 + e, s, old, curl, o3);
+                    out[0].v[e] = (T)o3[0];
+                    out[1].v[e] = (T)o3[1];
+                    out[2].v[e] = (T)o3[2];
+                }
+            }
 #pragma unroll
             for (int c = 0; c < 3; ++c) stv<T, V>(a.Hout[c] + pbase + orow, out[c]);
         }
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int e = 0; e < V; ++e) Ecur[c][e] = Enext[c][e];
     }
 }
 
 // EXTRAS = dense J input and/or E output (the per-step forward() API); the fused run() path
 // instantiates EXTRAS = false and carries neither.
-template <typename T, typename AT, int V, bool EXTRAS>
-__global__ void __launch_bounds__(32 * V2_BY, V2_MIN_CTAS) k_step_D_v2(const StepArgs<T, AT> a) {
+template <typename T, typename AT, int V, int LZ, bool EXTRAS>
+__global__ void __launch_bounds__(32 * V2_BY, V2_D_MIN_CTAS) k_step_D_v2(const StepArgs<T, AT> a) {
     const int bid = blockIdx.x;
     if (bid >= a.n_tiles) {
         probe_block<T, AT>(a, a.aux_slot0 + (bid - a.n_tiles));
         return;
     }
+    constexpr int RW = 32 / LZ;                  // rows per warp
     const int lane = threadIdx.x;
+    const int lz = lane % LZ, ly = lane / LZ;
     const int tz = bid % a.ntz;
     const int rest = bid / a.ntz;
     const int ty = rest % a.nty;
     const int xc = rest / a.nty;
-    const int j = ty * V2_BY + threadIdx.y;
-    if (j >= a.Ny) return;
-    const int k0raw = (tz * 32 + lane) * V;
-    const bool active = k0raw < a.Nz;
-    const int k0 = active ? k0raw : 0;
+    const int jraw = (ty * V2_BY + threadIdx.y) * RW + ly;
+    if (jraw - ly >= a.Ny) return;               // warp-uniform: the whole warp is below the grid
+    const int k0raw = (tz * LZ + lz) * V;
+    const bool active = k0raw < a.Nz && jraw < a.Ny;
+    const int j = jraw < a.Ny ? jraw : a.Ny - 1; // inactive lanes shadow a valid cell (loads only)
+    const int k0 = k0raw < a.Nz ? k0raw : 0;
     const int xs = a.x0 + xc * a.xchunk;
     const int xe = min(xs + a.xchunk, a.x1);
 
     const int plane = a.Ny * a.Nz;
     const int jm = (j == 0) ? a.Ny - 1 : j - 1;
-    const bool z_edge = (lane == 0) || (k0 == 0);
+    const bool z_edge = (lz == 0) || (k0 == 0);
     const int km = (k0 == 0) ? a.Nz - 1 : k0 - 1;
     const int orow = j * a.Nz + k0;
     const int orow_jm = jm * a.Nz + k0;
     const int okm = j * a.Nz + km;
 
-    const AT uy = a.uD[1][j], ry = a.rD[1][j];
-    const int my = a.mapD[1][j];
-    AT uz[V], rz[V];
-    int mz[V];
+    bool yz_pml = a.mapD[1][j] >= 0;
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-        uz[e] = a.uD[2][k0 + e];
-        rz[e] = a.rD[2][k0 + e];
-        mz[e] = a.mapD[2][k0 + e];
-    }
+    for (int e = 0; e < V; ++e) yz_pml |= a.mapD[2][k0 + e] >= 0;
     const AT s = a.cdt;
-    const AT zero = AT(0), one = AT(1);
-    // m1, m2 off the x-PML (ux = 0, rx = 1): hoisted out of the marching loop
-    AT m1x[V], m2x[V], m1y0[V], m2y0[V], m1z0, m2z0;
-#pragma unroll
-    for (int e = 0; e < V; ++e) {
-        coef12<AT>(uy, ry, uz[e], rz[e], s, m1x[e], m2x[e]);
-        coef12<AT>(zero, one, uz[e], rz[e], s, m1y0[e], m2y0[e]);
-    }
-    coef12<AT>(zero, one, uy, ry, s, m1z0, m2z0);
+    const AT inv = a.inv_dL;
 
     // H of the previous plane (own cells), y and z components
     AT Hprev[2][V];
@@ -252,59 +280,63 @@ __global__ void __launch_bounds__(32 * V2_BY, V2_MIN_CTAS) k_step_D_v2(const Ste
             hx_km = (AT)a.Hin[0][pbase + okm];
             hy_km = (AT)a.Hin[1][pbase + okm];
         }
-        const AT ux = a.uD[0][i], rx = a.rD[0][i];
-        const int mx = a.mapD[0][i];
+        if (a.pf_dist > 0 && (lz & 7) == 0 && i + a.pf_dist < xe) {
+            const int po = (i + a.pf_dist) * plane + orow;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                prefetch_l2(a.Hin[c] + po);
+                prefetch_l2(a.Din[c] + po);
+            }
+        }
+        const bool pml = yz_pml || (a.mapD[0][i] >= 0);
 
-        Vec<T, V> out[3], eout[3];
+        AT CH[3][V];
 #pragma unroll
         for (int e = 0; e < V; ++e) {
             const AT Hx = (AT)h[0].v[e], Hy = (AT)h[1].v[e], Hz = (AT)h[2].v[e];
             const AT Hx_km = (e > 0) ? (AT)h[0].v[(e + V - 1) % V] : hx_km;
             const AT Hy_km = (e > 0) ? (AT)h[1].v[(e + V - 1) % V] : hy_km;
-            const AT CHx = curl2<AT>(Hz, (AT)hzj.v[e], Hy, Hy_km, a.inv_dL);
-            const AT CHy = curl2<AT>(Hx, Hx_km, Hz, Hprev[1][e], a.inv_dL);
-            const AT CHz = curl2<AT>(Hy, Hprev[0][e], Hx, (AT)hxj.v[e], a.inv_dL);
-            const int k = k0 + e;
-            AT m1y = m1y0[e], m2y = m2y0[e], m1z = m1z0, m2z = m2z0;
-            int ic0 = -1, is0 = -1, ic1 = -1, is1 = -1, ic2 = -1, is2 = -1;
-            if (mx >= 0) {   // x-PML plane: CTA-uniform
-                coef12<AT>(ux, rx, uz[e], rz[e], s, m1y, m2y);
-                coef12<AT>(ux, rx, uy, ry, s, m1z, m2z);
-                ic0 = (mx * a.Ny + j) * a.Nz + k;
-                if (mz[e] >= 0) is1 = (mx * a.Ny + j) * a.nD[2] + mz[e];
-                if (my >= 0) is2 = (mx * a.nD[1] + my) * a.Nz + k;
-            }
-            if (my >= 0) {
-                ic1 = (i * a.nD[1] + my) * a.Nz + k;
-                if (mz[e] >= 0) is0 = (i * a.nD[1] + my) * a.nD[2] + mz[e];
-            }
-            if (mz[e] >= 0) ic2 = (i * a.Ny + j) * a.nD[2] + mz[e];
-            if (active) {
-                AT dn[3];
-                dn[0] = update_cell<T, AT>((AT)d[0].v[e], CHx, m1x[e], m2x[e], uy, ry, uz[e], rz[e], ux, s,
-                                           a.ICH[0], ic0, a.ID[0], is0);
-                dn[1] = update_cell<T, AT>((AT)d[1].v[e], CHy, m1y, m2y, ux, rx, uz[e], rz[e], uy, s,
-                                           a.ICH[1], ic1, a.ID[1], is1);
-                dn[2] = update_cell<T, AT>((AT)d[2].v[e], CHz, m1z, m2z, ux, rx, uy, ry, uz[e], s,
-                                           a.ICH[2], ic2, a.ID[2], is2);
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    if (EXTRAS && a.J[c]) {
-                        const AT sc = a.Jwave[c] ? (AT)(*a.Jwave[c]) : a.Jscale[c];
-                        dn[c] = add_rn(dn[c], mul_rn((AT)jv[c].v[e], sc));
-                    }
-                    out[c].v[e] = (T)dn[c];
-                    if (EXTRAS && a.Eout[c]) eout[c].v[e] = (T)mul_rn((AT)mev[c].v[e], (AT)out[c].v[e]);
-                }
-            }
+            CH[0][e] = curl2<AT>(Hz, (AT)hzj.v[e], Hy, Hy_km, inv);
+            CH[1][e] = curl2<AT>(Hx, Hx_km, Hz, Hprev[1][e], inv);
+            CH[2][e] = curl2<AT>(Hy, Hprev[0][e], Hx, (AT)hxj.v[e], inv);
             Hprev[0][e] = Hy;
             Hprev[1][e] = Hz;
         }
+
         if (active) {
+            Vec<T, V> out[3];
+            if (!pml) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int e = 0; e < V; ++e) out[c].v[e] = (T)add_rn((AT)d[c].v[e], mul_rn(s, CH[c][e]));
+            } else {
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    AT old[3] = {(AT)d[0].v[e], (AT)d[1].v[e], (AT)d[2].v[e]};
+                    AT curl[3] = {CH[0][e], CH[1][e], CH[2][e]};
+                    AT o3[3];
+                    pml_cell<T, AT, false>(a, i, j, k0 + e, s, old, curl, o3);
+                    out[0].v[e] = (T)o3[0];
+                    out[1].v[e] = (T)o3[1];
+                    out[2].v[e] = (T)o3[2];
+                }
+            }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
+                if (EXTRAS) {
+                    Vec<T, V> eo;
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        if (a.J[c]) {
+                            const AT sc = a.Jwave[c] ? (AT)(*a.Jwave[c]) : a.Jscale[c];
+                            out[c].v[e] = (T)add_rn((AT)out[c].v[e], mul_rn((AT)jv[c].v[e], sc));
+                        }
+                        if (a.Eout[c]) eo.v[e] = (T)mul_rn((AT)mev[c].v[e], (AT)out[c].v[e]);
+                    }
+                    if (a.Eout[c]) stv<T, V>(a.Eout[c] + pbase + orow, eo);
+                }
                 stv<T, V>(a.Dout[c] + pbase + orow, out[c]);
-                if (EXTRAS && a.Eout[c]) stv<T, V>(a.Eout[c] + pbase + orow, eout[c]);
             }
         }
     }
