@@ -42,42 +42,115 @@ constexpr int V2_BY = 4;        // warps per CTA; a warp covers LZ lanes along z
 // register caps = 65536 / (MIN_CTAS * 128) per thread; tuned on B200 (scripts/tune.py): the H kernel
 // carries more state and prefers fewer, fatter CTAs; the D kernel prefers occupancy
 #ifndef V2_H_MIN_CTAS
-#define V2_H_MIN_CTAS 4
+#define V2_H_MIN_CTAS 3
 #endif
 #ifndef V2_D_MIN_CTAS
-#define V2_D_MIN_CTAS 8
+#define V2_D_MIN_CTAS 5
 #endif
 
-// General (PML) update of the three components of one cell.  IS_H selects the H or the D tables at
-// compile time (no address of the parameter struct is taken: it stays in the constant bank).
-template <typename T, typename AT, bool IS_H>
-__device__ __forceinline__ void pml_cell(const StepArgs<T, AT>& a, int i, int j, int k, AT s, const AT* old,
-                                         const AT* curl, AT* out) {
-#define TAB(name, ax) (IS_H ? a.name##H[ax] : a.name##D[ax])
-    const AT ux = TAB(u, 0)[i], uy = TAB(u, 1)[j], uz = TAB(u, 2)[k];
-    const AT rx = TAB(r, 0)[i], ry = TAB(r, 1)[j], rz = TAB(r, 2)[k];
-    const int mx = TAB(map, 0)[i], my = TAB(map, 1)[j], mz = TAB(map, 2)[k];
-    const int n1 = IS_H ? a.nH[1] : a.nD[1], n2 = IS_H ? a.nH[2] : a.nD[2];
-#undef TAB
-    T* const Ic0 = IS_H ? a.ICE[0] : a.ICH[0];
-    T* const Ic1 = IS_H ? a.ICE[1] : a.ICH[1];
-    T* const Ic2 = IS_H ? a.ICE[2] : a.ICH[2];
-    T* const Is0 = IS_H ? a.IH[0] : a.ID[0];
-    T* const Is1 = IS_H ? a.IH[1] : a.ID[1];
-    T* const Is2 = IS_H ? a.IH[2] : a.ID[2];
-    // x: (a,b) = (y,z), own x.   Icurl_x (nCx,Ny,Nz), Iself_x (Nx,nCy,nCz)
-    out[0] = update_component<T, AT>(old[0], curl[0], uy, ry, uz, rz, ux, s, Ic0,
-                                     mx >= 0 ? (int64_t)((mx * a.Ny + j) * a.Nz + k) : -1, Is0,
-                                     (my >= 0 && mz >= 0) ? (int64_t)((i * n1 + my) * n2 + mz) : -1);
-    // y: (a,b) = (x,z), own y.   Icurl_y (Nx,nCy,Nz), Iself_y (nCx,Ny,nCz)
-    out[1] = update_component<T, AT>(old[1], curl[1], ux, rx, uz, rz, uy, s, Ic1,
-                                     my >= 0 ? (int64_t)((i * n1 + my) * a.Nz + k) : -1, Is1,
-                                     (mx >= 0 && mz >= 0) ? (int64_t)((mx * a.Ny + j) * n2 + mz) : -1);
-    // z: (a,b) = (x,y), own z.   Icurl_z (Nx,Ny,nCz), Iself_z (nCx,nCy,Nz)
-    out[2] = update_component<T, AT>(old[2], curl[2], ux, rx, uy, ry, uz, s, Ic2,
-                                     mz >= 0 ? (int64_t)((i * a.Ny + j) * n2 + mz) : -1, Is2,
-                                     (mx >= 0 && my >= 0) ? (int64_t)((mx * n1 + my) * a.Nz + k) : -1);
-}
+// PML work of one thread for one x-plane.  load() is called right after the main loads of the
+// iteration are issued: it fetches the old values of the curl integrals (vector loads for the x- and
+// y-slab arrays, whose z-runs are contiguous) and the table entries, so that their latency overlaps
+// the field loads instead of adding a second memory round trip.  apply() then does the general
+// update of fdtd.py:85-97 / :110-122 for the V cells.  IS_H selects the H or D tables at compile
+// time (no address of the parameter struct is taken: it stays in the constant bank).
+template <typename T, typename AT, int V, bool IS_H>
+struct PmlCtx {
+    AT ux, rx, uy, ry, uz[V], rz[V];
+    Vec<T, V> I0, I1;     // old Icurl_x / Icurl_y runs
+    T I2[V];              // old Icurl_z cells
+    int ic0, ic1;         // run offsets (or -1)
+
+#define CEV_TAB(a, name, ax) (IS_H ? (a).name##H[ax] : (a).name##D[ax])
+    __device__ __forceinline__ void load(const StepArgs<T, AT>& a, int i, int j, int k0, int mx, int my, const int* mz) {
+        const int n1 = IS_H ? a.nH[1] : a.nD[1], n2 = IS_H ? a.nH[2] : a.nD[2];
+        T* const* Ic = IS_H ? a.ICE : a.ICH;
+        ux = CEV_TAB(a, u, 0)[i];
+        rx = CEV_TAB(a, r, 0)[i];
+        uy = CEV_TAB(a, u, 1)[j];
+        ry = CEV_TAB(a, r, 1)[j];
+        ic0 = mx >= 0 ? (mx * a.Ny + j) * a.Nz + k0 : -1;      // Icurl_x (nCx,Ny,Nz)
+        ic1 = my >= 0 ? (i * n1 + my) * a.Nz + k0 : -1;        // Icurl_y (Nx,nCy,Nz)
+        if (ic0 >= 0) I0 = ldv<T, V>(Ic[0] + ic0);
+        if (ic1 >= 0) I1 = ldv<T, V>(Ic[1] + ic1);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            uz[e] = CEV_TAB(a, u, 2)[k0 + e];
+            rz[e] = CEV_TAB(a, r, 2)[k0 + e];
+            if (mz[e] >= 0) I2[e] = Ic[2][(i * a.Ny + j) * n2 + mz[e]];   // Icurl_z (Nx,Ny,nCz)
+        }
+    }
+
+    // old[c][e], curl[c][e] -> out[c].v[e]
+    __device__ __forceinline__ void apply(const StepArgs<T, AT>& a, int i, int j, int k0, int mx, int my, const int* mz,
+                                          AT s, const Vec<T, V>* old, const AT (*curl)[V], Vec<T, V>* out) {
+        const int n1 = IS_H ? a.nH[1] : a.nD[1], n2 = IS_H ? a.nH[2] : a.nD[2];
+        T* const* Ic = IS_H ? a.ICE : a.ICH;
+        T* const* Is = IS_H ? a.IH : a.ID;
+        Vec<T, V> n0, n1v;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const int k = k0 + e;
+            // x: (a,b) = (y,z), own x.   Iself_x (Nx,nCy,nCz)
+            {
+                AT m1, m2;
+                coef12<AT>(uy, ry, uz[e], rz[e], s, m1, m2);
+                AT v = add_rn(mul_rn(m1, (AT)old[0].v[e]), mul_rn(m2, curl[0][e]));
+                if (ic0 >= 0) {
+                    const AT I = (AT)I0.v[e] + curl[0][e];
+                    n0.v[e] = (T)I;
+                    v = add_rn(v, mul_rn(mul_rn(mul_rn(s, ux + ux), mul_rn(ry, rz[e])), I));
+                }
+                if (my >= 0 && mz[e] >= 0) {
+                    T* q = Is[0] + (i * n1 + my) * n2 + mz[e];
+                    const AT I = (AT)*q + (AT)old[0].v[e];
+                    *q = (T)I;
+                    v = add_rn(v, mul_rn(mul_rn(mul_rn(mul_rn(AT(-4), uy), uz[e]), mul_rn(ry, rz[e])), I));
+                }
+                out[0].v[e] = (T)v;
+            }
+            // y: (a,b) = (x,z), own y.   Iself_y (nCx,Ny,nCz)
+            {
+                AT m1, m2;
+                coef12<AT>(ux, rx, uz[e], rz[e], s, m1, m2);
+                AT v = add_rn(mul_rn(m1, (AT)old[1].v[e]), mul_rn(m2, curl[1][e]));
+                if (ic1 >= 0) {
+                    const AT I = (AT)I1.v[e] + curl[1][e];
+                    n1v.v[e] = (T)I;
+                    v = add_rn(v, mul_rn(mul_rn(mul_rn(s, uy + uy), mul_rn(rx, rz[e])), I));
+                }
+                if (mx >= 0 && mz[e] >= 0) {
+                    T* q = Is[1] + (mx * a.Ny + j) * n2 + mz[e];
+                    const AT I = (AT)*q + (AT)old[1].v[e];
+                    *q = (T)I;
+                    v = add_rn(v, mul_rn(mul_rn(mul_rn(mul_rn(AT(-4), ux), uz[e]), mul_rn(rx, rz[e])), I));
+                }
+                out[1].v[e] = (T)v;
+            }
+            // z: (a,b) = (x,y), own z.   Iself_z (nCx,nCy,Nz)
+            {
+                AT m1, m2;
+                coef12<AT>(ux, rx, uy, ry, s, m1, m2);
+                AT v = add_rn(mul_rn(m1, (AT)old[2].v[e]), mul_rn(m2, curl[2][e]));
+                if (mz[e] >= 0) {
+                    const AT I = (AT)I2[e] + curl[2][e];
+                    Ic[2][(i * a.Ny + j) * n2 + mz[e]] = (T)I;
+                    v = add_rn(v, mul_rn(mul_rn(mul_rn(s, uz[e] + uz[e]), mul_rn(rx, ry)), I));
+                }
+                if (mx >= 0 && my >= 0) {
+                    T* q = Is[2] + (mx * n1 + my) * a.Nz + k;
+                    const AT I = (AT)*q + (AT)old[2].v[e];
+                    *q = (T)I;
+                    v = add_rn(v, mul_rn(mul_rn(mul_rn(mul_rn(AT(-4), ux), uy), mul_rn(rx, ry)), I));
+                }
+                out[2].v[e] = (T)v;
+            }
+        }
+        if (ic0 >= 0) stv<T, V>(Ic[0] + ic0, n0);
+        if (ic1 >= 0) stv<T, V>(Ic[1] + ic1, n1v);
+    }
+#undef CEV_TAB
+};
 
 template <typename T, typename AT, int V, int LZ>
 __global__ void __launch_bounds__(32 * V2_BY, V2_H_MIN_CTAS) k_step_H_v2(const StepArgs<T, AT> a) {
@@ -110,9 +183,14 @@ __global__ void __launch_bounds__(32 * V2_BY, V2_H_MIN_CTAS) k_step_H_v2(const S
     const int orow_jp = jp * a.Nz + k0;
     const int okp = j * a.Nz + kp;
 
-    bool yz_pml = a.mapH[1][j] >= 0;
+    const int my = a.mapH[1][j];
+    int mz[V];
+    bool yz_pml = my >= 0;
 #pragma unroll
-    for (int e = 0; e < V; ++e) yz_pml |= a.mapH[2][k0 + e] >= 0;
+    for (int e = 0; e < V; ++e) {
+        mz[e] = a.mapH[2][k0 + e];
+        yz_pml |= mz[e] >= 0;
+    }
     const AT s = -a.cdt;
     const AT inv = a.inv_dL;
 
@@ -160,7 +238,10 @@ __global__ void __launch_bounds__(32 * V2_BY, V2_H_MIN_CTAS) k_step_H_v2(const S
                 }
             }
         }
-        const bool pml = yz_pml || (a.mapH[0][i] >= 0);
+        const int mx = a.mapH[0][i];
+        const bool pml = yz_pml || mx >= 0;
+        PmlCtx<T, AT, V, true> ctx;
+        if (pml) ctx.load(a, i, j, k0, mx, my, mz);
 
         // ---- curls (consume the neighbour loads); E of the next plane becomes current
         AT CE[3][V];
@@ -194,16 +275,7 @@ __global__ void __launch_bounds__(32 * V2_BY, V2_H_MIN_CTAS) k_step_H_v2(const S
                     for (int e = 0; e < V; ++e)   // m1 = 1, m2 = -C0 dt: exactly what the general formula gives off the PML
                         out[c].v[e] = (T)add_rn((AT)h[c].v[e], mul_rn(s, CE[c][e]));
             } else {
-#pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    AT old[3] = {(AT)h[0].v[e], (AT)h[1].v[e], (AT)h[2].v[e]};
-                    AT curl[3] = {CE[0][e], CE[1][e], CE[2][e]};
-                    AT o3[3];
-                    pml_cell<T, AT, true>(a, i, j, k0 + e, s, old, curl, o3);
-                    out[0].v[e] = (T)o3[0];
-                    out[1].v[e] = (T)o3[1];
-                    out[2].v[e] = (T)o3[2];
-                }
+                ctx.apply(a, i, j, k0, mx, my, mz, s, h, CE, out);
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) stv<T, V>(a.Hout[c] + pbase + orow, out[c]);
@@ -244,9 +316,14 @@ __global__ void __launch_bounds__(32 * V2_BY, V2_D_MIN_CTAS) k_step_D_v2(const S
     const int orow_jm = jm * a.Nz + k0;
     const int okm = j * a.Nz + km;
 
-    bool yz_pml = a.mapD[1][j] >= 0;
+    const int my = a.mapD[1][j];
+    int mz[V];
+    bool yz_pml = my >= 0;
 #pragma unroll
-    for (int e = 0; e < V; ++e) yz_pml |= a.mapD[2][k0 + e] >= 0;
+    for (int e = 0; e < V; ++e) {
+        mz[e] = a.mapD[2][k0 + e];
+        yz_pml |= mz[e] >= 0;
+    }
     const AT s = a.cdt;
     const AT inv = a.inv_dL;
 
@@ -288,7 +365,10 @@ __global__ void __launch_bounds__(32 * V2_BY, V2_D_MIN_CTAS) k_step_D_v2(const S
                 prefetch_l2(a.Din[c] + po);
             }
         }
-        const bool pml = yz_pml || (a.mapD[0][i] >= 0);
+        const int mx = a.mapD[0][i];
+        const bool pml = yz_pml || mx >= 0;
+        PmlCtx<T, AT, V, false> ctx;
+        if (pml) ctx.load(a, i, j, k0, mx, my, mz);
 
         AT CH[3][V];
 #pragma unroll
@@ -311,16 +391,7 @@ __global__ void __launch_bounds__(32 * V2_BY, V2_D_MIN_CTAS) k_step_D_v2(const S
 #pragma unroll
                     for (int e = 0; e < V; ++e) out[c].v[e] = (T)add_rn((AT)d[c].v[e], mul_rn(s, CH[c][e]));
             } else {
-#pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    AT old[3] = {(AT)d[0].v[e], (AT)d[1].v[e], (AT)d[2].v[e]};
-                    AT curl[3] = {CH[0][e], CH[1][e], CH[2][e]};
-                    AT o3[3];
-                    pml_cell<T, AT, false>(a, i, j, k0 + e, s, old, curl, o3);
-                    out[0].v[e] = (T)o3[0];
-                    out[1].v[e] = (T)o3[1];
-                    out[2].v[e] = (T)o3[2];
-                }
+                ctx.apply(a, i, j, k0, mx, my, mz, s, d, CH, out);
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
