@@ -4,6 +4,8 @@ Scope: the hot path of ceviche.fdtd.forward() (Yee-grid curl updates, sigma-PML,
 its caller loop and its eps_r derivatives -- nothing else of ceviche."""
 from .constants import C_0, EPSILON_0, ETA_0, MU_0
 from .fdtd import fdtd
+from .jacobians import jacobian
+from . import utils
 
 __version__ = "0.1.0"
-__all__ = ["fdtd", "C_0", "EPSILON_0", "MU_0", "ETA_0"]
+__all__ = ["fdtd", "jacobian", "utils", "C_0", "EPSILON_0", "MU_0", "ETA_0"]

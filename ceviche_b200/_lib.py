@@ -26,6 +26,14 @@ class cev_points(C.Structure):
                 ("weight", C.c_void_p)]
 
 
+class cev_tangent(C.Structure):
+    _fields_ = [("d_inv_eps", c_void_p3), ("D_primal", c_void_p3)]
+
+
+class cev_adjoint(C.Structure):
+    _fields_ = [(n, c_void_p3) for n in ("lH", "lD", "lICE", "lIH", "lICH", "lID", "gC", "gC2", "G_mE")]
+
+
 class CevicheB200Error(RuntimeError):
     pass
 
@@ -43,7 +51,16 @@ def _declare(lib):
         "cev_fdtd_step_H": [C.c_void_p, P(cev_state), C.c_void_p, C.c_int64, C.c_int64, C.c_void_p],
         "cev_fdtd_step_D": [C.c_void_p, P(cev_state), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                             C.c_int64, C.c_int64, C.c_void_p],
-        "cev_fdtd_compute_E": [C.c_void_p, P(cev_state), C.c_void_p, C.c_void_p],
+        "cev_fdtd_compute_E": [C.c_void_p, P(cev_state), P(cev_tangent), C.c_void_p, C.c_void_p],
+        "cev_fdtd_step_H_ex": [C.c_void_p, P(cev_state), P(cev_tangent), C.c_void_p, C.c_int64, C.c_int64, C.c_int64,
+                               C.c_void_p, C.c_void_p],
+        "cev_fdtd_step_D_ex": [C.c_void_p, P(cev_state), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p],
+        "cev_fdtd_sample_probes": [C.c_void_p, P(cev_state), P(cev_tangent), C.c_int, C.c_int64, C.c_void_p, C.c_void_p],
+        "cev_fdtd_jvp_run": [C.c_void_p, P(cev_state), C.c_int, P(cev_state), P(cev_tangent), C.c_int64, C.c_void_p,
+                             C.c_void_p, C.c_void_p, C.c_void_p],
+        "cev_fdtd_adjoint_step": [C.c_void_p, P(cev_state), P(cev_adjoint), C.c_void_p],
+        "cev_fdtd_adjoint_seed": [C.c_void_p, P(cev_state), P(cev_adjoint), C.c_void_p, C.c_void_p],
         "cev_fdtd_set_sources": [C.c_void_p, C.c_int, P(cev_points)],
         "cev_fdtd_set_probes": [C.c_void_p, C.c_int, P(cev_points), P(C.c_int64)],
         "cev_fdtd_probe_slots": [C.c_void_p, P(C.c_int32)],
@@ -59,7 +76,8 @@ def _declare(lib):
 EXPORTS = ("cev_last_error", "cev_abi_version", "cev_fdtd_create", "cev_fdtd_destroy", "cev_fdtd_pml_shapes",
            "cev_fdtd_set_option",
            "cev_fdtd_step_H", "cev_fdtd_step_D", "cev_fdtd_compute_E", "cev_fdtd_set_sources",
-           "cev_fdtd_set_probes", "cev_fdtd_probe_slots", "cev_fdtd_run")
+           "cev_fdtd_set_probes", "cev_fdtd_probe_slots", "cev_fdtd_run", "cev_fdtd_step_H_ex", "cev_fdtd_step_D_ex",
+           "cev_fdtd_sample_probes", "cev_fdtd_jvp_run", "cev_fdtd_adjoint_step", "cev_fdtd_adjoint_seed")
 
 
 def load():

@@ -1,17 +1,270 @@
-"""Differentiation of the FDTD path w.r.t. eps_r (custom VJP / JVP).  Filled in below."""
+"""Differentiation of the FDTD path with respect to eps_r.
+
+The reference gets FDTD derivatives from HIPS autograd tracing every numpy op of every step
+(ceviche/fdtd.py:2, ceviche/jacobians.py:29-51); each non-traceable operator there is registered with
+`defvjp` / `defjvp` (ceviche/primitives.py:28-54).  Here the FDTD step itself is that operator:
+
+* `_StepFn`  - one `forward()` call as a torch.autograd.Function whose backward is ONE transposed step
+               (cev_fdtd_adjoint_step), so reference-style loops `for t: fields = F.forward(...)` stay
+               differentiable in reverse mode with O(steps x 3 arrays) memory (only D is saved: the step
+               is linear in the state and bilinear in (1/eps, D));
+* `_RunFn`   - the fused `run()` with a custom backward: checkpointed, time-reversed adjoint FDTD
+               (forward snapshots every K steps, each segment recomputed once storing D per step);
+* `jvp_run`  - forward mode: the primal and a BATCH of tangent states advance in one sweep
+               (cev_fdtd_jvp_run), instead of one complete traced run per direction (jacobians.py:43).
+
+eps_r enters only through mE = 1/eps_yee (fdtd.py:67, 314-316); both Functions take the three fp64 mE
+arrays as differentiable inputs and torch chains through `1/x` and the Yee averaging on its own.
+"""
+import ctypes as C
+import math
+
 import torch
+import torch.autograd.forward_ad as fwAD
+
+from . import _lib
+
+_FAMS = ("ICE", "IH", "ICH", "ID")
 
 
 def needs_grad(sim, J):
-    if not torch.is_grad_enabled():
-        return False
+    """True when the step must go through the differentiable Functions: some input carries a
+    reverse-mode graph or a forward-mode tangent."""
     ts = list(sim._mE64) + [j for j in J if j is not None] + list(sim._H) + list(sim._D)
-    return any(t.requires_grad for t in ts)
+    if sim._pml is not None:
+        ts += [t for fam in _FAMS for t in sim._pml[fam]]
+    if torch.is_grad_enabled() and any(t.requires_grad for t in ts):
+        return True
+    if fwAD._current_level >= 0:
+        return any(fwAD.unpack_dual(t).tangent is not None for t in ts)
+    return False
+
+
+def _p3(ts):
+    return _lib.c_void_p3(*[None if (t is None or t.numel() == 0) else t.data_ptr() for t in ts])
+
+
+def _state(H, D, mE, pml):
+    st = _lib.cev_state()
+    st.H, st.D, st.inv_eps = _p3(H), _p3(D), _p3(mE)
+    for f, fam in enumerate(_FAMS):
+        setattr(st, fam, _p3(pml[3 * f:3 * f + 3]))
+    return st
+
+
+def _adjoint(lH, lD, lpml, gC, gC2, G):
+    adj = _lib.cev_adjoint()
+    adj.lH, adj.lD, adj.gC, adj.gC2, adj.G_mE = _p3(lH), _p3(lD), _p3(gC), _p3(gC2), _p3(G)
+    for f, fam in enumerate(_FAMS):
+        setattr(adj, "l" + fam, _p3(lpml[3 * f:3 * f + 3]))
+    return adj
+
+
+def _flat_pml(sim):
+    return [t for fam in _FAMS for t in sim._pml[fam]]
+
+
+# ----------------------------------------------------------------------------- one step
+class _StepFn(torch.autograd.Function):
+    """inputs : mE64[3], H[3], D[3], J[3] (zeros-size tensor = absent), pml[12]
+    outputs: H'[3], D'[3], E'[3], pml'[12]"""
+
+    @staticmethod
+    def forward(ctx, sim, *ts):
+        mE64, H, D, J, pml = ts[0:3], ts[3:6], ts[6:9], ts[9:12], ts[12:24]
+        plan = sim._ensure_plan()
+        lib, h, s = plan.lib, plan.handle, sim._stream()
+        with torch.cuda.device(sim.device):
+            mE = [m.detach().to(sim.dtype).contiguous() for m in mE64]
+            Hn = [torch.empty_like(t) for t in H]
+            Dn = [torch.empty_like(t) for t in D]
+            En = [torch.empty_like(t) for t in D]
+            pml_n = [t.detach().clone() for t in pml]           # integrals advance in place on the copies
+            st = _state([t.detach() for t in H], [t.detach() for t in D], mE, pml_n)
+            _lib.check(lib.cev_fdtd_step_H(h, C.byref(st), _p3(Hn), 0, sim.Nx, s))
+            st.H = _p3(Hn)
+            Jp = [None if j.numel() == 0 else j.detach().contiguous() for j in J]
+            _lib.check(lib.cev_fdtd_step_D(h, C.byref(st), _p3(Dn), _p3(En), _p3(Jp), _lib.c_double3(1.0, 1.0, 1.0),
+                                           0, sim.Nx, s))
+        ctx.sim = sim
+        ctx.has_J = [j.numel() != 0 for j in J]
+        ctx.save_for_backward(*mE, *[t.detach() for t in D], *Dn)
+        ctx.fw = (mE, [t.detach() for t in D], Dn)            # for forward mode (jvp)
+        return tuple(Hn + Dn + En + pml_n)
+
+    @staticmethod
+    def jvp(ctx, _sim, *dts):
+        """Tangent of one step: the same linear step on the tangent state with J = dJ, except
+        dE = mE dD + dmE D (product rule on fdtd.py:135-137), once for the E feeding curl_E (primal D
+        before the step) and once for the returned E' (primal D after the step)."""
+        sim = ctx.sim
+        mE, D_in, D_out = ctx.fw
+        plan = sim._ensure_plan()
+        lib, h, s = plan.lib, plan.handle, sim._stream()
+        shapes = plan.pml_shapes
+        with torch.cuda.device(sim.device):
+            zf = lambda: torch.zeros(sim.grid_shape, dtype=sim.dtype, device=sim.device)
+            dmE = [zf() if t is None else t.to(sim.dtype).contiguous() for t in dts[0:3]]
+            dH = [zf() if t is None else t.contiguous() for t in dts[3:6]]
+            dD = [zf() if t is None else t.contiguous() for t in dts[6:9]]
+            dJ = [None if (t is None or not ctx.has_J[c]) else t.contiguous() for c, t in enumerate(dts[9:12])]
+            dP = [torch.zeros(shapes[q], dtype=sim.dtype, device=sim.device) if t is None else t.clone().contiguous()
+                  for q, t in enumerate(dts[12:24])]
+            dHn, dDn, dEn = [zf() for _ in range(3)], [zf() for _ in range(3)], [zf() for _ in range(3)]
+            tst = _state(dH, dD, mE, dP)
+            tan = _lib.cev_tangent()
+            tan.d_inv_eps, tan.D_primal = _p3(dmE), _p3(D_in)
+            _lib.check(lib.cev_fdtd_step_H_ex(h, C.byref(tst), C.byref(tan), _p3(dHn), 0, sim.Nx, -1, None, s))
+            tst.H = _p3(dHn)
+            _lib.check(lib.cev_fdtd_step_D(h, C.byref(tst), _p3(dDn), None, _p3(dJ), _lib.c_double3(1.0, 1.0, 1.0),
+                                           0, sim.Nx, s))
+            tst.D = _p3(dDn)
+            tan.D_primal = _p3(D_out)
+            _lib.check(lib.cev_fdtd_compute_E(h, C.byref(tst), C.byref(tan), _p3(dEn), s))
+        return tuple(dHn + dDn + dEn + dP)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        sim = ctx.sim
+        saved = ctx.saved_tensors
+        mE, D_in, D_out = saved[0:3], saved[3:6], saved[6:9]
+        plan = sim._ensure_plan()
+        shapes = plan.pml_shapes
+        with torch.cuda.device(sim.device):
+            z = lambda ref: torch.zeros_like(ref)
+            gH = [g.detach().clone().contiguous() if g is not None else z(D_in[c]) for c, g in enumerate(gs[0:3])]
+            gD = [g.detach().clone().contiguous() if g is not None else z(D_in[c]) for c, g in enumerate(gs[3:6])]
+            gE = gs[6:9]
+            gp = [g.detach().clone().contiguous() if g is not None
+                  else torch.zeros(shapes[q], dtype=sim.dtype, device=sim.device) for q, g in enumerate(gs[9:21])]
+            G = [torch.zeros(D_in[c].shape, dtype=torch.float64, device=sim.device) for c in range(3)]
+            for c in range(3):       # E' = mE * D'  (fdtd.py:135-137)
+                if gE[c] is not None:
+                    gD[c] += mE[c] * gE[c]
+                    G[c] += gE[c].double() * D_out[c].double()
+            gJ = [gD[c].clone() if ctx.has_J[c] else None for c in range(3)]   # D' = ... + J
+            gC = [z(D_in[c]) for c in range(3)]
+            gC2 = [z(D_in[c]) for c in range(3)]
+            fwd = _state(D_in, D_in, mE, [None] * 12)      # only inv_eps and D (= D before the step) are read
+            adj = _adjoint(gH, gD, gp, gC, gC2, G)
+            _lib.check(plan.lib.cev_fdtd_adjoint_step(plan.handle, C.byref(fwd), C.byref(adj), sim._stream()))
+        grads_J = [g if g is not None else None for g in gJ]
+        return (None, *G, *gH, *gD, *grads_J, *gp)
 
 
 def step(sim, J):
-    raise NotImplementedError
+    """Differentiable `forward()`: returns (H', D', E', pml dict)."""
+    empty = torch.zeros(0, dtype=sim.dtype, device=sim.device)
+    Jt = [empty if j is None else j for j in J]
+    out = _StepFn.apply(sim, *sim._mE64, *sim._H, *sim._D, *Jt, *_flat_pml(sim))
+    H, D, E, p = list(out[0:3]), list(out[3:6]), list(out[6:9]), out[9:21]
+    pml = {fam: list(p[3 * f:3 * f + 3]) for f, fam in enumerate(_FAMS)}
+    return H, D, E, pml
 
 
-def run(sim, steps, waveforms):
-    raise NotImplementedError
+# ----------------------------------------------------------------------------- fused run
+class _RunFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sim, steps, waveforms, every, mEx, mEy, mEz):
+        ctx.sim, ctx.steps, ctx.waveforms = sim, steps, waveforms
+        every = max(1, int(every or math.ceil(math.sqrt(max(steps, 1)))))
+        ctx.every = every
+        ctx.checkpoints = []
+        chunks = []
+        with torch.cuda.device(sim.device):
+            for t0 in range(0, steps, every):
+                t1 = min(steps, t0 + every)
+                ctx.checkpoints.append((t0, t1, [t.clone() for t in sim._H], [t.clone() for t in sim._D],
+                                        [t.clone() for t in _flat_pml(sim)]))
+                chunks.append(sim._run_raw(t1 - t0, waveforms[t0:t1], refresh=False))
+            sim._refresh_E()
+        ctx.mE = [m.clone() for m in sim._mE]
+        ctx.n_probes = sim._n_probes
+        return torch.cat(chunks) if chunks else torch.zeros((0, sim._n_probes), dtype=torch.float64, device=sim.device)
+
+    @staticmethod
+    def backward(ctx, gbar):
+        sim = ctx.sim
+        plan = sim._ensure_plan()
+        lib, h, s = plan.lib, plan.handle, sim._stream()
+        shapes = plan.pml_shapes
+        with torch.cuda.device(sim.device):
+            gbar = gbar.detach().to(torch.float64).contiguous()
+            zf = lambda: [torch.zeros(sim.grid_shape, dtype=sim.dtype, device=sim.device) for _ in range(3)]
+            lH, lD, gC, gC2 = zf(), zf(), zf(), zf()
+            lp = [torch.zeros(shapes[q], dtype=sim.dtype, device=sim.device) for q in range(12)]
+            G = [torch.zeros(sim.grid_shape, dtype=torch.float64, device=sim.device) for _ in range(3)]
+            adj = _adjoint(lH, lD, lp, gC, gC2, G)
+            dummy = torch.zeros((1, max(1, sim._n_slots)), dtype=torch.float64, device=sim.device)
+            for t0, t1, H0, D0, P0 in reversed(ctx.checkpoints):
+                # recompute the segment, keeping D after every step (the only forward quantity the
+                # transposed step needs: the step is linear in the state)
+                H = [t.clone() for t in H0]
+                D = [t.clone() for t in D0]
+                P = [t.clone() for t in P0]
+                st = _state(H, D, ctx.mE, P)
+                hist = [[t.clone() for t in D]]
+                for t in range(t0, t1):
+                    _lib.check(lib.cev_fdtd_run(h, C.byref(st), 1, _ptr(ctx.waveforms[t:t + 1]), _ptr(dummy), s))
+                    hist.append([x.clone() for x in D])
+                for t in range(t1, t0, -1):          # step number t (1-based in the segment's frame)
+                    k = t - t0
+                    if ctx.n_probes:
+                        fwd = _state(hist[k], hist[k], ctx.mE, [None] * 12)
+                        _lib.check(lib.cev_fdtd_adjoint_seed(h, C.byref(fwd), C.byref(adj), _ptr(gbar[t - 1]), s))
+                    fwd = _state(hist[k - 1], hist[k - 1], ctx.mE, [None] * 12)
+                    _lib.check(lib.cev_fdtd_adjoint_step(h, C.byref(fwd), C.byref(adj), s))
+                del hist
+        return (None, None, None, None, *G)
+
+
+def _ptr(t):
+    return None if t is None or t.numel() == 0 else t.data_ptr()
+
+
+def run(sim, steps, waveforms, checkpoint_every=None):
+    if sim.t_index != 0 or any(bool(t.requires_grad) for t in sim._H + sim._D):
+        raise RuntimeError("a differentiable run() must start from initialize_fields(): gradients do not chain "
+                           "across run() calls (use the per-step forward() API for that)")
+    return _RunFn.apply(sim, steps, waveforms.contiguous(), checkpoint_every, *sim._mE64)
+
+
+# ----------------------------------------------------------------------------- forward mode
+def jvp_run(sim, steps, waveforms, eps_tangents):
+    """Primal + B tangents.  eps_tangents: [B, Nx, Ny, Nz] directions in eps_r.
+    Returns (series [steps, P], dseries [B, steps, P])."""
+    plan = sim._ensure_plan()
+    v = eps_tangents.to(device=sim.device, dtype=torch.float64)
+    if v.dim() == 3:
+        v = v.unsqueeze(0)
+    B = v.shape[0]
+    eps_yee = (sim.eps_xx, sim.eps_yy, sim.eps_zz)
+    with torch.cuda.device(sim.device), torch.no_grad():
+        if sim._published:
+            sim._H = [t.clone() for t in sim._H]
+            sim._D = [t.clone() for t in sim._D]
+            sim._published = False
+        keep, tsts, tans = [], (_lib.cev_state * max(1, B))(), (_lib.cev_tangent * max(1, B))()
+        for b in range(B):
+            # d(eps_yee) = Yee average of v (utils.py:167-174); d(1/x) = -dx/x^2
+            dmE = [(-((v[b] + torch.roll(v[b], 1, a)) / 2) / eps_yee[a].detach() ** 2).to(sim.dtype).contiguous()
+                   for a in range(3)]
+            tH = [torch.zeros_like(t) for t in sim._H]
+            tD = [torch.zeros_like(t) for t in sim._D]
+            tP = [torch.zeros_like(t) for t in _flat_pml(sim)]
+            keep.append((dmE, tH, tD, tP))
+            tsts[b] = _state(tH, tD, sim._mE, tP)
+            tans[b].d_inv_eps = _p3(dmE)
+            tans[b].D_primal = _p3(sim._D)
+        partials = torch.zeros((steps, sim._n_slots), dtype=torch.float64, device=sim.device)
+        tpart = torch.zeros((B, steps, sim._n_slots), dtype=torch.float64, device=sim.device)
+        st = sim._state()
+        _lib.check(plan.lib.cev_fdtd_jvp_run(plan.handle, C.byref(st), B, tsts, tans, steps, _ptr(waveforms),
+                                             _ptr(partials), _ptr(tpart), sim._stream()))
+        sim.t_index += steps
+        sim._refresh_E()
+        sim._tangent_states = keep
+        if sim._n_probes == 0:
+            return (torch.zeros((steps, 0), dtype=torch.float64, device=sim.device),
+                    torch.zeros((B, steps, 0), dtype=torch.float64, device=sim.device))
+        return partials @ sim._slot_fold, tpart @ sim._slot_fold

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "step_v1.cuh"
 #include "step_v2.cuh"
+#include "adjoint.cuh"
 
 namespace {
 
@@ -86,7 +87,7 @@ struct cev_fdtd {
     // probes
     int nprobe = 0, n_slots = 0, n_slots_ED = 0;
     std::vector<int32_t> slot_probe;
-    DeviceBuf pr_field, pr_wbegin, pr_ibegin, pr_cell0, pr_n, pr_idx, pr_weight;
+    DeviceBuf pr_field, pr_wbegin, pr_ibegin, pr_cell0, pr_n, pr_idx, pr_weight, pr_owner;
 
     int to_internal(int logical_axis) const { return (logical_axis + rot) % 3; }
     int to_logical(int internal_axis) const { return (internal_axis - rot + 3) % 3; }
@@ -96,8 +97,19 @@ namespace {
 
 using namespace cev;
 
+void fill_probe_table(const cev_fdtd* p, ProbeTable& pr) {
+    pr.n_slots = p->n_slots;
+    pr.slot_field = (const int32_t*)p->pr_field.p;
+    pr.slot_wbegin = (const int64_t*)p->pr_wbegin.p;
+    pr.slot_ibegin = (const int64_t*)p->pr_ibegin.p;
+    pr.slot_cell0 = (const int64_t*)p->pr_cell0.p;
+    pr.slot_n = (const int64_t*)p->pr_n.p;
+    pr.idx = (const int64_t*)p->pr_idx.p;
+    pr.weight = (const double*)p->pr_weight.p;
+}
+
 template <typename T, typename AT>
-int fill_args(const cev_fdtd* p, const cev_state* st, StepArgs<T, AT>& a) {
+int fill_args(const cev_fdtd* p, const cev_state* st, StepArgs<T, AT>& a, const cev_tangent* tan = nullptr) {
     memset(&a, 0, sizeof a);
     a.Nx = p->N[0];
     a.Ny = p->N[1];
@@ -128,7 +140,15 @@ int fill_args(const cev_fdtd* p, const cev_state* st, StepArgs<T, AT>& a) {
         a.uD[A] = (const AT*)p->uD[A][w];
         a.rD[A] = (const AT*)p->rD[A][w];
         a.Jscale[A] = AT(1);
+        if (tan) {
+            a.dmE[A] = (const T*)tan->d_inv_eps[L];
+            a.Dp[A] = (const T*)tan->D_primal[L];
+            if (!a.dmE[A] || !a.Dp[A]) return fail("cev_tangent: d_inv_eps and D_primal must be non-NULL");
+            a.dmEhi[A] = a.dmE[A];     // tangents run on whole (periodic) grids only
+            a.Dphi[A] = a.Dp[A];
+        }
     }
+    if (tan && (st->D_xhi[1] || st->D_xhi[2])) return fail("tangent steps do not support x-halo planes");
     if (p->rot != 0 && (st->D_xhi[1] || st->D_xhi[2] || st->H_xlo[1] || st->H_xlo[2]))
         return fail("x-halo planes need Nz > 1 (no slab decomposition of a rotated 2-D/1-D grid)");
     // PML integral arrays must exist wherever the kernels will touch them
@@ -141,14 +161,7 @@ int fill_args(const cev_fdtd* p, const cev_state* st, StepArgs<T, AT>& a) {
     }
     a.cdt = (AT)p->cdt;
     a.inv_dL = (AT)(1.0 / p->dL);
-    a.pr.n_slots = p->n_slots;
-    a.pr.slot_field = (const int32_t*)p->pr_field.p;
-    a.pr.slot_wbegin = (const int64_t*)p->pr_wbegin.p;
-    a.pr.slot_ibegin = (const int64_t*)p->pr_ibegin.p;
-    a.pr.slot_cell0 = (const int64_t*)p->pr_cell0.p;
-    a.pr.slot_n = (const int64_t*)p->pr_n.p;
-    a.pr.idx = (const int64_t*)p->pr_idx.p;
-    a.pr.weight = (const double*)p->pr_weight.p;
+    fill_probe_table(p, a.pr);
     a.t_probe = -1;
     return 0;
 }
@@ -172,7 +185,7 @@ constexpr int vec_width() {
 // array 16-byte aligned (torch allocations are; odd Nz falls back to the baseline kernels).
 template <typename T, typename AT>
 bool can_march(const cev_fdtd* p, const StepArgs<T, AT>& a, bool isH) {
-    if (p->variant == 1) return false;
+    if (p->variant == 1 || a.dmE[0]) return false;    // tangent steps use the baseline kernels
     constexpr int V = vec_width<T>();
     if (a.Nz % V != 0) return false;
     auto ok = [](const void* q) { return q == nullptr || ((uintptr_t)q % 16) == 0; };
@@ -218,10 +231,10 @@ int attach_probes(const cev_fdtd* p, StepArgs<T, AT>& a, int which, int64_t t, d
 }
 
 template <typename T, typename AT>
-int launch_H(cev_fdtd* p, const cev_state* st, void* const H_out[3], int64_t x0, int64_t x1,
+int launch_H(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, void* const H_out[3], int64_t x0, int64_t x1,
              int64_t probe_t, double* partials, cudaStream_t s) {
     StepArgs<T, AT> a;
-    if (fill_args(p, st, a)) return -1;
+    if (fill_args(p, st, a, tan)) return -1;
     if (H_out)
         for (int A = 0; A < 3; ++A) {
             a.Hout[A] = (T*)H_out[p->to_logical(A)];
@@ -305,9 +318,10 @@ int launch_inject(cev_fdtd* p, const cev_state* st, const double* wave_row, cuda
 }
 
 template <typename T, typename AT>
-int launch_probe_only(cev_fdtd* p, const cev_state* st, int which, int64_t t, double* partials, cudaStream_t s) {
+int launch_probe_only(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, int which, int64_t t, double* partials,
+                      cudaStream_t s) {
     StepArgs<T, AT> a;
-    if (fill_args(p, st, a)) return -1;
+    if (fill_args(p, st, a, tan)) return -1;
     const int aux = attach_probes(p, a, which, t, partials);
     if (aux == 0) return 0;
     k_probe_only<T, AT><<<aux, dim3(V1_TZ, V1_TY), 0, s>>>(a);
@@ -316,7 +330,7 @@ int launch_probe_only(cev_fdtd* p, const cev_state* st, int which, int64_t t, do
 }
 
 template <typename T, typename AT>
-int launch_compute_E(cev_fdtd* p, const cev_state* st, void* const E_out[3], cudaStream_t s) {
+int launch_compute_E(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, void* const E_out[3], cudaStream_t s) {
     const int64_t n = p->Nl[0] * p->Nl[1] * p->Nl[2];
     if (n == 0) return 0;
     for (int c = 0; c < 3; ++c) {
@@ -324,7 +338,9 @@ int launch_compute_E(cev_fdtd* p, const cev_state* st, void* const E_out[3], cud
         const int bs = 256;
         const int64_t want = (n + bs - 1) / bs;
         const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
-        k_compute_E<T, AT><<<grid, bs, 0, s>>>((const T*)st->inv_eps[c], (const T*)st->D[c], (T*)E_out[c], n);
+        k_compute_E<T, AT><<<grid, bs, 0, s>>>((const T*)st->inv_eps[c], (const T*)st->D[c],
+                                               tan ? (const T*)tan->d_inv_eps[c] : nullptr,
+                                               tan ? (const T*)tan->D_primal[c] : nullptr, (T*)E_out[c], n);
         CUDA_TRY(cudaGetLastError());
     }
     return 0;
@@ -337,11 +353,102 @@ int run_loop(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* wav
     for (int64_t n = 0; n < nsteps; ++n) {
         // E/D probes of step n-1 ride on the H launch of step n (D is read-only there);
         // H probes of step n ride on its D launch (H is read-only there).
-        if (launch_H<T, AT>(p, st, nullptr, 0, Nx, n - 1, partials, s)) return -1;
+        if (launch_H<T, AT>(p, st, nullptr, nullptr, 0, Nx, n - 1, partials, s)) return -1;
         if (launch_D<T, AT>(p, st, nullptr, nullptr, nullptr, nullptr, nullptr, 0, Nx, n, partials, s)) return -1;
         if (waveform && launch_inject<T, AT>(p, st, waveform + n * p->nsrc, s)) return -1;
     }
-    if (nsteps > 0 && launch_probe_only<T, AT>(p, st, 0, nsteps - 1, partials, s)) return -1;
+    if (nsteps > 0 && launch_probe_only<T, AT>(p, st, nullptr, 0, nsteps - 1, partials, s)) return -1;
+    return 0;
+}
+
+// Primal + B tangents in one sweep.  Per step: tangent H half-steps first (they need the primal D of
+// the previous step), then the primal step, then the tangent D half-steps (same linear update, J = 0).
+template <typename T, typename AT>
+int jvp_loop(cev_fdtd* p, const cev_state* st, int B, const cev_state* tst, const cev_tangent* tan, int64_t nsteps,
+             const double* waveform, double* partials, double* tpartials, cudaStream_t s) {
+    const int64_t Nx = p->N[0];
+    const int64_t stride = nsteps * p->n_slots;
+    for (int64_t n = 0; n < nsteps; ++n) {
+        for (int b = 0; b < B; ++b)
+            if (launch_H<T, AT>(p, &tst[b], &tan[b], nullptr, 0, Nx, n - 1, tpartials ? tpartials + b * stride : nullptr, s)) return -1;
+        if (launch_H<T, AT>(p, st, nullptr, nullptr, 0, Nx, n - 1, partials, s)) return -1;
+        if (launch_D<T, AT>(p, st, nullptr, nullptr, nullptr, nullptr, nullptr, 0, Nx, n, partials, s)) return -1;
+        if (waveform && launch_inject<T, AT>(p, st, waveform + n * p->nsrc, s)) return -1;
+        for (int b = 0; b < B; ++b)
+            if (launch_D<T, AT>(p, &tst[b], nullptr, nullptr, nullptr, nullptr, nullptr, 0, Nx, n, tpartials ? tpartials + b * stride : nullptr, s)) return -1;
+    }
+    if (nsteps > 0) {
+        if (launch_probe_only<T, AT>(p, st, nullptr, 0, nsteps - 1, partials, s)) return -1;
+        for (int b = 0; b < B; ++b)
+            if (launch_probe_only<T, AT>(p, &tst[b], &tan[b], 0, nsteps - 1, tpartials ? tpartials + b * stride : nullptr, s)) return -1;
+    }
+    return 0;
+}
+
+template <typename T, typename AT>
+int fill_adj(const cev_fdtd* p, const cev_state* fwd, const cev_adjoint* adj, AdjArgs<T, AT>& a) {
+    memset(&a, 0, sizeof a);
+    a.Nx = p->N[0];
+    a.Ny = p->N[1];
+    a.Nz = p->N[2];
+    constexpr int w = sizeof(AT) == 8 ? 1 : 0;
+    for (int A = 0; A < 3; ++A) {
+        const int L = p->to_logical(A);
+        a.lH[A] = (T*)adj->lH[L];
+        a.lD[A] = (T*)adj->lD[L];
+        a.lICE[A] = (T*)adj->lICE[L];
+        a.lIH[A] = (T*)adj->lIH[L];
+        a.lICH[A] = (T*)adj->lICH[L];
+        a.lID[A] = (T*)adj->lID[L];
+        a.gC[A] = (T*)adj->gC[L];
+        a.gC2[A] = (T*)adj->gC2[L];
+        a.G[A] = adj->G_mE[L];
+        a.mE[A] = (const T*)fwd->inv_eps[L];
+        a.Dprev[A] = (const T*)fwd->D[L];
+        if (!a.lH[A] || !a.lD[A] || !a.gC[A] || !a.gC2[A] || !a.mE[A] || !a.Dprev[A])
+            return fail("cev_adjoint: lH, lD, gC, gC2 and the forward inv_eps / D must be non-NULL");
+        const int Bx = (A + 1) % 3, C = (A + 2) % 3;
+        if (p->nH[A] > 0 && !a.lICE[A]) return fail("cev_adjoint: lICE missing for a PML axis");
+        if (p->nD[A] > 0 && !a.lICH[A]) return fail("cev_adjoint: lICH missing for a PML axis");
+        if (p->nH[Bx] > 0 && p->nH[C] > 0 && !a.lIH[A]) return fail("cev_adjoint: lIH missing for a PML corner");
+        if (p->nD[Bx] > 0 && p->nD[C] > 0 && !a.lID[A]) return fail("cev_adjoint: lID missing for a PML corner");
+        a.mapH[A] = p->mapH[A];
+        a.mapD[A] = p->mapD[A];
+        a.nH[A] = p->nH[A];
+        a.nD[A] = p->nD[A];
+        a.uH[A] = (const AT*)p->uH[A][w];
+        a.rH[A] = (const AT*)p->rH[A][w];
+        a.uD[A] = (const AT*)p->uD[A][w];
+        a.rD[A] = (const AT*)p->rD[A][w];
+    }
+    a.cdt = (AT)p->cdt;
+    a.inv_dL = (AT)(1.0 / p->dL);
+    return 0;
+}
+
+template <typename T, typename AT>
+int launch_adjoint_step(cev_fdtd* p, const cev_state* fwd, const cev_adjoint* adj, cudaStream_t s) {
+    AdjArgs<T, AT> a;
+    if (fill_adj(p, fwd, adj, a)) return -1;
+    const dim3 blk(64, 4);
+    const dim3 grd((a.Nz + 63) / 64, (a.Ny + 3) / 4, a.Nx);
+    if (grd.y > 65535 || grd.z > 65535) return fail("adjoint kernels: grid extent too large");
+    k_adj_D<T, AT><<<grd, blk, 0, s>>>(a);
+    k_adj_H<T, AT><<<grd, blk, 0, s>>>(a);
+    k_adj_E<T, AT><<<grd, blk, 0, s>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, typename AT>
+int launch_adjoint_seed(cev_fdtd* p, const cev_state* fwd, const cev_adjoint* adj, const double* gbar_row, cudaStream_t s) {
+    if (p->n_slots == 0) return 0;
+    AdjArgs<T, AT> a;
+    if (fill_adj(p, fwd, adj, a)) return -1;
+    ProbeTable pr;
+    fill_probe_table(p, pr);
+    k_adj_seed<T, AT><<<p->n_slots, 128, 0, s>>>(a, pr, (const int32_t*)p->pr_owner.p, gbar_row, a.Dprev[0], a.Dprev[1], a.Dprev[2]);
+    CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
@@ -482,7 +589,7 @@ int cev_fdtd_destroy(cev_fdtd* p) {
     p->tables.release();
     p->src_comp.release(); p->src_id.release(); p->src_cell.release(); p->src_weight.release();
     p->pr_field.release(); p->pr_wbegin.release(); p->pr_ibegin.release(); p->pr_cell0.release();
-    p->pr_n.release(); p->pr_idx.release(); p->pr_weight.release();
+    p->pr_n.release(); p->pr_idx.release(); p->pr_weight.release(); p->pr_owner.release();
     delete p;
     return 0;
 }
@@ -528,7 +635,64 @@ int cev_fdtd_step_H(cev_fdtd* p, const cev_state* st, void* const H_out[3], int6
     if (check_range(p, x0, x1)) return -1;
     DeviceGuard guard(p->device);
     const int64_t a0 = p->rot ? 0 : x0, a1 = p->rot ? p->N[0] : x1;
-    return DISPATCH(p, launch_H, p, st, H_out, a0, a1, (int64_t)-1, (double*)nullptr, (cudaStream_t)stream);
+    return DISPATCH(p, launch_H, p, st, (const cev_tangent*)nullptr, H_out, a0, a1, (int64_t)-1, (double*)nullptr, (cudaStream_t)stream);
+}
+
+int cev_fdtd_step_H_ex(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, void* const H_out[3], int64_t x0,
+                       int64_t x1, int64_t probe_t, double* partials, void* stream) {
+    if (!p || !st) return fail("NULL argument");
+    if (check_range(p, x0, x1)) return -1;
+    DeviceGuard guard(p->device);
+    const int64_t a0 = p->rot ? 0 : x0, a1 = p->rot ? p->N[0] : x1;
+    return DISPATCH(p, launch_H, p, st, tan, H_out, a0, a1, probe_t, partials, (cudaStream_t)stream);
+}
+
+int cev_fdtd_step_D_ex(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const E_out[3], const void* const J[3],
+                       const double J_scale[3], const double* waveform_row, int64_t x0, int64_t x1, int64_t probe_t,
+                       double* partials, void* stream) {
+    if (!p || !st) return fail("NULL argument");
+    if (check_range(p, x0, x1)) return -1;
+    DeviceGuard guard(p->device);
+    const int64_t a0 = p->rot ? 0 : x0, a1 = p->rot ? p->N[0] : x1;
+    if (DISPATCH(p, launch_D, p, st, D_out, E_out, J, J_scale, (const double* const*)nullptr, a0, a1, probe_t, partials,
+                 (cudaStream_t)stream))
+        return -1;
+    if (waveform_row && p->n_src_pts > 0) {
+        if (D_out) return fail("source injection works on the in-place D (pass D_out = NULL)");
+        return DISPATCH(p, launch_inject, p, st, waveform_row, (cudaStream_t)stream);
+    }
+    return 0;
+}
+
+int cev_fdtd_sample_probes(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, int which, int64_t t, double* partials,
+                           void* stream) {
+    if (!p || !st) return fail("NULL argument");
+    if (which != 0 && which != 1) return fail("which must be 0 (E/D probes) or 1 (H probes)");
+    DeviceGuard guard(p->device);
+    return DISPATCH(p, launch_probe_only, p, st, tan, which, t, partials, (cudaStream_t)stream);
+}
+
+int cev_fdtd_jvp_run(cev_fdtd* p, const cev_state* st, int B, const cev_state* tangents, const cev_tangent* tans,
+                     int64_t nsteps, const double* waveform, double* partials, double* tangent_partials, void* stream) {
+    if (!p || !st || B < 0 || (B > 0 && (!tangents || !tans))) return fail("bad jvp arguments");
+    if (nsteps < 0) return fail("nsteps must be >= 0");
+    if (p->n_src_pts > 0 && !waveform) return fail("plan has sources but waveform is NULL");
+    if (p->n_slots > 0 && (!partials || (B > 0 && !tangent_partials))) return fail("plan has probes but partials is NULL");
+    DeviceGuard guard(p->device);
+    return DISPATCH(p, jvp_loop, p, st, B, tangents, tans, nsteps, p->n_src_pts > 0 ? waveform : nullptr, partials,
+                    tangent_partials, (cudaStream_t)stream);
+}
+
+int cev_fdtd_adjoint_step(cev_fdtd* p, const cev_state* fwd, const cev_adjoint* adj, void* stream) {
+    if (!p || !fwd || !adj) return fail("NULL argument");
+    DeviceGuard guard(p->device);
+    return DISPATCH(p, launch_adjoint_step, p, fwd, adj, (cudaStream_t)stream);
+}
+
+int cev_fdtd_adjoint_seed(cev_fdtd* p, const cev_state* fwd, const cev_adjoint* adj, const double* gbar_row, void* stream) {
+    if (!p || !fwd || !adj || !gbar_row) return fail("NULL argument");
+    DeviceGuard guard(p->device);
+    return DISPATCH(p, launch_adjoint_seed, p, fwd, adj, gbar_row, (cudaStream_t)stream);
 }
 
 int cev_fdtd_step_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const E_out[3], const void* const J[3],
@@ -541,10 +705,10 @@ int cev_fdtd_step_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void
                     (double*)nullptr, (cudaStream_t)stream);
 }
 
-int cev_fdtd_compute_E(cev_fdtd* p, const cev_state* st, void* const E_out[3], void* stream) {
+int cev_fdtd_compute_E(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, void* const E_out[3], void* stream) {
     if (!p || !st || !E_out) return fail("NULL argument");
     DeviceGuard guard(p->device);
-    return DISPATCH(p, launch_compute_E, p, st, E_out, (cudaStream_t)stream);
+    return DISPATCH(p, launch_compute_E, p, st, tan, E_out, (cudaStream_t)stream);
 }
 
 int cev_fdtd_set_sources(cev_fdtd* p, int nsrc, const cev_points* src) {
@@ -623,7 +787,7 @@ int cev_fdtd_set_probes(cev_fdtd* p, int nprobe, const cev_points* probe, int64_
     }
     const int ns = (int)field.size();
     if (p->pr_field.alloc(ns * 4) || p->pr_wbegin.alloc(ns * 8) || p->pr_ibegin.alloc(ns * 8) || p->pr_cell0.alloc(ns * 8) ||
-        p->pr_n.alloc(ns * 8) || p->pr_idx.alloc(itotal * 8) || p->pr_weight.alloc(wtotal * 8))
+        p->pr_n.alloc(ns * 8) || p->pr_idx.alloc(itotal * 8) || p->pr_weight.alloc(wtotal * 8) || p->pr_owner.alloc(ns * 4))
         return -1;
     if (ns) {
         CUDA_TRY(cudaMemcpy(p->pr_field.p, field.data(), ns * 4, cudaMemcpyHostToDevice));
@@ -631,6 +795,7 @@ int cev_fdtd_set_probes(cev_fdtd* p, int nprobe, const cev_points* probe, int64_
         CUDA_TRY(cudaMemcpy(p->pr_ibegin.p, ibegin.data(), ns * 8, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(p->pr_cell0.p, cell0.data(), ns * 8, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(p->pr_n.p, cnt.data(), ns * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(p->pr_owner.p, owner.data(), ns * 4, cudaMemcpyHostToDevice));
     }
     for (int q = 0; q < nprobe; ++q) {
         const cev_points& P = probe[q];

@@ -5,6 +5,14 @@
 
 namespace cev {
 
+// Explicitly rounded arithmetic: no FMA contraction, so that (i) every kernel variant produces
+// bit-identical results and (ii) the rounding sequence is the reference's numpy one (each product
+// and each sum rounded separately, fdtd.py:95-97 / derivatives.py:18).
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+
 // Sampling of probe point sets: one CTA per "slot" (a chunk of one probe's points) does a
 // fixed-order reduction and writes ONE partial sum -> deterministic series, no atomics.
 struct ProbeTable {
@@ -47,6 +55,12 @@ struct StepArgs {
     const AT* rD[3];
     AT cdt;             // C_0 * dt
     AT inv_dL;
+    // forward-mode tangent of E = mE*D w.r.t. eps_r: E = mE*D + dmE*Dp (D is then the TANGENT state,
+    // Dp the primal D); all NULL for an ordinary step
+    const T* dmE[3];
+    const T* Dp[3];
+    const T* dmEhi[3];
+    const T* Dphi[3];
     const T* J[3];      // dense source per component (nullable)
     AT       Jscale[3];
     const double* Jwave[3];   // nullable device scalar overriding Jscale (waveform entry)
@@ -62,7 +76,11 @@ struct StepArgs {
 template <typename T, typename AT>
 __device__ __forceinline__ AT probe_value(const StepArgs<T, AT>& a, int field, int64_t cell) {
     const int c = field % 3;
-    if (field < 3) return (AT)a.mE[c][cell] * (AT)a.Din[c][cell];   // feeds a double product: no contraction issue
+    if (field < 3) {
+        AT e = mul_rn((AT)a.mE[c][cell], (AT)a.Din[c][cell]);
+        if (a.dmE[c]) e = add_rn(e, mul_rn((AT)a.dmE[c][cell], (AT)a.Dp[c][cell]));
+        return e;
+    }
     if (field < 6) return (AT)a.Din[c][cell];
     return (AT)a.Hin[c][cell];
 }
@@ -95,14 +113,6 @@ __device__ void probe_block(const StepArgs<T, AT>& a, int slot) {
     }
     if (tid == 0) a.partials[a.t_probe * a.pr.n_slots + slot] = red[0];
 }
-
-// Explicitly rounded arithmetic: no FMA contraction, so that (i) every kernel variant produces
-// bit-identical results and (ii) the rounding sequence is the reference's numpy one (each product
-// and each sum rounded separately, fdtd.py:95-97 / derivatives.py:18).
-__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
 
 // (a1-a0)/dL - (b1-b0)/dL, both quotients rounded before the subtraction (derivatives.py:16-30)
 template <typename AT>

@@ -37,7 +37,9 @@ __global__ void __launch_bounds__(V1_TZ* V1_TY) k_step_H_v1(const StepArgs<T, AT
     const int64_t o_kp = i * plane + (int64_t)j * a.Nz + kp;
     const bool last = (i + 1 == a.Nx);
 
-#define E_AT(c, off) mul_rn((AT)a.mE[c][off], (AT)a.Din[c][off])
+#define E_AT(c, off)                                                                        \
+    (a.dmE[c] ? add_rn(mul_rn((AT)a.mE[c][off], (AT)a.Din[c][off]), mul_rn((AT)a.dmE[c][off], (AT)a.Dp[c][off])) \
+              : mul_rn((AT)a.mE[c][off], (AT)a.Din[c][off]))
     const AT Ex = E_AT(0, o), Ey = E_AT(1, o), Ez = E_AT(2, o);
     const AT Ex_jp = E_AT(0, o_jp), Ez_jp = E_AT(2, o_jp);
     const AT Ex_kp = E_AT(0, o_kp), Ey_kp = E_AT(1, o_kp);
@@ -48,6 +50,8 @@ __global__ void __launch_bounds__(V1_TZ* V1_TY) k_step_H_v1(const StepArgs<T, AT
     } else {
         Ey_ip = mul_rn((AT)a.mEhi[1][o_in], (AT)a.Dhi[1][o_in]);
         Ez_ip = mul_rn((AT)a.mEhi[2][o_in], (AT)a.Dhi[2][o_in]);
+        if (a.dmE[1]) Ey_ip = add_rn(Ey_ip, mul_rn((AT)a.dmEhi[1][o_in], (AT)a.Dphi[1][o_in]));
+        if (a.dmE[2]) Ez_ip = add_rn(Ez_ip, mul_rn((AT)a.dmEhi[2][o_in], (AT)a.Dphi[2][o_in]));
     }
 #undef E_AT
     const AT inv = a.inv_dL;
@@ -155,9 +159,13 @@ __global__ void __launch_bounds__(V1_TZ* V1_TY) k_step_D_v1(const StepArgs<T, AT
 
 // E = mE * D  (fdtd.py:135-137), plain streaming kernel.
 template <typename T, typename AT>
-__global__ void k_compute_E(const T* __restrict__ mE, const T* __restrict__ D, T* __restrict__ E, int64_t n) {
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x)
-        E[q] = (T)mul_rn((AT)mE[q], (AT)D[q]);
+__global__ void k_compute_E(const T* __restrict__ mE, const T* __restrict__ D, const T* __restrict__ dmE,
+                            const T* __restrict__ Dp, T* __restrict__ E, int64_t n) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        AT e = mul_rn((AT)mE[q], (AT)D[q]);
+        if (dmE) e = add_rn(e, mul_rn((AT)dmE[q], (AT)Dp[q]));   // tangent: dE = mE dD + dmE D
+        E[q] = (T)e;
+    }
 }
 
 // Sparse J injection: D[field][cell] += weight * waveform[src]   (fdtd.py:125-127 for

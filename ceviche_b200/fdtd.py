@@ -360,16 +360,7 @@ class fdtd:
         self.set_sources([(s[0], s[1]) for s in sources])
         self.set_probes(list(probes))
 
-    def run(self, steps, sources=None, probes=None, waveforms=None):
-        """`steps` fused time steps: the loop of ceviche/utils.py:325-331 on the device.
-
-        sources: [(component, profile, waveform[steps])]  (or (component, profile) with
-                 `waveforms` a [steps, n_sources] array/tensor); None = keep the prepared ones
-        probes:  [(field key, mask)]; None = keep the prepared ones
-        Returns series[steps, n_probes] (float64 tensor on the device).  State advances in place;
-        `fields` is refreshed at the end."""
-        from . import autodiff
-        steps = int(steps)
+    def _prepare_run(self, steps, sources, probes, waveforms):
         self._ensure_plan()
         if sources is None and probes is None and waveforms is None and self._n_sources == 0:
             sources = ()
@@ -394,9 +385,31 @@ class fdtd:
         waveforms = waveforms.to(device=self.device, dtype=torch.float64).contiguous()
         if tuple(waveforms.shape) != (steps, n_src):
             raise ValueError("waveforms must have shape (steps, n_sources) = {}".format((steps, n_src)))
+        return waveforms
+
+    def run(self, steps, sources=None, probes=None, waveforms=None, checkpoint_every=None):
+        """`steps` fused time steps: the loop of ceviche/utils.py:325-331 on the device.
+
+        sources: [(component, profile, waveform[steps])]  (or (component, profile) with
+                 `waveforms` a [steps, n_sources] array/tensor); None = keep the prepared ones
+        probes:  [(field key, mask)]; None = keep the prepared ones
+        Returns series[steps, n_probes] (float64 tensor on the device).  State advances in place;
+        `fields` is refreshed at the end.  If eps_r requires grad the series is differentiable
+        (checkpointed adjoint FDTD, snapshots every `checkpoint_every` steps, default sqrt(steps))."""
+        from . import autodiff
+        steps = int(steps)
+        waveforms = self._prepare_run(steps, sources, probes, waveforms)
         if autodiff.needs_grad(self, []):
-            return autodiff.run(self, steps, waveforms)
+            return autodiff.run(self, steps, waveforms, checkpoint_every)
         return self._run_raw(steps, waveforms)
+
+    def jvp_run(self, steps, eps_tangents, sources=None, probes=None, waveforms=None):
+        """Forward mode: the primal run plus a batch of tangents d/d(eps_r) along `eps_tangents`
+        [B, Nx, Ny, Nz] in ONE sweep.  Returns (series [steps, P], dseries [B, steps, P])."""
+        from . import autodiff
+        steps = int(steps)
+        waveforms = self._prepare_run(steps, sources, probes, waveforms)
+        return autodiff.jvp_run(self, steps, waveforms, eps_tangents)
 
     def _run_raw(self, steps, waveforms, refresh=True):
         plan = self._ensure_plan()
@@ -420,6 +433,6 @@ class fdtd:
         plan = self._ensure_plan()
         En = [torch.empty_like(t) for t in self._D]
         st = self._state()
-        _lib.check(plan.lib.cev_fdtd_compute_E(plan.handle, C.byref(st), _ptr3(En), self._stream()))
+        _lib.check(plan.lib.cev_fdtd_compute_E(plan.handle, C.byref(st), None, _ptr3(En), self._stream()))
         self._E = En
         self._publish()

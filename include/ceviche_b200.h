@@ -72,6 +72,28 @@ typedef struct cev_points {
     const double*  weight;       /* n weights (profile / mask values) */
 } cev_points;
 
+/* Forward-mode tangent inputs: with eps_r perturbed along v, d(inv_eps) = -d(eps_yee)/eps_yee^2 and the
+ * tangent state obeys the SAME step with J = 0, except E = inv_eps*dD + d_inv_eps*D_primal (product rule
+ * on fdtd.py:135-137).  Both arrays are full grids, borrowed device pointers. */
+typedef struct cev_tangent {
+    const void* d_inv_eps[3];
+    const void* D_primal[3];
+} cev_tangent;
+
+/* Cotangent state of the reverse sweep (same layouts as cev_state: compact PML arrays), two scratch
+ * vector fields, and the fp64 accumulators of dL/d(inv_eps).  G_mE entries may be NULL (not wanted). */
+typedef struct cev_adjoint {
+    void*   lH[3];
+    void*   lD[3];
+    void*   lICE[3];
+    void*   lIH[3];
+    void*   lICH[3];
+    void*   lID[3];
+    void*   gC[3];
+    void*   gC2[3];
+    double* G_mE[3];
+} cev_adjoint;
+
 const char* cev_last_error(void);
 int         cev_abi_version(void);
 
@@ -100,8 +122,21 @@ int cev_fdtd_step_H(cev_fdtd* plan, const cev_state* st, void* const H_out[3],
 int cev_fdtd_step_D(cev_fdtd* plan, const cev_state* st, void* const D_out[3], void* const E_out[3],
                     const void* const J[3], const double J_scale[3],
                     int64_t x0, int64_t x1, void* stream);
-/* E = inv_eps * D (fdtd.py:135-137) into E_out. */
-int cev_fdtd_compute_E(cev_fdtd* plan, const cev_state* st, void* const E_out[3], void* stream);
+/* E = inv_eps * D (fdtd.py:135-137) into E_out (tan != NULL: the tangent dE). */
+int cev_fdtd_compute_E(cev_fdtd* plan, const cev_state* st, const cev_tangent* tan, void* const E_out[3], void* stream);
+
+/* Extended half-steps used by the slab driver and the derivative sweeps: optional tangent inputs,
+ * probe sampling riding on the launch (probe_t >= 0: E/D probes of the PREVIOUS step on an H launch,
+ * H probes of THIS step on a D launch, written to row probe_t of partials), and in-place injection of
+ * the plan's sources scaled by waveform_row[n_sources] (device) after the D update. */
+int cev_fdtd_step_H_ex(cev_fdtd* plan, const cev_state* st, const cev_tangent* tan, void* const H_out[3],
+                       int64_t x0, int64_t x1, int64_t probe_t, double* partials, void* stream);
+int cev_fdtd_step_D_ex(cev_fdtd* plan, const cev_state* st, void* const D_out[3], void* const E_out[3],
+                       const void* const J[3], const double J_scale[3], const double* waveform_row,
+                       int64_t x0, int64_t x1, int64_t probe_t, double* partials, void* stream);
+/* Stand-alone probe sampling: which = 0 (E/D probes) or 1 (H probes) into row t of partials. */
+int cev_fdtd_sample_probes(cev_fdtd* plan, const cev_state* st, const cev_tangent* tan, int which, int64_t t,
+                           double* partials, void* stream);
 
 /* Sources and probes of the caller loop (utils.py:316-332): J(t) = sum_s profile_s * waveform[t, s],
  * series[t, p] = sum(field_p * mask_p).  Point sets are copied into the plan. */
@@ -115,6 +150,19 @@ int cev_fdtd_probe_slots(const cev_fdtd* plan, int32_t* slot_probe);
  * (series[t, p] = sum of the slots of p, in slot order: deterministic). */
 int cev_fdtd_run(cev_fdtd* plan, const cev_state* st, int64_t nsteps,
                  const double* waveform, double* partials, void* stream);
+
+/* Forward mode (replaces one traced re-run per direction, ceviche/jacobians.py:38-51): the primal and
+ * B tangent states advance together; tangent_partials is [B, nsteps, n_slots]. */
+int cev_fdtd_jvp_run(cev_fdtd* plan, const cev_state* st, int B, const cev_state* tangents, const cev_tangent* tans,
+                     int64_t nsteps, const double* waveform, double* partials, double* tangent_partials, void* stream);
+
+/* Reverse mode (replaces autograd's tape, ceviche/jacobians.py:29-35): one transposed time step.
+ * fwd->D must hold the forward D after step n-1 and fwd->inv_eps the material; on return adj holds the
+ * cotangents of the state after step n-1 and G_mE has gained step n's term.  cev_fdtd_adjoint_seed adds
+ * the probe-series cotangents gbar_row[n_probes] (device) of one step; there fwd->D is D after THAT step. */
+int cev_fdtd_adjoint_step(cev_fdtd* plan, const cev_state* fwd, const cev_adjoint* adj, void* stream);
+int cev_fdtd_adjoint_seed(cev_fdtd* plan, const cev_state* fwd, const cev_adjoint* adj, const double* gbar_row,
+                          void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,160 @@
+"""Derivatives w.r.t. eps_r: the custom VJP (time-reversed adjoint FDTD) and JVP (tangent FDTD) against
+the torch-autograd / torch.func.jvp oracle vectors in tests/golden/ (rel-L2 <= 1e-10 in fp64) and against
+finite differences through the REFERENCE numpy code (<= 1e-4, the reference's own criterion,
+tests/test_gradients_fdtd.py:19-20, 52-64).  The first four tests restate the reference's four gradient
+tests on its 8x8x1 / 500-step problem."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases
+from oracle.fdtd_numpy import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+ALLOWED_RATIO = 1e-4     # tests/test_gradients_fdtd.py:19
+
+
+def _gold(golden_dir, name):
+    return np.load(os.path.join(golden_dir, "grad_%s.npz" % name))
+
+
+def _ref_objective(F, case, shape, array_valued):
+    """The reference's objective bodies (test_gradients_fdtd.py:72-78, 98-104) on our drop-in object."""
+    comp, prof, wave = case["sources"][0]
+    keys = [k for k, _ in case["probes"]]
+    prof_t = torch.as_tensor(prof).cuda()
+
+    def run_loop(F):
+        S = 0.0
+        for t in range(case["steps"]):
+            fields = F.forward(**{"J" + comp: prof_t * float(wave[t])})
+            term = fields[keys[0]] + fields[keys[1]] + fields[keys[2]]
+            S = S + (term if array_valued else torch.sum(term))
+        return S
+    return run_loop
+
+
+@pytest.mark.parametrize("name", ["ref_rev_E", "ref_rev_H"])
+def test_reference_reverse_mode_tests(name, golden_dir):
+    import ceviche_b200
+    from ceviche_b200 import jacobian
+    case, gold = cases.grad_case(name), _gold(golden_dir, name)
+    shape = case["eps"].shape
+    F = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"])
+    loop = _ref_objective(F, case, shape, array_valued=False)
+
+    def objective(eps_arr):
+        F.eps_r = eps_arr.reshape(shape)
+        return loop(F)
+
+    jac = jacobian(objective, mode='reverse')(case["eps"].flatten()).cpu().numpy().reshape(shape)
+    assert rel_l2(jac, gold["grad_ad"]) <= 1e-10
+    # AD vs finite differences through the reference's numpy code
+    assert rel_l2(jac.ravel(), gold["fd_one_sided"]) <= ALLOWED_RATIO
+    assert rel_l2(jac.ravel(), gold["fd_central"]) <= 1e-6
+    assert abs(float(objective(torch.as_tensor(case["eps"].flatten()).cuda())) - float(gold["value"])) <= 1e-10 * abs(float(gold["value"]))
+
+
+@pytest.mark.parametrize("name", ["ref_fwd_E", "ref_fwd_H"])
+def test_reference_forward_mode_tests(name, golden_dir):
+    import ceviche_b200
+    from ceviche_b200 import jacobian
+    case, gold = cases.grad_case(name), _gold(golden_dir, name)
+    shape = case["eps"].shape
+    eps0 = torch.as_tensor(case["eps"]).cuda()
+
+    def objective(c):
+        F = ceviche_b200.fdtd(c.cuda() * eps0, case["dL"], case["npml"])
+        return _ref_objective(F, case, shape, array_valued=True)(F)
+
+    jac = jacobian(objective, mode='forward')(2.0).cpu().numpy().reshape(shape)
+    assert rel_l2(jac, gold["jvp_ad"]) <= 1e-10
+    assert rel_l2(jac, gold["fd_one_sided"]) <= ALLOWED_RATIO
+    assert rel_l2(jac, gold["fd_central"]) <= 1e-6
+    # the batched tangent sweep gives the same derivative (here summed over cells, per field component)
+    F = ceviche_b200.fdtd(2.0 * case["eps"], case["dL"], case["npml"])
+    series, dseries = F.jvp_run(case["steps"], torch.as_tensor(case["eps"])[None], case["sources"], case["probes"])
+    assert abs(float(dseries.sum()) - float(gold["jvp_ad"].sum())) <= 1e-9 * np.abs(gold["jvp_ad"]).sum()
+    assert abs(float(series.sum()) - float(gold["value"].sum())) <= 1e-10 * np.abs(gold["value"]).sum()
+
+
+def _loss(series, case):
+    w = torch.as_tensor(cases.objective_weights(case["steps"], len(case["probes"]))).to(series.device)
+    return (series ** 2 * w).sum()
+
+
+@pytest.mark.parametrize("every", [None, 1, 7, 1000])
+def test_checkpointed_adjoint_run_matches_autograd_oracle(every, golden_dir):
+    import ceviche_b200
+    case, gold = cases.grad_case("probe3d"), _gold(golden_dir, "probe3d")
+    eps = torch.as_tensor(case["eps"]).cuda().requires_grad_(True)
+    F = ceviche_b200.fdtd(eps, case["dL"], case["npml"])
+    series = F.run(case["steps"], case["sources"], case["probes"], checkpoint_every=every)
+    L = _loss(series, case)
+    assert abs(L.item() - float(gold["value"])) <= 1e-10 * abs(float(gold["value"]))
+    (g,) = torch.autograd.grad(L, eps)
+    g = g.cpu().numpy()
+    assert rel_l2(g, gold["grad_ad"]) <= 1e-10
+    cells = gold["fd_cells"]
+    picked = np.array([g[tuple(c)] for c in cells])
+    assert rel_l2(picked, gold["fd_central"]) <= 1e-6
+    assert rel_l2(picked, gold["fd_one_sided"]) <= ALLOWED_RATIO
+
+
+def test_run_and_per_step_gradients_agree():
+    import ceviche_b200
+    case = cases.grad_case("probe3d")
+    grads = []
+    for fused in (True, False):
+        eps = torch.as_tensor(case["eps"]).cuda().requires_grad_(True)
+        F = ceviche_b200.fdtd(eps, case["dL"], case["npml"])
+        if fused:
+            series = F.run(case["steps"], case["sources"], case["probes"])
+        else:
+            masks = [torch.as_tensor(m).cuda() for _, m in case["probes"]]
+            profs = [(c, torch.as_tensor(p).cuda(), w) for c, p, w in case["sources"]]
+            rows = []
+            for t in range(case["steps"]):
+                f = F.forward(**{"J" + c: p * float(w[t]) for c, p, w in profs})
+                rows.append(torch.stack([torch.sum(f[k] * m) for (k, _), m in zip(case["probes"], masks)]))
+            series = torch.stack(rows)
+        (g,) = torch.autograd.grad(_loss(series, case), eps)
+        grads.append(g.cpu().numpy())
+    assert rel_l2(grads[0], grads[1]) <= 1e-12
+
+
+def test_adjoint_identity_and_batched_jvp():
+    """<gbar, J v> = <J^T gbar, v> for random v, gbar; a batch of tangents equals one-by-one runs."""
+    import ceviche_b200
+    case = cases.grad_case("probe3d")
+    rng = np.random.default_rng(8)
+    shape = case["eps"].shape
+    V = torch.as_tensor(rng.standard_normal((3,) + shape))
+    gbar = torch.as_tensor(rng.standard_normal((case["steps"], len(case["probes"])))).cuda()
+    eps = torch.as_tensor(case["eps"]).cuda().requires_grad_(True)
+    F = ceviche_b200.fdtd(eps, case["dL"], case["npml"])
+    series = F.run(case["steps"], case["sources"], case["probes"])
+    (g,) = torch.autograd.grad((series * gbar).sum(), eps)
+    F2 = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"])
+    s2, ds = F2.jvp_run(case["steps"], V, case["sources"], case["probes"])
+    assert torch.equal(s2, series.detach())
+    for b in range(3):
+        lhs = float((gbar * ds[b]).sum())
+        rhs = float((g * V[b].cuda()).sum())
+        assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), abs(rhs)), (b, lhs, rhs)
+        F3 = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"])
+        _, d1 = F3.jvp_run(case["steps"], V[b:b + 1], case["sources"], case["probes"])
+        assert torch.equal(d1[0], ds[b])
+
+
+def test_fp32_gradients_within_tolerance(golden_dir):
+    import ceviche_b200
+    case, gold = cases.grad_case("probe3d"), _gold(golden_dir, "probe3d")
+    eps = torch.as_tensor(case["eps"]).cuda().requires_grad_(True)
+    F = ceviche_b200.fdtd(eps, case["dL"], case["npml"], dtype=torch.float32)
+    series = F.run(case["steps"], case["sources"], case["probes"])
+    (g,) = torch.autograd.grad(_loss(series, case), eps)
+    assert rel_l2(g.cpu().numpy(), gold["grad_ad"]) <= 1e-5
