@@ -210,8 +210,7 @@ def run_ours(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
     if world > 1:
-        from ceviche_b200 import slab
-        return slab.bench(args, dist, dev, dtype, hbm_peak, peak_src, ClockSampler, workload)
+        return run_slabs(args, dist, dev, local, rank, world, dtype, w, hbm_peak, peak_src)
 
     shape = tuple(args.grid)
     cells = shape[0] * shape[1] * shape[2]
@@ -330,6 +329,125 @@ def run_ours(args):
     print(json.dumps(line))
 
 
+def splitter_eps_slab(shape, lo, hi):
+    """Planes lo-1 .. hi-1 (periodic) of the config-3 permittivity: the config-2 splitter stretched to
+    the global grid, built slab by slab (the dense 1024x1024x512 array is never materialised)."""
+    Nx, Ny, Nz = shape
+    out = np.ones((hi - lo + 1, Ny, Nz))
+    cy, cz, off_max = Ny // 2, Nz // 2, 40 * Ny // 256
+    for q, i in enumerate(range(lo - 1, hi)):
+        i %= Nx
+        if i < Nx // 2:
+            centres = [cy]
+        else:
+            d = int(round(off_max * min(1.0, (i - Nx // 2) / max(1, (Nx // 2 - Nx // 8)))))
+            centres = [cy - d, cy + d]
+        for c in centres:
+            out[q, c - 5:c + 5, cz - 3:cz + 3] = 5.9536
+    return out
+
+
+def _box(i, j0, j1, k0, k1, Ny, Nz, val=1.0):
+    jj, kk = np.meshgrid(np.arange(j0, j1), np.arange(k0, k1), indexing="ij")
+    ijk = np.stack([np.full(jj.size, i), jj.ravel(), kk.ravel()], 1)
+    return {"ijk": ijk, "w": np.full(jj.size, val), "Ny": Ny, "Nz": Nz}
+
+
+def run_slabs(args, dist, dev, local, rank, world, dtype, w, hbm_peak, peak_src):
+    """N > 1: BASELINE config 3 -- 1024 x 1024 x 512 (npml 20) cut into x-slabs, one per GPU, NCCL halo
+    exchange.  Total work is fixed as N grows (strong scaling)."""
+    import ctypes as C
+    import torch
+    from ceviche_b200 import _lib
+    from ceviche_b200.constants import C_0
+    from ceviche_b200.slab import SlabFDTD, partition
+    shape = tuple(args.slab_grid)
+    Nx, Ny, Nz = shape
+    cells = Nx * Ny * Nz
+    chunk = args.slab_chunk
+    lo, hi = partition(Nx, world)[rank]
+    cy, cz, off = Ny // 2, Nz // 2, 40 * Ny // 256
+    sources = [("z", _box(30 * Nx // 256, cy - 5, cy + 5, cz - 3, cz + 3, Ny, Nz))]
+    probes = [("Ez", _box(226 * Nx // 256, c - 5, c + 5, cz - 3, cz + 3, Ny, Nz)) for c in (cy - off, cy + off)]
+    dt = 0.5 * DL / (np.sqrt(3) * C_0)
+    t = np.arange(chunk)
+    wave = (5 * np.exp(-(t - 2000) ** 2 / (2 * 100 ** 2)) * np.cos(2 * np.pi * C_0 / 2e-6 * dt * t))[:, None]
+    eps_local = splitter_eps_slab(shape, lo, hi)
+    sim = SlabFDTD(shape, eps_local, DL, NPML, dtype=dtype, device=dev)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        _lib.check(sim.be.plan.lib.cev_fdtd_set_option(sim.be.plan.handle, k.encode(), int(v)))
+    sim.prepare(sources, probes)
+    wave_dev = torch.as_tensor(wave).to(dev)
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+
+    for _ in range(args.warmup):
+        sim.run(chunk, wave_dev)
+    sync()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        ev0.record()
+        for _ in range(args.steps):
+            sim.run(chunk, wave_dev)
+        ev1.record()
+        sync()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    value = cells * chunk * args.steps / (ms * 1e-3) / 1e9
+
+    # per-kernel timing of the local H half-step (whole local slab, halo in place)
+    be = sim.be
+    be.new_partials(1)
+    reps = 20
+    for _ in range(3):
+        be.step_H(0, be.nx, -1)
+    torch.cuda.synchronize(dev)
+    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        be.step_H(0, be.nx, -1)
+    b_.record()
+    torch.cuda.synchronize(dev)
+    h_ms = a.elapsed_time(b_) / reps
+    local_cells = be.nx * Ny * Nz
+    h_gbs = local_cells * H_KERNEL_WORDS * w / (h_ms * 1e-3) / 1e9
+    step_gbs = value * B_ALG_WORDS * w / world
+
+    # end to end: host eps slab -> new simulator -> run -> series on the host
+    eps_host = torch.as_tensor(eps_local).pin_memory()
+    dist.barrier()
+    t0 = time.perf_counter()
+    sim2 = SlabFDTD(shape, eps_host.to(dev, non_blocking=True), DL, NPML, dtype=dtype, device=dev)
+    sim2.prepare(sources, probes)
+    out = sim2.run(chunk, torch.as_tensor(wave).pin_memory().to(dev, non_blocking=True)).cpu()
+    sync()
+    e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e)
+    if rank == 0:
+        line = {"metric": "Gcell-updates/s", "value": value, "unit": "Gcell/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": "config 3: 3-D %dx%dx%d splitter, npml 20, x-slabs over %d GPUs, NCCL halo exchange" % (shape + (world,)),
+                           "time_steps_per_bench_step": chunk, "planes_per_gpu": hi - lo,
+                           "l2": "per-GPU state %.0f MB >> 126 MB L2" % (local_cells * w * 9 / 1e6)},
+                "roofline": {"bound": "hbm", "kernel": "step_H on the local slab (12 words/cell)", "achieved": h_gbs, "peak": hbm_peak,
+                             "unit": "GB/s", "frac": h_gbs / hbm_peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": h_ms,
+                             "whole_step_per_gpu": {"achieved": step_gbs, "frac": step_gbs / hbm_peak}},
+                "cpu_baseline": None,
+                "e2e": {"value": cells * chunk / e2e_s / 1e9, "unit": "Gcell/s",
+                        "h2d_bytes_per_step": int(eps_host.numel() * 8 * world + wave.size * 8 * world),
+                        "d2h_bytes_per_step": int(chunk * len(probes) * 8 * world), "ms_per_step": e2e_s * 1e3},
+                "gpu_launches": int(args.steps * chunk * 5 + args.steps), "clocks": clk.summary()}
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -340,6 +458,8 @@ def main():
     ap.add_argument("--arith", default=None, choices=[None, "f64", "f32"])
     ap.add_argument("--chunk", type=int, default=1000, help="FDTD time steps per bench step")
     ap.add_argument("--grid", type=int, nargs=3, default=[256, 256, 256])
+    ap.add_argument("--slab-grid", type=int, nargs=3, default=[1024, 1024, 512], help="global grid for N > 1 (config 3)")
+    ap.add_argument("--slab-chunk", type=int, default=200, help="FDTD time steps per bench step for N > 1")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel tuning runs)")
     ap.add_argument("--opt", action="append", default=[], help="plan option name=value (repeatable)")

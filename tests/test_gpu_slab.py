@@ -1,0 +1,73 @@
+"""x-slab decomposition on real GPUs (needs >= 2): NCCL halo exchange, bit-identical to the 1-GPU run."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _case(shape, npml, steps, seed):
+    rng = np.random.default_rng(seed)
+    eps = 1 + 2 * rng.random(shape)
+    src = [("z", rng.random(shape) * (rng.random(shape) < 0.02), cases.modulated(steps, steps / 3, steps / 8, 9.0, 2.0)),
+           ("y", cases.one_hot(shape, (0, 1, 2)), cases.gaussian(steps, steps / 4, steps / 10)),
+           ("x", cases.one_hot(shape, (shape[0] // 2, 0, 0)), cases.gaussian(steps, steps / 5, steps / 10))]
+    probes = [("Ez", rng.random(shape)), ("Hy", cases.one_hot(shape, (shape[0] - 1, 2, 1))), ("Dx", rng.random(shape))]
+    return dict(eps=eps, dL=cases.DL, npml=list(npml), steps=steps, sources=src, probes=probes)
+
+
+def _worker(rank, world, port, shape, npml, steps, seed, dtype_name, out):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from ceviche_b200.slab import SlabFDTD, partition
+        case = _case(shape, npml, steps, seed)
+        lo, hi = partition(shape[0], world)[rank]
+        eps = case["eps"]
+        eps_local = np.concatenate([eps[(lo - 1) % shape[0]][None], eps[lo:hi]], 0)
+        sim = SlabFDTD(shape, eps_local, case["dL"], case["npml"], dtype=getattr(torch, dtype_name), device="cuda:%d" % rank)
+        sim.prepare([(c, p) for c, p, _ in case["sources"]], case["probes"])
+        wf = np.stack([w for _, _, w in case["sources"]], 1)
+        half = steps // 2
+        series = torch.cat([sim.run(half, wf[:half]), sim.run(steps - half, wf[half:])]).cpu().numpy()
+        fields = {k: sim.gather(k).cpu().numpy() for k in ("Ex", "Ey", "Ez", "Dx", "Dy", "Dz", "Hx", "Hy", "Hz")}
+        if rank == 0:
+            np.savez(out, series=series, **fields)
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("dtype_name", ["float64", "float32"])
+@pytest.mark.parametrize("shape,npml", [((24, 20, 72), (4, 3, 6)), ((14, 9, 40), (0, 2, 3))])
+def test_slabs_bit_identical_to_single_gpu(shape, npml, dtype_name, tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    import ceviche_b200
+    world = min(torch.cuda.device_count(), 4)
+    steps, seed = 30, 11
+    out = str(tmp_path / "slab.npz")
+    mp.spawn(_worker, args=(world, _free_port(), shape, npml, steps, seed, dtype_name, out), nprocs=world, join=True)
+    got = np.load(out)
+    case = _case(shape, npml, steps, seed)
+    F = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"], dtype=getattr(torch, dtype_name))
+    series = F.run(steps, case["sources"], case["probes"]).cpu().numpy()
+    for k in F.fields:
+        assert np.array_equal(got[k], F.fields[k].cpu().numpy()), k
+    np.testing.assert_allclose(got["series"], series, rtol=1e-11, atol=1e-12 * np.abs(series).max())

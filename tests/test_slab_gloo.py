@@ -1,0 +1,85 @@
+"""The multi-GPU slab driver's host logic on CPU: world_size-2 (and 3) gloo groups, numpy compute
+backend, against the single-domain oracle.  Covers the ring wrap (npml[0] = 0), uneven partitions,
+sources/probes on slab boundaries and two consecutive run() calls."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import cases
+from oracle.fdtd_numpy import OracleFDTD
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _case(shape, npml, steps, seed):
+    rng = np.random.default_rng(seed)
+    eps = 1 + 2 * rng.random(shape)
+    src = [("z", rng.random(shape) * (rng.random(shape) < 0.05), cases.modulated(steps, steps / 3, steps / 8, 9.0, 2.0)),
+           ("y", cases.one_hot(shape, (0, 1, 2)), cases.gaussian(steps, steps / 4, steps / 10)),
+           ("x", cases.one_hot(shape, (shape[0] // 2, 0, 0)), cases.gaussian(steps, steps / 5, steps / 10))]
+    probes = [("Ez", rng.random(shape)), ("Hy", cases.one_hot(shape, (shape[0] - 1, 2, 1))), ("Dx", rng.random(shape))]
+    return dict(eps=eps, dL=cases.DL, npml=list(npml), steps=steps, sources=src, probes=probes)
+
+
+def _worker(rank, world, port, shape, npml, steps, seed, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ceviche_b200.slab import SlabFDTD, partition
+        from slab_backend_cpu import NumpySlabBackend
+        case = _case(shape, npml, steps, seed)
+        lo, hi = partition(shape[0], world)[rank]
+        eps = case["eps"]
+        eps_local = np.concatenate([eps[(lo - 1) % shape[0]][None], eps[lo:hi]], 0)
+        sim = SlabFDTD(shape, eps_local, case["dL"], case["npml"], backend_factory=NumpySlabBackend)
+        sim.prepare([(c, p) for c, p, _ in case["sources"]], case["probes"])
+        wf = np.stack([w for _, _, w in case["sources"]], 1)
+        half = steps // 2
+        s1 = sim.run(half, wf[:half])
+        s2 = sim.run(steps - half, wf[half:])
+        series = torch.cat([s1, s2]).numpy()
+        fields = {k: sim.gather(k).numpy() for k in ("Ex", "Ey", "Ez", "Dx", "Dy", "Dz", "Hx", "Hy", "Hz")}
+        if rank == 0:
+            np.savez(out, series=series, **fields)
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world,shape,npml", [(2, (12, 7, 6), (3, 2, 2)), (2, (9, 6, 5), (0, 2, 0)), (3, (11, 5, 6), (2, 0, 2))])
+def test_slab_driver_matches_single_domain_oracle(world, shape, npml, tmp_path):
+    steps, seed = 40, 5
+    out = str(tmp_path / "slab.npz")
+    mp.spawn(_worker, args=(world, _free_port(), shape, npml, steps, seed, out), nprocs=world, join=True)
+    got = np.load(out)
+    case = _case(shape, npml, steps, seed)
+    O = OracleFDTD(case["eps"], case["dL"], case["npml"])
+    o_series, _ = O.run(steps, case["sources"], case["probes"])
+    for k, v in O.fields().items():
+        assert np.array_equal(got[k], v), k          # no arithmetic is reordered by the decomposition
+    np.testing.assert_allclose(got["series"], o_series, rtol=1e-12, atol=1e-12 * np.abs(o_series).max())
+
+
+def test_partition_and_localize():
+    from ceviche_b200.slab import localize_points, partition
+    assert partition(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    assert partition(8, 8) == [(i, i + 1) for i in range(8)]
+    a = np.zeros((6, 2, 3))
+    a[2, 1, 2], a[3, 0, 0], a[5, 1, 1] = 1.5, -2.0, 3.0
+    idx, w = localize_points(a, 2, 4, 6)
+    assert idx.tolist() == [5, 6] and w.tolist() == [1.5, -2.0]
+    idx, w = localize_points(a, 4, 6, 6)
+    assert idx.tolist() == [6 + 4] and w.tolist() == [3.0]
