@@ -8,6 +8,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
+#include <memory>
+#include <numeric>
 #include <string>
 #include <vector>
 
@@ -84,6 +87,14 @@ struct cev_fdtd {
     int nsrc = 0;
     int64_t n_src_pts = 0;
     DeviceBuf src_comp, src_id, src_cell, src_weight;
+    std::vector<int32_t> h_src_comp, h_src_id;      // host copies: re-sorted per kernel tiling
+    std::vector<int64_t> h_src_cell;
+    std::vector<double> h_src_w;
+    struct SrcTiling {                              // source points sorted by owning CTA of one launch geometry
+        int x0, x1, xchunk, lz, vec;
+        DeviceBuf begin, comp, id, cell, w;
+    };
+    std::vector<std::unique_ptr<SrcTiling>> src_tilings;
     // probes
     int nprobe = 0, n_slots = 0, n_slots_ED = 0;
     std::vector<int32_t> slot_probe;
@@ -220,6 +231,69 @@ void set_tiles_v2(const cev_fdtd* p, StepArgs<T, AT>& a, int64_t x0, int64_t x1)
     a.n_tiles = nx > 0 ? cols * ((nx + chunk - 1) / chunk) : 0;
 }
 
+// Source points of the x-planes [a.x0, a.x1), sorted by the CTA of the marching D kernel that owns
+// their cell (built once per launch geometry, cached in the plan).
+template <typename T, typename AT>
+int attach_sources_v2(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row) {
+    constexpr int V = vec_width<T>();
+    cev_fdtd::SrcTiling* hit = nullptr;
+    for (auto& t : p->src_tilings)
+        if (t->x0 == a.x0 && t->x1 == a.x1 && t->xchunk == a.xchunk && t->lz == p->lz && t->vec == V) hit = t.get();
+    if (!hit) {
+        const int LZ = p->lz, rows = V2_BY * (32 / LZ);
+        const int64_t plane = (int64_t)a.Ny * a.Nz;
+        std::vector<int> owner;
+        std::vector<int64_t> pick;
+        for (int64_t q = 0; q < p->n_src_pts; ++q) {
+            const int64_t cell = p->h_src_cell[q];
+            const int i = (int)(cell / plane), j = (int)((cell % plane) / a.Nz), k = (int)(cell % a.Nz);
+            if (i < a.x0 || i >= a.x1) continue;
+            const int bid = (((i - a.x0) / a.xchunk) * a.nty + j / rows) * a.ntz + k / (LZ * V);
+            owner.push_back(bid);
+            pick.push_back(q);
+        }
+        std::vector<int64_t> order(pick.size());
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return owner[x] < owner[y]; });
+        const int64_t m = (int64_t)pick.size();
+        std::vector<int> begin(a.n_tiles + 1, 0);
+        std::vector<int32_t> comp(m), id(m), cell(m);
+        std::vector<double> w(m);
+        for (int64_t r = 0; r < m; ++r) {
+            const int64_t q = pick[order[r]];
+            begin[owner[order[r]] + 1]++;
+            comp[r] = p->h_src_comp[q];
+            id[r] = p->h_src_id[q];
+            cell[r] = (int32_t)p->h_src_cell[q];
+            w[r] = p->h_src_w[q];
+        }
+        for (int b = 0; b < a.n_tiles; ++b) begin[b + 1] += begin[b];
+        std::unique_ptr<cev_fdtd::SrcTiling> t(new cev_fdtd::SrcTiling());
+        t->x0 = a.x0; t->x1 = a.x1; t->xchunk = a.xchunk; t->lz = p->lz; t->vec = V;
+        const size_t mm = (size_t)(m > 0 ? m : 1);
+        if (t->begin.alloc(begin.size() * 4) || t->comp.alloc(mm * 4) || t->id.alloc(mm * 4) || t->cell.alloc(mm * 4) ||
+            t->w.alloc(mm * 8))
+            return -1;
+        CUDA_TRY(cudaMemcpy(t->begin.p, begin.data(), begin.size() * 4, cudaMemcpyHostToDevice));
+        if (m) {
+            CUDA_TRY(cudaMemcpy(t->comp.p, comp.data(), m * 4, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(t->id.p, id.data(), m * 4, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(t->cell.p, cell.data(), m * 4, cudaMemcpyHostToDevice));
+            CUDA_TRY(cudaMemcpy(t->w.p, w.data(), m * 8, cudaMemcpyHostToDevice));
+        }
+        if (p->src_tilings.size() >= 8) p->src_tilings.erase(p->src_tilings.begin());
+        p->src_tilings.push_back(std::move(t));
+        hit = p->src_tilings.back().get();
+    }
+    a.src_begin = (const int*)hit->begin.p;
+    a.src_comp = (const int32_t*)hit->comp.p;
+    a.src_id = (const int32_t*)hit->id.p;
+    a.src_cell = (const int32_t*)hit->cell.p;
+    a.src_w = (const double*)hit->w.p;
+    a.src_wave = wave_row;
+    return 0;
+}
+
 // which: 0 = E/D-family slots, 1 = H-family slots
 template <typename T, typename AT>
 int attach_probes(const cev_fdtd* p, StepArgs<T, AT>& a, int which, int64_t t, double* partials) {
@@ -259,9 +333,15 @@ int launch_H(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, void* con
 }
 
 template <typename T, typename AT>
+int launch_inject(cev_fdtd* p, const cev_state* st, void* const D_out[3], const double* wave_row, int64_t x0, int64_t x1,
+                  cudaStream_t s);
+
+// wave_row != NULL: the plan's sparse sources of planes [x0, x1) are injected (fused into the marching
+// kernel; a small follow-up kernel after the baseline one).
+template <typename T, typename AT>
 int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const E_out[3], const void* const J[3],
-             const double J_scale[3], const double* const J_wave[3], int64_t x0, int64_t x1, int64_t probe_t,
-             double* partials, cudaStream_t s) {
+             const double J_scale[3], const double* const J_wave[3], const double* wave_row, int64_t x0, int64_t x1,
+             int64_t probe_t, double* partials, cudaStream_t s) {
     StepArgs<T, AT> a;
     if (fill_args(p, st, a)) return -1;
     for (int A = 0; A < 3; ++A) {
@@ -278,6 +358,8 @@ int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const
     const bool march = can_march(p, a, false);
     if (march) set_tiles_v2(p, a, x0, x1);
     else set_tiles_v1(a, x0, x1);
+    const bool inject = wave_row && p->n_src_pts > 0 && x1 > x0;
+    if (inject && march && attach_sources_v2(p, a, wave_row)) return -1;
     const int aux = attach_probes(p, a, 1, probe_t, partials);
     if (a.n_tiles + aux == 0) return 0;
     const bool extras = a.J[0] || a.J[1] || a.J[2] || a.Eout[0] || a.Eout[1] || a.Eout[2];
@@ -297,11 +379,13 @@ int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const
     }
     else k_step_D_v1<T, AT><<<a.n_tiles + aux, dim3(V1_TZ, V1_TY), 0, s>>>(a);
     CUDA_TRY(cudaGetLastError());
+    if (inject && !march) return launch_inject<T, AT>(p, st, D_out, wave_row, x0, x1, s);
     return 0;
 }
 
 template <typename T, typename AT>
-int launch_inject(cev_fdtd* p, const cev_state* st, const double* wave_row, cudaStream_t s) {
+int launch_inject(cev_fdtd* p, const cev_state* st, void* const D_out[3], const double* wave_row, int64_t x0, int64_t x1,
+                  cudaStream_t s) {
     if (p->n_src_pts == 0) return 0;
     SourceTable t;
     t.n = p->n_src_pts;
@@ -310,9 +394,10 @@ int launch_inject(cev_fdtd* p, const cev_state* st, const double* wave_row, cuda
     t.cell = (const int64_t*)p->src_cell.p;
     t.weight = (const double*)p->src_weight.p;
     T* D[3];
-    for (int A = 0; A < 3; ++A) D[A] = (T*)st->D[p->to_logical(A)];
+    for (int A = 0; A < 3; ++A) D[A] = (T*)(D_out ? D_out[p->to_logical(A)] : st->D[p->to_logical(A)]);
+    const int64_t plane = (int64_t)p->N[1] * p->N[2];
     const int bs = 128;
-    k_inject<T, AT><<<(unsigned)((t.n + bs - 1) / bs), bs, 0, s>>>(t, D[0], D[1], D[2], wave_row);
+    k_inject<T, AT><<<(unsigned)((t.n + bs - 1) / bs), bs, 0, s>>>(t, D[0], D[1], D[2], wave_row, x0 * plane, x1 * plane);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -354,8 +439,9 @@ int run_loop(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* wav
         // E/D probes of step n-1 ride on the H launch of step n (D is read-only there);
         // H probes of step n ride on its D launch (H is read-only there).
         if (launch_H<T, AT>(p, st, nullptr, nullptr, 0, Nx, n - 1, partials, s)) return -1;
-        if (launch_D<T, AT>(p, st, nullptr, nullptr, nullptr, nullptr, nullptr, 0, Nx, n, partials, s)) return -1;
-        if (waveform && launch_inject<T, AT>(p, st, waveform + n * p->nsrc, s)) return -1;
+        if (launch_D<T, AT>(p, st, nullptr, nullptr, nullptr, nullptr, nullptr, waveform ? waveform + n * p->nsrc : nullptr, 0,
+                            Nx, n, partials, s))
+            return -1;
     }
     if (nsteps > 0 && launch_probe_only<T, AT>(p, st, nullptr, 0, nsteps - 1, partials, s)) return -1;
     return 0;
@@ -372,10 +458,13 @@ int jvp_loop(cev_fdtd* p, const cev_state* st, int B, const cev_state* tst, cons
         for (int b = 0; b < B; ++b)
             if (launch_H<T, AT>(p, &tst[b], &tan[b], nullptr, 0, Nx, n - 1, tpartials ? tpartials + b * stride : nullptr, s)) return -1;
         if (launch_H<T, AT>(p, st, nullptr, nullptr, 0, Nx, n - 1, partials, s)) return -1;
-        if (launch_D<T, AT>(p, st, nullptr, nullptr, nullptr, nullptr, nullptr, 0, Nx, n, partials, s)) return -1;
-        if (waveform && launch_inject<T, AT>(p, st, waveform + n * p->nsrc, s)) return -1;
+        if (launch_D<T, AT>(p, st, nullptr, nullptr, nullptr, nullptr, nullptr, waveform ? waveform + n * p->nsrc : nullptr, 0,
+                            Nx, n, partials, s))
+            return -1;
         for (int b = 0; b < B; ++b)
-            if (launch_D<T, AT>(p, &tst[b], nullptr, nullptr, nullptr, nullptr, nullptr, 0, Nx, n, tpartials ? tpartials + b * stride : nullptr, s)) return -1;
+            if (launch_D<T, AT>(p, &tst[b], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, Nx, n,
+                                tpartials ? tpartials + b * stride : nullptr, s))
+                return -1;
     }
     if (nsteps > 0) {
         if (launch_probe_only<T, AT>(p, st, nullptr, 0, nsteps - 1, partials, s)) return -1;
@@ -588,6 +677,9 @@ int cev_fdtd_destroy(cev_fdtd* p) {
     DeviceGuard guard(p->device);
     p->tables.release();
     p->src_comp.release(); p->src_id.release(); p->src_cell.release(); p->src_weight.release();
+    for (auto& t : p->src_tilings) {
+        t->begin.release(); t->comp.release(); t->id.release(); t->cell.release(); t->w.release();
+    }
     p->pr_field.release(); p->pr_wbegin.release(); p->pr_ibegin.release(); p->pr_cell0.release();
     p->pr_n.release(); p->pr_idx.release(); p->pr_weight.release(); p->pr_owner.release();
     delete p;
@@ -654,14 +746,8 @@ int cev_fdtd_step_D_ex(cev_fdtd* p, const cev_state* st, void* const D_out[3], v
     if (check_range(p, x0, x1)) return -1;
     DeviceGuard guard(p->device);
     const int64_t a0 = p->rot ? 0 : x0, a1 = p->rot ? p->N[0] : x1;
-    if (DISPATCH(p, launch_D, p, st, D_out, E_out, J, J_scale, (const double* const*)nullptr, a0, a1, probe_t, partials,
-                 (cudaStream_t)stream))
-        return -1;
-    if (waveform_row && p->n_src_pts > 0) {
-        if (D_out) return fail("source injection works on the in-place D (pass D_out = NULL)");
-        return DISPATCH(p, launch_inject, p, st, waveform_row, (cudaStream_t)stream);
-    }
-    return 0;
+    return DISPATCH(p, launch_D, p, st, D_out, E_out, J, J_scale, (const double* const*)nullptr, waveform_row, a0, a1,
+                    probe_t, partials, (cudaStream_t)stream);
 }
 
 int cev_fdtd_sample_probes(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, int which, int64_t t, double* partials,
@@ -701,8 +787,8 @@ int cev_fdtd_step_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void
     if (check_range(p, x0, x1)) return -1;
     DeviceGuard guard(p->device);
     const int64_t a0 = p->rot ? 0 : x0, a1 = p->rot ? p->N[0] : x1;
-    return DISPATCH(p, launch_D, p, st, D_out, E_out, J, J_scale, (const double* const*)nullptr, a0, a1, (int64_t)-1,
-                    (double*)nullptr, (cudaStream_t)stream);
+    return DISPATCH(p, launch_D, p, st, D_out, E_out, J, J_scale, (const double* const*)nullptr, (const double*)nullptr, a0,
+                    a1, (int64_t)-1, (double*)nullptr, (cudaStream_t)stream);
 }
 
 int cev_fdtd_compute_E(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, void* const E_out[3], void* stream) {
@@ -742,6 +828,20 @@ int cev_fdtd_set_sources(cev_fdtd* p, int nsrc, const cev_points* src) {
         CUDA_TRY(cudaMemcpy(p->src_comp.p, comp.data(), total * 4, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(p->src_id.p, id.data(), total * 4, cudaMemcpyHostToDevice));
     }
+    p->h_src_comp = comp;
+    p->h_src_id = id;
+    p->h_src_cell.resize(total);
+    p->h_src_w.resize(total);
+    if (total) {
+        CUDA_TRY(cudaMemcpy(p->h_src_cell.data(), p->src_cell.p, total * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(p->h_src_w.data(), p->src_weight.p, total * 8, cudaMemcpyDeviceToHost));
+        for (int64_t q = 0; q < total; ++q)
+            if (p->h_src_cell[q] < 0 || p->h_src_cell[q] >= ncell) return fail("source point outside the grid");
+    }
+    for (auto& t : p->src_tilings) {
+        t->begin.release(); t->comp.release(); t->id.release(); t->cell.release(); t->w.release();
+    }
+    p->src_tilings.clear();
     return 0;
 }
 

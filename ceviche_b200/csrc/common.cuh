@@ -64,6 +64,15 @@ struct StepArgs {
     const T* J[3];      // dense source per component (nullable)
     AT       Jscale[3];
     const double* Jwave[3];   // nullable device scalar overriding Jscale (waveform entry)
+    // sparse sources J(t) = sum_s profile_s * waveform[t, s] (fdtd.py:125-127 for the callers' J = profile *
+    // scalar(t), utils.py:328), injected by the D half-step itself: the points are pre-sorted by the CTA
+    // that owns their cell; src_begin[bid] .. src_begin[bid+1] is CTA bid's run.  src_wave == NULL: none.
+    const int*     src_begin;
+    const int32_t* src_comp;
+    const int32_t* src_id;
+    const int32_t* src_cell;
+    const double*  src_w;
+    const double*  src_wave;
     // tiling + auxiliary probe CTAs appended to the grid
     int n_tiles, ntz, nty, xchunk;
     int pf_dist;              // L2 prefetch distance in x-planes (0 = off)

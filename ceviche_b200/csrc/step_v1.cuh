@@ -179,9 +179,11 @@ struct SourceTable {
 };
 
 template <typename T, typename AT>
-__global__ void k_inject(SourceTable s, T* D0, T* D1, T* D2, const double* __restrict__ wave_row) {
+__global__ void k_inject(SourceTable s, T* D0, T* D1, T* D2, const double* __restrict__ wave_row, int64_t cell_lo,
+                         int64_t cell_hi) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= s.n) return;
+    if (s.cell[q] < cell_lo || s.cell[q] >= cell_hi) return;   // only the x-planes this launch updated
     T* D = s.comp[q] == 0 ? D0 : (s.comp[q] == 1 ? D1 : D2);
     const T add = (T)(s.weight[q] * wave_row[s.src[q]]);
     atomicAdd(&D[s.cell[q]], add);

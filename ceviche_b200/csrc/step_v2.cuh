@@ -39,8 +39,9 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 }
 
 constexpr int V2_BY = 4;        // warps per CTA; a warp covers LZ lanes along z times 32/LZ rows
-// register caps = 65536 / (MIN_CTAS * 128) per thread; tuned on B200 (scripts/tune.py): the H kernel
-// carries more state and prefers fewer, fatter CTAs; the D kernel prefers occupancy
+// register caps = 65536 / (MIN_CTAS * 128) per thread; tuned on B200 (scripts/tune.py, 256^3 with and
+// without PML): the H kernel carries more state and prefers fewer, fatter CTAs (3 for fp64, 4 for fp32);
+// the D kernel prefers occupancy
 #ifndef V2_H_MIN_CTAS
 #define V2_H_MIN_CTAS 3
 #endif
@@ -153,7 +154,7 @@ struct PmlCtx {
 };
 
 template <typename T, typename AT, int V, int LZ>
-__global__ void __launch_bounds__(32 * V2_BY, V2_H_MIN_CTAS) k_step_H_v2(const StepArgs<T, AT> a) {
+__global__ void __launch_bounds__(32 * V2_BY, (sizeof(T) == 8 ? V2_H_MIN_CTAS : V2_H_MIN_CTAS + 1)) k_step_H_v2(const StepArgs<T, AT> a) {
     const int bid = blockIdx.x;
     if (bid >= a.n_tiles) {
         probe_block<T, AT>(a, a.aux_slot0 + (bid - a.n_tiles));
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(32 * V2_BY, V2_D_MIN_CTAS) k_step_D_v2(const S
     const int ty = rest % a.nty;
     const int xc = rest / a.nty;
     const int jraw = (ty * V2_BY + threadIdx.y) * RW + ly;
-    if (jraw - ly >= a.Ny) return;               // warp-uniform: the whole warp is below the grid
+    const bool warp_on = jraw - ly < a.Ny;       // warp-uniform; no early return: the CTA meets at a barrier below
     const int k0raw = (tz * LZ + lz) * V;
     const bool active = k0raw < a.Nz && jraw < a.Ny;
     const int j = jraw < a.Ny ? jraw : a.Ny - 1; // inactive lanes shadow a valid cell (loads only)
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(32 * V2_BY, V2_D_MIN_CTAS) k_step_D_v2(const S
         }
     }
 
-    for (int i = xs; i < xe; ++i) {
+    for (int i = xs; i < (warp_on ? xe : xs); ++i) {
         const int pbase = i * plane;
         Vec<T, V> h[3], d[3], jv[3], mev[3];
 #pragma unroll
@@ -409,6 +410,18 @@ __global__ void __launch_bounds__(32 * V2_BY, V2_D_MIN_CTAS) k_step_D_v2(const S
                 }
                 stv<T, V>(a.Dout[c] + pbase + orow, out[c]);
             }
+        }
+    }
+
+    // ---- in-kernel source injection: D += J after the update (fdtd.py:125-127)
+    if (a.src_wave) {
+        __syncthreads();                         // every D store of this CTA has been issued and is visible CTA-wide
+        const int tid = threadIdx.y * 32 + threadIdx.x;
+        const int qe = a.src_begin[bid + 1];
+        for (int q = a.src_begin[bid] + tid; q < qe; q += 32 * V2_BY) {
+            const int c = a.src_comp[q];
+            T* Dc = c == 0 ? a.Dout[0] : (c == 1 ? a.Dout[1] : a.Dout[2]);
+            atomicAdd(Dc + a.src_cell[q], (T)(a.src_w[q] * a.src_wave[a.src_id[q]]));
         }
     }
 }

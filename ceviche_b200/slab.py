@@ -135,21 +135,14 @@ class CudaSlabBackend:
         _lib.check(self.plan.lib.cev_fdtd_step_H_ex(self.plan.handle, C.byref(st), None, None, x0, x1, probe_t,
                                                     self.partials.data_ptr() if self.n_slots else None, self._s()))
 
-    def step_D(self, x0, x1, probe_t):
+    def step_D(self, x0, x1, probe_t, wave_row):
+        """D half-step of planes [x0, x1); the sources lying in those planes are injected in-kernel."""
         if x1 <= x0:
             return
         st = self._state()
-        _lib.check(self.plan.lib.cev_fdtd_step_D_ex(self.plan.handle, C.byref(st), None, None, None, None, None, x0, x1,
-                                                    probe_t, self.partials.data_ptr() if self.n_slots else None, self._s()))
-
-    def inject(self, wave_row):
-        """In-place J injection of the local source points (after ALL local D planes are updated)."""
-        if self.n_sources == 0:
-            return
-        st = self._state()
-        # zero-plane D launch: only the injection part of step_D_ex runs
         _lib.check(self.plan.lib.cev_fdtd_step_D_ex(self.plan.handle, C.byref(st), None, None, None, None,
-                                                    wave_row.data_ptr(), 0, 0, -1, None, self._s()))
+                                                    wave_row.data_ptr() if self.n_sources else None, x0, x1, probe_t,
+                                                    self.partials.data_ptr() if self.n_slots else None, self._s()))
 
     def sample(self, which, t):
         if self.n_slots == 0:
@@ -257,15 +250,13 @@ class SlabFDTD:
                 be.step_H(nx - 1, nx, -1)
                 self._exchange([be.H[1][nx - 1], be.H[2][nx - 1]], self.right, [be.H_lo[1], be.H_lo[2]], self.left)
                 # ---- D half-step (fdtd.py:105-127): interior, then the plane that needs the left neighbour's H
-                be.step_D(1, nx, n)
+                be.step_D(1, nx, n, wf[n])
                 self._wait()
-                be.step_D(0, 1, -1)
-                be.inject(wf[n])
+                be.step_D(0, 1, -1, wf[n])
                 self._exchange([be.D[1][0], be.D[2][0]], self.left, [be.D_hi[1], be.D_hi[2]], self.right)
             else:
                 be.step_H(0, nx, n - 1)
-                be.step_D(0, nx, n)
-                be.inject(wf[n])
+                be.step_D(0, nx, n, wf[n])
         if steps > 0:
             be.sample(0, steps - 1)
         self.t_index += steps

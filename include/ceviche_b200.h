@@ -127,8 +127,9 @@ int cev_fdtd_compute_E(cev_fdtd* plan, const cev_state* st, const cev_tangent* t
 
 /* Extended half-steps used by the slab driver and the derivative sweeps: optional tangent inputs,
  * probe sampling riding on the launch (probe_t >= 0: E/D probes of the PREVIOUS step on an H launch,
- * H probes of THIS step on a D launch, written to row probe_t of partials), and in-place injection of
- * the plan's sources scaled by waveform_row[n_sources] (device) after the D update. */
+ * H probes of THIS step on a D launch, written to row probe_t of partials), and in-kernel injection of
+ * the plan's sources lying in planes [x0, x1), scaled by waveform_row[n_sources] (device), after the D
+ * update (fdtd.py:125-127). */
 int cev_fdtd_step_H_ex(cev_fdtd* plan, const cev_state* st, const cev_tangent* tan, void* const H_out[3],
                        int64_t x0, int64_t x1, int64_t probe_t, double* partials, void* stream);
 int cev_fdtd_step_D_ex(cev_fdtd* plan, const cev_state* st, void* const D_out[3], void* const E_out[3],

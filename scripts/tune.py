@@ -16,8 +16,9 @@ dtype = torch.float64 if sys.argv[2] == "f64" else torch.float32
 w = 8 if dtype == torch.float64 else 4
 shape = (N, N, N)
 eps = 1 + np.random.default_rng(0).random(shape)
-NPML = int(os.environ.get("TUNE_NPML", "20"))
-F = ceviche_b200.fdtd(eps, 5e-8, [NPML] * 3, dtype=dtype)
+NPML = [int(v) for v in os.environ.get("TUNE_NPML", "20,20,20").split(",")]
+NPML = NPML * 3 if len(NPML) == 1 else NPML
+F = ceviche_b200.fdtd(eps, 5e-8, NPML, dtype=dtype)
 for t in F._H + F._D:
     t.normal_()
 plan = F._ensure_plan()

@@ -75,7 +75,7 @@ class NumpySlabBackend:
             self.I["IH"][c][x0:x1] = self.I["IH"][c][x0:x1] + H[x0:x1]
             H[x0:x1] = m1 * H[x0:x1] + m2 * CE[c] + m3 * self.I["ICE"][c][x0:x1] + m4 * self.I["IH"][c][x0:x1]
 
-    def step_D(self, x0, x1, probe_t):
+    def step_D(self, x0, x1, probe_t, wave_row):
         if x1 <= x0:
             return
         self._probe(1, probe_t)
@@ -100,10 +100,10 @@ class NumpySlabBackend:
             self.I["ICH"][c][x0:x1] = self.I["ICH"][c][x0:x1] + CH[c]
             self.I["ID"][c][x0:x1] = self.I["ID"][c][x0:x1] + D[x0:x1]
             D[x0:x1] = m1 * D[x0:x1] + m2 * CH[c] + m3 * self.I["ICH"][c][x0:x1] + m4 * self.I["ID"][c][x0:x1]
-
-    def inject(self, wave_row):
-        for s, (comp, idx, w) in enumerate(self.sources):
-            self.D[comp].numpy().reshape(-1)[idx] += w * float(wave_row[s])
+        plane = self.Ny * self.Nz
+        for s, (comp, idx, w) in enumerate(self.sources):      # sources of the planes just updated
+            sel = (idx >= x0 * plane) & (idx < x1 * plane)
+            self.D[comp].numpy().reshape(-1)[idx[sel]] += w[sel] * float(wave_row[s])
 
     def sample(self, which, t):
         self._probe(which, t)
