@@ -76,6 +76,8 @@ struct cev_fdtd {
     int xchunk = 0;              // 0 auto
     int pf_dist = 1;             // L2 prefetch distance of the marching kernels (planes)
     int lz = 8;                  // lanes of a warp along z in the marching kernels (8, 16 or 32)
+    int split = 0;               // 1: separate launches for the PML-free interior box and the PML shell
+    int in_lo[3] = {0, 0, 0}, in_hi[3] = {0, 0, 0};   // per internal axis: longest index run off the PML (H and D sampling)
     DeviceBuf tables;            // u/r (f32 + f64) and maps for 3 axes x {H, D}
     const void* uH[3][2];        // [axis][0: f32, 1: f64]
     const void* rH[3][2];
@@ -91,7 +93,7 @@ struct cev_fdtd {
     std::vector<int64_t> h_src_cell;
     std::vector<double> h_src_w;
     struct SrcTiling {                              // source points sorted by owning CTA of one launch geometry
-        int x0, x1, xchunk, lz, vec;
+        int x0, x1, xchunk, lz, vec, part;
         DeviceBuf begin, comp, id, cell, w;
     };
     std::vector<std::unique_ptr<SrcTiling>> src_tilings;
@@ -209,36 +211,79 @@ bool can_march(const cev_fdtd* p, const StepArgs<T, AT>& a, bool isH) {
     return p->variant == 2 || a.Nz >= 2 * V;
 }
 
+// Tiling of one marching launch over a list of boxes.  part: 0 = the whole range [x0,x1) x Ny x Nz in one
+// box (general kernel); 1 = the PML-free interior box clipped to [x0,x1); 2 = the shell = the rest, as up to six slabs.
 template <typename T, typename AT>
-void set_tiles_v2(const cev_fdtd* p, StepArgs<T, AT>& a, int64_t x0, int64_t x1) {
+void set_tiles_v2(const cev_fdtd* p, StepArgs<T, AT>& a, int64_t x0, int64_t x1, int part) {
     constexpr int V = vec_width<T>();
+    const int LZ = p->lz, rows = V2_BY * (32 / LZ);
     a.x0 = (int)x0;
     a.x1 = (int)x1;
-    const int LZ = p->lz, rows = V2_BY * (32 / LZ);
-    a.ntz = (a.Nz + LZ * V - 1) / (LZ * V);
-    a.nty = (a.Ny + rows - 1) / rows;
-    const int nx = (int)(x1 - x0);
-    const int cols = a.ntz * a.nty;
     int chunk = p->xchunk;
     if (chunk <= 0) {
         // short chunks keep the concurrently-active working set (CTAs x streams x planes) inside L2
         // and give the scheduler many CTAs to balance; tuned on B200 (scripts/tune.py)
+        const int cols = ((a.Nz + LZ * V - 1) / (LZ * V)) * ((a.Ny + rows - 1) / rows);
         chunk = cols >= 512 ? 8 : 4;
-        if (chunk > nx) chunk = nx > 0 ? nx : 1;
     }
     a.xchunk = chunk;
     a.pf_dist = p->pf_dist;
-    a.n_tiles = nx > 0 ? cols * ((nx + chunk - 1) / chunk) : 0;
+    a.n_boxes = 0;
+    int cta = 0;
+    auto add = [&](int bx0, int bx1, int by0, int by1, int bz0, int bz1) {
+        if (bx1 <= bx0 || by1 <= by0 || bz1 <= bz0) return;
+        Box& B = a.box[a.n_boxes++];
+        B.x0 = bx0; B.x1 = bx1; B.y0 = by0; B.y1 = by1; B.z0 = bz0; B.z1 = bz1;
+        B.ntz = (bz1 - bz0 + LZ * V - 1) / (LZ * V);
+        B.nty = (by1 - by0 + rows - 1) / rows;
+        B.cta0 = cta;
+        cta += B.ntz * B.nty * ((bx1 - bx0 + chunk - 1) / chunk);
+    };
+    const int X0 = (int)x0, X1 = (int)x1;
+    // interior box (z limits rounded inwards to the vector width)
+    const int ix0 = std::max(X0, p->in_lo[0]), ix1 = std::min(X1, p->in_hi[0]);
+    const int iy0 = p->in_lo[1], iy1 = p->in_hi[1];
+    const int iz0 = (p->in_lo[2] + V - 1) / V * V, iz1 = p->in_hi[2] / V * V;
+    if (part == 0) {
+        add(X0, X1, 0, a.Ny, 0, a.Nz);
+    } else if (part == 1) {
+        add(ix0, ix1, iy0, iy1, iz0, iz1);
+    } else {
+        add(X0, std::min(ix0, X1), 0, a.Ny, 0, a.Nz);          // x-low slab (or everything if no interior x here)
+        add(std::max(ix1, std::min(ix0, X1)), X1, 0, a.Ny, 0, a.Nz);   // x-high slab
+        add(ix0, ix1, 0, iy0, 0, a.Nz);                        // y-low
+        add(ix0, ix1, iy1, a.Ny, 0, a.Nz);                     // y-high
+        add(ix0, ix1, iy0, iy1, 0, iz0);                       // z-low
+        add(ix0, ix1, iy0, iy1, iz1, a.Nz);                    // z-high
+    }
+    a.n_tiles = cta;
+    a.ntz = a.n_boxes ? a.box[0].ntz : 1;
+    a.nty = a.n_boxes ? a.box[0].nty : 1;
+}
+
+// Is it worth (and possible) to split [x0,x1) into an interior launch and a shell launch?
+template <typename T>
+bool want_split(const cev_fdtd* p, int64_t x0, int64_t x1) {
+    if (!p->split) return false;
+    constexpr int V = vec_width<T>();
+    const int64_t ix = std::min<int64_t>(x1, p->in_hi[0]) - std::max<int64_t>(x0, p->in_lo[0]);
+    const int64_t iy = p->in_hi[1] - p->in_lo[1];
+    const int64_t iz = p->in_hi[2] / V * V - (p->in_lo[2] + V - 1) / V * V;
+    if (ix <= 0 || iy <= 0 || iz <= 0) return false;
+    const int64_t all = (x1 - x0) * p->N[1] * p->N[2];
+    const int64_t inner = ix * iy * iz;
+    return inner != all && inner * 8 >= all && inner >= 32768;   // some PML, a worthwhile interior
 }
 
 // Source points of the x-planes [a.x0, a.x1), sorted by the CTA of the marching D kernel that owns
 // their cell (built once per launch geometry, cached in the plan).
 template <typename T, typename AT>
-int attach_sources_v2(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row) {
+int attach_sources_v2(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row, int part) {
     constexpr int V = vec_width<T>();
     cev_fdtd::SrcTiling* hit = nullptr;
     for (auto& t : p->src_tilings)
-        if (t->x0 == a.x0 && t->x1 == a.x1 && t->xchunk == a.xchunk && t->lz == p->lz && t->vec == V) hit = t.get();
+        if (t->x0 == a.x0 && t->x1 == a.x1 && t->xchunk == a.xchunk && t->lz == p->lz && t->vec == V && t->part == part)
+            hit = t.get();
     if (!hit) {
         const int LZ = p->lz, rows = V2_BY * (32 / LZ);
         const int64_t plane = (int64_t)a.Ny * a.Nz;
@@ -247,10 +292,13 @@ int attach_sources_v2(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row) {
         for (int64_t q = 0; q < p->n_src_pts; ++q) {
             const int64_t cell = p->h_src_cell[q];
             const int i = (int)(cell / plane), j = (int)((cell % plane) / a.Nz), k = (int)(cell % a.Nz);
-            if (i < a.x0 || i >= a.x1) continue;
-            const int bid = (((i - a.x0) / a.xchunk) * a.nty + j / rows) * a.ntz + k / (LZ * V);
-            owner.push_back(bid);
-            pick.push_back(q);
+            for (int b = 0; b < a.n_boxes; ++b) {
+                const Box& B = a.box[b];
+                if (i < B.x0 || i >= B.x1 || j < B.y0 || j >= B.y1 || k < B.z0 || k >= B.z1) continue;
+                owner.push_back(B.cta0 + (((i - B.x0) / a.xchunk) * B.nty + (j - B.y0) / rows) * B.ntz + (k - B.z0) / (LZ * V));
+                pick.push_back(q);
+                break;
+            }
         }
         std::vector<int64_t> order(pick.size());
         std::iota(order.begin(), order.end(), 0);
@@ -269,7 +317,7 @@ int attach_sources_v2(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row) {
         }
         for (int b = 0; b < a.n_tiles; ++b) begin[b + 1] += begin[b];
         std::unique_ptr<cev_fdtd::SrcTiling> t(new cev_fdtd::SrcTiling());
-        t->x0 = a.x0; t->x1 = a.x1; t->xchunk = a.xchunk; t->lz = p->lz; t->vec = V;
+        t->x0 = a.x0; t->x1 = a.x1; t->xchunk = a.xchunk; t->lz = p->lz; t->vec = V; t->part = part;
         const size_t mm = (size_t)(m > 0 ? m : 1);
         if (t->begin.alloc(begin.size() * 4) || t->comp.alloc(mm * 4) || t->id.alloc(mm * 4) || t->cell.alloc(mm * 4) ||
             t->w.alloc(mm * 8))
@@ -281,7 +329,7 @@ int attach_sources_v2(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row) {
             CUDA_TRY(cudaMemcpy(t->cell.p, cell.data(), m * 4, cudaMemcpyHostToDevice));
             CUDA_TRY(cudaMemcpy(t->w.p, w.data(), m * 8, cudaMemcpyHostToDevice));
         }
-        if (p->src_tilings.size() >= 8) p->src_tilings.erase(p->src_tilings.begin());
+        if (p->src_tilings.size() >= 16) p->src_tilings.erase(p->src_tilings.begin());
         p->src_tilings.push_back(std::move(t));
         hit = p->src_tilings.back().get();
     }
@@ -315,19 +363,39 @@ int launch_H(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, void* con
             if (!a.Hout[A]) return fail("H_out entries must be non-NULL");
         }
     const bool march = can_march(p, a, true);
-    if (march) set_tiles_v2(p, a, x0, x1);
-    else set_tiles_v1(a, x0, x1);
-    const int aux = attach_probes(p, a, 0, probe_t, partials);
-    if (a.n_tiles + aux == 0) return 0;
-    if (march) {
-        constexpr int V = vec_width<T>();
-        const dim3 blk(32, V2_BY);
-        const int g = a.n_tiles + aux;
-        if (p->lz == 8) k_step_H_v2<T, AT, V, 8><<<g, blk, 0, s>>>(a);
-        else if (p->lz == 16) k_step_H_v2<T, AT, V, 16><<<g, blk, 0, s>>>(a);
-        else k_step_H_v2<T, AT, V, 32><<<g, blk, 0, s>>>(a);
+    if (!march) {
+        set_tiles_v1(a, x0, x1);
+        const int aux = attach_probes(p, a, 0, probe_t, partials);
+        if (a.n_tiles + aux == 0) return 0;
+        k_step_H_v1<T, AT><<<a.n_tiles + aux, dim3(V1_TZ, V1_TY), 0, s>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
     }
-    else k_step_H_v1<T, AT><<<a.n_tiles + aux, dim3(V1_TZ, V1_TY), 0, s>>>(a);
+    constexpr int V = vec_width<T>();
+    const dim3 blk(32, V2_BY);
+    const bool split = want_split<T>(p, x0, x1);
+    bool probes_done = false;
+    for (int part = split ? 1 : 0; part <= (split ? 2 : 0); ++part) {
+        set_tiles_v2(p, a, x0, x1, part);
+        int aux = 0;
+        if (!probes_done) {
+            aux = attach_probes(p, a, 0, probe_t, partials);
+            probes_done = true;
+        } else {
+            a.t_probe = -1;
+        }
+        const int g = a.n_tiles + aux;
+        if (g == 0) continue;
+        if (part == 1) {
+            if (p->lz == 8) k_step_H_v2<T, AT, V, 8, true><<<g, blk, 0, s>>>(a);
+            else if (p->lz == 16) k_step_H_v2<T, AT, V, 16, true><<<g, blk, 0, s>>>(a);
+            else k_step_H_v2<T, AT, V, 32, true><<<g, blk, 0, s>>>(a);
+        } else {
+            if (p->lz == 8) k_step_H_v2<T, AT, V, 8, false><<<g, blk, 0, s>>>(a);
+            else if (p->lz == 16) k_step_H_v2<T, AT, V, 16, false><<<g, blk, 0, s>>>(a);
+            else k_step_H_v2<T, AT, V, 32, false><<<g, blk, 0, s>>>(a);
+        }
+    }
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -356,30 +424,48 @@ int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const
         if (J_wave) a.Jwave[A] = J_wave[L];
     }
     const bool march = can_march(p, a, false);
-    if (march) set_tiles_v2(p, a, x0, x1);
-    else set_tiles_v1(a, x0, x1);
     const bool inject = wave_row && p->n_src_pts > 0 && x1 > x0;
-    if (inject && march && attach_sources_v2(p, a, wave_row)) return -1;
-    const int aux = attach_probes(p, a, 1, probe_t, partials);
-    if (a.n_tiles + aux == 0) return 0;
+    if (!march) {
+        set_tiles_v1(a, x0, x1);
+        const int aux = attach_probes(p, a, 1, probe_t, partials);
+        if (a.n_tiles + aux == 0) return 0;
+        k_step_D_v1<T, AT><<<a.n_tiles + aux, dim3(V1_TZ, V1_TY), 0, s>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        if (inject) return launch_inject<T, AT>(p, st, D_out, wave_row, x0, x1, s);
+        return 0;
+    }
+    constexpr int V = vec_width<T>();
+    const dim3 blk(32, V2_BY);
     const bool extras = a.J[0] || a.J[1] || a.J[2] || a.Eout[0] || a.Eout[1] || a.Eout[2];
-    if (march) {
-        constexpr int V = vec_width<T>();
-        const dim3 blk(32, V2_BY);
-        const int g = a.n_tiles + aux;
-        if (extras) {   // per-step forward() API: one shape is enough
-            p->lz == 8 ? k_step_D_v2<T, AT, V, 8, true><<<g, blk, 0, s>>>(a)
-                       : (p->lz == 16 ? k_step_D_v2<T, AT, V, 16, true><<<g, blk, 0, s>>>(a)
-                                      : k_step_D_v2<T, AT, V, 32, true><<<g, blk, 0, s>>>(a));
+    const bool split = !extras && want_split<T>(p, x0, x1);   // the per-step forward() API keeps one launch
+    bool probes_done = false;
+    for (int part = split ? 1 : 0; part <= (split ? 2 : 0); ++part) {
+        set_tiles_v2(p, a, x0, x1, part);
+        if (inject && attach_sources_v2(p, a, wave_row, part)) return -1;
+        int aux = 0;
+        if (!probes_done) {
+            aux = attach_probes(p, a, 1, probe_t, partials);
+            probes_done = true;
         } else {
-            p->lz == 8 ? k_step_D_v2<T, AT, V, 8, false><<<g, blk, 0, s>>>(a)
-                       : (p->lz == 16 ? k_step_D_v2<T, AT, V, 16, false><<<g, blk, 0, s>>>(a)
-                                      : k_step_D_v2<T, AT, V, 32, false><<<g, blk, 0, s>>>(a));
+            a.t_probe = -1;
+        }
+        const int g = a.n_tiles + aux;
+        if (g == 0) continue;
+        if (extras) {
+            p->lz == 8 ? k_step_D_v2<T, AT, V, 8, true, false><<<g, blk, 0, s>>>(a)
+                       : (p->lz == 16 ? k_step_D_v2<T, AT, V, 16, true, false><<<g, blk, 0, s>>>(a)
+                                      : k_step_D_v2<T, AT, V, 32, true, false><<<g, blk, 0, s>>>(a));
+        } else if (part == 1) {
+            p->lz == 8 ? k_step_D_v2<T, AT, V, 8, false, true><<<g, blk, 0, s>>>(a)
+                       : (p->lz == 16 ? k_step_D_v2<T, AT, V, 16, false, true><<<g, blk, 0, s>>>(a)
+                                      : k_step_D_v2<T, AT, V, 32, false, true><<<g, blk, 0, s>>>(a));
+        } else {
+            p->lz == 8 ? k_step_D_v2<T, AT, V, 8, false, false><<<g, blk, 0, s>>>(a)
+                       : (p->lz == 16 ? k_step_D_v2<T, AT, V, 16, false, false><<<g, blk, 0, s>>>(a)
+                                      : k_step_D_v2<T, AT, V, 32, false, false><<<g, blk, 0, s>>>(a));
         }
     }
-    else k_step_D_v1<T, AT><<<a.n_tiles + aux, dim3(V1_TZ, V1_TY), 0, s>>>(a);
     CUDA_TRY(cudaGetLastError());
-    if (inject && !march) return launch_inject<T, AT>(p, st, D_out, wave_row, x0, x1, s);
     return 0;
 }
 
@@ -658,6 +744,19 @@ int cev_fdtd_create(cev_fdtd** out, int device, int dtype, int arith_f64, int64_
             }
         }
     }
+    for (int A = 0; A < 3; ++A) {   // longest run of indices where neither the H nor the D profile is in the PML
+        const int L = p->to_logical(A);
+        int best_lo = 0, best_hi = 0, run_lo = 0;
+        for (int q = 0; q <= p->N[A]; ++q) {
+            const bool zero = q < p->N[A] && sH[L][q] == 0.0 && sD[L][q] == 0.0;
+            if (!zero) {
+                if (q - run_lo > best_hi - best_lo) { best_lo = run_lo; best_hi = q; }
+                run_lo = q + 1;
+            }
+        }
+        p->in_lo[A] = best_lo;
+        p->in_hi[A] = best_hi;
+    }
     if (off > total) {
         delete p;
         return fail("internal: table overflow");
@@ -694,6 +793,9 @@ int cev_fdtd_set_option(cev_fdtd* p, const char* name, int64_t value) {
     } else if (!strcmp(name, "prefetch_planes")) {
         if (value < 0 || value > 64) return fail("prefetch_planes must be in [0, 64]");
         p->pf_dist = (int)value;
+    } else if (!strcmp(name, "split_launch")) {
+        if (value != 0 && value != 1) return fail("split_launch must be 0 or 1");
+        p->split = (int)value;
     } else if (!strcmp(name, "lanes_z")) {
         if (value != 8 && value != 16 && value != 32) return fail("lanes_z must be 8, 16 or 32");
         p->lz = (int)value;

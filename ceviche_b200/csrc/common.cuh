@@ -26,6 +26,14 @@ struct ProbeTable {
     const double*  weight;
 };
 
+// A launch of the marching kernels covers up to 6 boxes of cells (the whole grid; or the PML-free
+// interior; or the six slabs of the PML shell), each tiled from its own origin.
+struct Box {
+    int x0, x1, y0, y1, z0, z1;   // cell ranges (z0 a multiple of the vector width)
+    int cta0, ntz, nty;           // first CTA of the box, tiles along z and y
+};
+constexpr int MAX_BOXES = 6;
+
 // Everything a half-step kernel needs.  Axes/components are in the plan's INTERNAL order
 // (a cyclic relabelling of x,y,z chosen so that the last internal axis is the contiguous
 // one with extent > 1; see cev_fdtd.cu).  T = storage type, AT = arithmetic type.
@@ -75,6 +83,8 @@ struct StepArgs {
     const double*  src_wave;
     // tiling + auxiliary probe CTAs appended to the grid
     int n_tiles, ntz, nty, xchunk;
+    int n_boxes;
+    Box box[MAX_BOXES];
     int pf_dist;              // L2 prefetch distance in x-planes (0 = off)
     ProbeTable pr;
     int        aux_slot0;     // first slot handled by the aux CTAs of this launch
@@ -131,13 +141,17 @@ __device__ __forceinline__ AT curl2(AT a1, AT a0, AT b1, AT b0, AT inv) {
 
 // Coefficients of fdtd.py:272-311 rewritten division-free from the per-axis tables
 //   u = sigma*dt/(2 eps0), r = 1/(1+u):   m0*dt = (1+ua)(1+ub),  1/m0 = dt*ra*rb
-//   m1 = (1-ua-ub-ua*ub) ra rb,  m2 = s*C0*dt ra rb,  m3 = s*C0*dt*2uc ra rb,  m4 = -4 ua ub ra rb
+//   m1 = (1-ua-ub-ua*ub) ra rb = (2 - (1+ua)(1+ub)) ra rb = 2 ra rb - 1
+//   m2 = s*C0*dt ra rb,  m3 = s*C0*dt*2uc ra rb,  m4 = -4 ua ub ra rb
 // (s = -1 for H, +1 for D; (ua,ub) = the two other axes, uc = the component's own axis).
+// Off the PML (u = 0, r = 1) this gives m1 = 1 and m2 = s*C0*dt exactly.
 template <typename AT>
 __device__ __forceinline__ void coef12(AT ua, AT ra, AT ub, AT rb, AT scdt, AT& m1, AT& m2) {
     const AT rr = mul_rn(ra, rb);
-    m1 = mul_rn(AT(1) - ua - ub - mul_rn(ua, ub), rr);
+    m1 = add_rn(rr + rr, AT(-1));
     m2 = mul_rn(scdt, rr);
+    (void)ua;
+    (void)ub;
 }
 
 // One field component of one half-step (fdtd.py:85-97 for H, :110-122 for D):

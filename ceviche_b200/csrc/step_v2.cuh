@@ -48,6 +48,9 @@ constexpr int V2_BY = 4;        // warps per CTA; a warp covers LZ lanes along z
 #ifndef V2_D_MIN_CTAS
 #define V2_D_MIN_CTAS 5
 #endif
+#ifndef V2_INTERIOR_MIN_CTAS
+#define V2_INTERIOR_MIN_CTAS 6
+#endif
 
 // PML work of one thread for one x-plane.  load() is called right after the main loads of the
 // iteration are issued: it fetches the old values of the curl integrals (vector loads for the x- and
@@ -72,6 +75,9 @@ struct PmlCtx {
         ry = CEV_TAB(a, r, 1)[j];
         ic0 = mx >= 0 ? (mx * a.Ny + j) * a.Nz + k0 : -1;      // Icurl_x (nCx,Ny,Nz)
         ic1 = my >= 0 ? (i * n1 + my) * a.Nz + k0 : -1;        // Icurl_y (Nx,nCy,Nz)
+#ifdef CEV_EXP_NO_RMW
+        ic0 = ic1 = -1;
+#endif
         if (ic0 >= 0) I0 = ldv<T, V>(Ic[0] + ic0);
         if (ic1 >= 0) I1 = ldv<T, V>(Ic[1] + ic1);
 #pragma unroll
@@ -80,6 +86,21 @@ struct PmlCtx {
             rz[e] = CEV_TAB(a, r, 2)[k0 + e];
             if (mz[e] >= 0) I2[e] = Ic[2][(i * a.Ny + j) * n2 + mz[e]];   // Icurl_z (Nx,Ny,nCz)
         }
+    }
+
+    // pull the curl integrals of plane ip (a later iteration of this thread) into L2: without it they
+    // are the only loads of a PML iteration that still pay the full DRAM latency
+    static __device__ __forceinline__ void prefetch(const StepArgs<T, AT>& a, int ip, int j, int k0, int my, const int* mz,
+                                                    bool line_lane) {
+        const int n1 = IS_H ? a.nH[1] : a.nD[1], n2 = IS_H ? a.nH[2] : a.nD[2];
+        T* const* Ic = IS_H ? a.ICE : a.ICH;
+        const int mxp = CEV_TAB(a, map, 0)[ip];
+        if (line_lane) {
+            if (mxp >= 0) prefetch_l2(Ic[0] + (mxp * a.Ny + j) * a.Nz + k0);
+            if (my >= 0) prefetch_l2(Ic[1] + (ip * n1 + my) * a.Nz + k0);
+        }
+        if (mz[0] >= 0) prefetch_l2(Ic[2] + (ip * a.Ny + j) * n2 + mz[0]);
+        else if (mz[V - 1] >= 0) prefetch_l2(Ic[2] + (ip * a.Ny + j) * n2 + mz[V - 1]);
     }
 
     // old[c][e], curl[c][e] -> out[c].v[e]
@@ -153,8 +174,11 @@ struct PmlCtx {
 #undef CEV_TAB
 };
 
-template <typename T, typename AT, int V, int LZ>
-__global__ void __launch_bounds__(32 * V2_BY, (sizeof(T) == 8 ? V2_H_MIN_CTAS : V2_H_MIN_CTAS + 1)) k_step_H_v2(const StepArgs<T, AT> a) {
+// INTERIOR = the launch covers only cells off every PML: all PML code is compiled out (few registers,
+// high occupancy); otherwise the general kernel.
+template <typename T, typename AT, int V, int LZ, bool INTERIOR>
+__global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS : (sizeof(T) == 8 ? V2_H_MIN_CTAS : V2_H_MIN_CTAS + 1)))
+k_step_H_v2(const StepArgs<T, AT> a) {
     const int bid = blockIdx.x;
     if (bid >= a.n_tiles) {
         probe_block<T, AT>(a, a.aux_slot0 + (bid - a.n_tiles));
@@ -163,33 +187,39 @@ __global__ void __launch_bounds__(32 * V2_BY, (sizeof(T) == 8 ? V2_H_MIN_CTAS : 
     constexpr int RW = 32 / LZ;                  // rows per warp
     const int lane = threadIdx.x;
     const int lz = lane % LZ, ly = lane / LZ;
-    const int tz = bid % a.ntz;
-    const int rest = bid / a.ntz;
-    const int ty = rest % a.nty;
-    const int xc = rest / a.nty;
-    const int jraw = (ty * V2_BY + threadIdx.y) * RW + ly;
-    if (jraw - ly >= a.Ny) return;               // warp-uniform: the whole warp is below the grid
-    const int k0raw = (tz * LZ + lz) * V;
-    const bool active = k0raw < a.Nz && jraw < a.Ny;
-    const int j = jraw < a.Ny ? jraw : a.Ny - 1; // inactive lanes shadow a valid cell (loads only)
-    const int k0 = k0raw < a.Nz ? k0raw : 0;
-    const int xs = a.x0 + xc * a.xchunk;
-    const int xe = min(xs + a.xchunk, a.x1);
+    int bx = 0;                                  // which box of this launch (CTA-uniform)
+#pragma unroll
+    for (int q = 1; q < MAX_BOXES; ++q)
+        if (q < a.n_boxes && bid >= a.box[q].cta0) bx = q;
+    const Box& B = a.box[bx];
+    const int lid = bid - B.cta0;
+    const int tz = lid % B.ntz;
+    const int rest = lid / B.ntz;
+    const int ty = rest % B.nty;
+    const int xc = rest / B.nty;
+    const int jraw = B.y0 + (ty * V2_BY + threadIdx.y) * RW + ly;
+    if (jraw - ly >= B.y1) return;               // warp-uniform: the whole warp is outside the box
+    const int k0raw = B.z0 + (tz * LZ + lz) * V;
+    const bool active = k0raw < B.z1 && jraw < B.y1;
+    const int j = jraw < B.y1 ? jraw : B.y1 - 1; // inactive lanes shadow a valid cell (loads only)
+    const int k0 = k0raw < B.z1 ? k0raw : B.z0;
+    const int xs = B.x0 + xc * a.xchunk;
+    const int xe = min(xs + a.xchunk, B.x1);
 
     const int plane = a.Ny * a.Nz;
     const int jp = (j + 1 == a.Ny) ? 0 : j + 1;
-    const bool z_edge = (lz == LZ - 1) || (k0 + V >= a.Nz);   // +1 neighbour not in lane+1
+    const bool z_edge = (lz == LZ - 1) || (k0 + V >= B.z1);   // +1 neighbour not in lane+1 (tile / box edge)
     const int kp = (k0 + V >= a.Nz) ? 0 : k0 + V;
     const int orow = j * a.Nz + k0;
     const int orow_jp = jp * a.Nz + k0;
     const int okp = j * a.Nz + kp;
 
-    const int my = a.mapH[1][j];
+    const int my = INTERIOR ? -1 : a.mapH[1][j];
     int mz[V];
     bool yz_pml = my >= 0;
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-        mz[e] = a.mapH[2][k0 + e];
+        mz[e] = INTERIOR ? -1 : a.mapH[2][k0 + e];
         yz_pml |= mz[e] >= 0;
     }
     const AT s = -a.cdt;
@@ -228,19 +258,27 @@ __global__ void __launch_bounds__(32 * V2_BY, (sizeof(T) == 8 ? V2_H_MIN_CTAS : 
             ex_kp = mul_rn((AT)a.mE[0][pbase + okp], (AT)a.Din[0][pbase + okp]);
             ey_kp = mul_rn((AT)a.mE[1][pbase + okp], (AT)a.Din[1][pbase + okp]);
         }
-        if (a.pf_dist > 0 && (lz & 7) == 0 && i + a.pf_dist < xe) {   // one lane per 128-byte line
-            const int po = (i + a.pf_dist) * plane + orow;
+        if (a.pf_dist > 0 && i + a.pf_dist < a.x1) {   // next plane(s) of every stream into L2, also across the chunk end
+            const int ip = i + a.pf_dist;
+            if ((lz & 7) == 0) {                       // one lane per 128-byte line
+                const int po = ip * plane + orow;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                prefetch_l2(a.Hin[c] + po);
-                if (i + a.pf_dist + 1 < a.Nx) {
-                    prefetch_l2(a.Din[c] + po + plane);
-                    prefetch_l2(a.mE[c] + po + plane);
+                for (int c = 0; c < 3; ++c) {
+                    prefetch_l2(a.Hin[c] + po);
+                    if (ip + 1 < a.Nx) {
+                        prefetch_l2(a.Din[c] + po + plane);
+                        prefetch_l2(a.mE[c] + po + plane);
+                    }
                 }
             }
+            if (!INTERIOR) PmlCtx<T, AT, V, true>::prefetch(a, ip, j, k0, my, mz, (lz & 7) == 0);
         }
-        const int mx = a.mapH[0][i];
-        const bool pml = yz_pml || mx >= 0;
+        const int mx = INTERIOR ? -1 : a.mapH[0][i];
+#ifdef CEV_EXP_NO_PML
+        const bool pml = false;
+#else
+        const bool pml = !INTERIOR && (yz_pml || mx >= 0);
+#endif
         PmlCtx<T, AT, V, true> ctx;
         if (pml) ctx.load(a, i, j, k0, mx, my, mz);
 
@@ -286,8 +324,8 @@ __global__ void __launch_bounds__(32 * V2_BY, (sizeof(T) == 8 ? V2_H_MIN_CTAS : 
 
 // EXTRAS = dense J input and/or E output (the per-step forward() API); the fused run() path
 // instantiates EXTRAS = false and carries neither.
-template <typename T, typename AT, int V, int LZ, bool EXTRAS>
-__global__ void __launch_bounds__(32 * V2_BY, V2_D_MIN_CTAS) k_step_D_v2(const StepArgs<T, AT> a) {
+template <typename T, typename AT, int V, int LZ, bool EXTRAS, bool INTERIOR>
+__global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS : V2_D_MIN_CTAS)) k_step_D_v2(const StepArgs<T, AT> a) {
     const int bid = blockIdx.x;
     if (bid >= a.n_tiles) {
         probe_block<T, AT>(a, a.aux_slot0 + (bid - a.n_tiles));
@@ -296,33 +334,39 @@ __global__ void __launch_bounds__(32 * V2_BY, V2_D_MIN_CTAS) k_step_D_v2(const S
     constexpr int RW = 32 / LZ;                  // rows per warp
     const int lane = threadIdx.x;
     const int lz = lane % LZ, ly = lane / LZ;
-    const int tz = bid % a.ntz;
-    const int rest = bid / a.ntz;
-    const int ty = rest % a.nty;
-    const int xc = rest / a.nty;
-    const int jraw = (ty * V2_BY + threadIdx.y) * RW + ly;
-    const bool warp_on = jraw - ly < a.Ny;       // warp-uniform; no early return: the CTA meets at a barrier below
-    const int k0raw = (tz * LZ + lz) * V;
-    const bool active = k0raw < a.Nz && jraw < a.Ny;
-    const int j = jraw < a.Ny ? jraw : a.Ny - 1; // inactive lanes shadow a valid cell (loads only)
-    const int k0 = k0raw < a.Nz ? k0raw : 0;
-    const int xs = a.x0 + xc * a.xchunk;
-    const int xe = min(xs + a.xchunk, a.x1);
+    int bx = 0;                                  // which box of this launch (CTA-uniform)
+#pragma unroll
+    for (int q = 1; q < MAX_BOXES; ++q)
+        if (q < a.n_boxes && bid >= a.box[q].cta0) bx = q;
+    const Box& B = a.box[bx];
+    const int lid = bid - B.cta0;
+    const int tz = lid % B.ntz;
+    const int rest = lid / B.ntz;
+    const int ty = rest % B.nty;
+    const int xc = rest / B.nty;
+    const int jraw = B.y0 + (ty * V2_BY + threadIdx.y) * RW + ly;
+    const bool warp_on = jraw - ly < B.y1;       // warp-uniform; no early return: the CTA meets at a barrier below
+    const int k0raw = B.z0 + (tz * LZ + lz) * V;
+    const bool active = k0raw < B.z1 && jraw < B.y1;
+    const int j = jraw < B.y1 ? jraw : B.y1 - 1; // inactive lanes shadow a valid cell (loads only)
+    const int k0 = k0raw < B.z1 ? k0raw : B.z0;
+    const int xs = B.x0 + xc * a.xchunk;
+    const int xe = min(xs + a.xchunk, B.x1);
 
     const int plane = a.Ny * a.Nz;
     const int jm = (j == 0) ? a.Ny - 1 : j - 1;
-    const bool z_edge = (lz == 0) || (k0 == 0);
+    const bool z_edge = (lz == 0) || (k0 == B.z0);            // -1 neighbour not in lane-1 (tile / box edge)
     const int km = (k0 == 0) ? a.Nz - 1 : k0 - 1;
     const int orow = j * a.Nz + k0;
     const int orow_jm = jm * a.Nz + k0;
     const int okm = j * a.Nz + km;
 
-    const int my = a.mapD[1][j];
+    const int my = INTERIOR ? -1 : a.mapD[1][j];
     int mz[V];
     bool yz_pml = my >= 0;
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-        mz[e] = a.mapD[2][k0 + e];
+        mz[e] = INTERIOR ? -1 : a.mapD[2][k0 + e];
         yz_pml |= mz[e] >= 0;
     }
     const AT s = a.cdt;
@@ -358,16 +402,24 @@ __global__ void __launch_bounds__(32 * V2_BY, V2_D_MIN_CTAS) k_step_D_v2(const S
             hx_km = (AT)a.Hin[0][pbase + okm];
             hy_km = (AT)a.Hin[1][pbase + okm];
         }
-        if (a.pf_dist > 0 && (lz & 7) == 0 && i + a.pf_dist < xe) {
-            const int po = (i + a.pf_dist) * plane + orow;
+        if (a.pf_dist > 0 && i + a.pf_dist < a.x1) {
+            const int ip = i + a.pf_dist;
+            if ((lz & 7) == 0) {
+                const int po = ip * plane + orow;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                prefetch_l2(a.Hin[c] + po);
-                prefetch_l2(a.Din[c] + po);
+                for (int c = 0; c < 3; ++c) {
+                    prefetch_l2(a.Hin[c] + po);
+                    prefetch_l2(a.Din[c] + po);
+                }
             }
+            if (!INTERIOR) PmlCtx<T, AT, V, false>::prefetch(a, ip, j, k0, my, mz, (lz & 7) == 0);
         }
-        const int mx = a.mapD[0][i];
-        const bool pml = yz_pml || mx >= 0;
+        const int mx = INTERIOR ? -1 : a.mapD[0][i];
+#ifdef CEV_EXP_NO_PML
+        const bool pml = false;
+#else
+        const bool pml = !INTERIOR && (yz_pml || mx >= 0);
+#endif
         PmlCtx<T, AT, V, false> ctx;
         if (pml) ctx.load(a, i, j, k0, mx, my, mz);
 

@@ -108,7 +108,9 @@ int cev_fdtd_create(cev_fdtd** plan, int device, int dtype, int arith_f64,
 int cev_fdtd_destroy(cev_fdtd* plan);
 
 /* Tuning / test knobs: "kernel_variant" 0 auto | 1 baseline (one thread per cell) | 2 marching;
- * "xchunk" x-planes per CTA of the marching kernels (0 = auto).  Results do not depend on them. */
+ * "xchunk" x-planes per CTA of the marching kernels (0 = auto); "lanes_z" 8|16|32 lanes of a warp along z;
+ * "prefetch_planes" L2 prefetch distance; "split_launch" 0|1 separate launches for the PML-free interior and
+ * the PML shell.  Results do not depend on them (bit-identical). */
 int cev_fdtd_set_option(cev_fdtd* plan, const char* name, int64_t value);
 
 /* Logical shapes of the 12 compact PML integral arrays, order ICE[3], IH[3], ICH[3], ID[3]. */

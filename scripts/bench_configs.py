@@ -1,0 +1,114 @@
+"""Timings of the other BASELINE configs (1, 4, 5) on one B200: python scripts/bench_configs.py [c1] [c4] [c5]
+Prints one JSON line per measurement (recorded in profiles/)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ceviche_b200
+from oracle import cases
+
+DL = 5e-8
+which = sys.argv[1:] or ["c1", "c4", "c5"]
+
+
+def timed(fn, reps=1):
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        out = fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps * 1e-3, out
+
+
+if "c1" in which:
+    # config 1: 2-D 200x200, npml 20, point dipole Jz, 1000 steps, fp64 (tests/test_fields_fdtd.py path)
+    case = cases.field_case("c1_tm")
+    for dtype, name in ((torch.float64, "f64"), (torch.float32, "f32")):
+        F = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"], dtype=dtype)
+        F.prepare(case["sources"], case["probes"])
+        wf = torch.as_tensor(np.stack([w for _, _, w in case["sources"]], 1)).cuda()
+        F.run(1000, waveforms=wf)
+        F.initialize_fields()
+        s, _ = timed(lambda: F.run(1000, waveforms=wf), reps=5)
+        print(json.dumps({"config": "c1 2-D 200x200x1 npml [20,20,0] 1000 steps fused run()", "dtype": name, "seconds": s,
+                          "us_per_step": s / 1000 * 1e6, "gcell_per_s": 200 * 200 * 1000 / s / 1e9}), flush=True)
+    F = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"])
+    prof = torch.as_tensor(case["sources"][0][1]).cuda()
+    wave = case["sources"][0][2]
+    def loop():
+        for t in range(1000):
+            F.forward(Jz=prof * float(wave[t]))
+    loop()
+    s, _ = timed(loop)
+    print(json.dumps({"config": "c1 per-step forward() API (reference caller loop), 1000 steps", "dtype": "f64", "seconds": s,
+                      "us_per_step": s / 1000 * 1e6, "gcell_per_s": 200 * 200 * 1000 / s / 1e9}), flush=True)
+
+if "c4" in which:
+    # config 4: reverse-mode gradient of a probe objective w.r.t. eps_r on 256x256x128, checkpointed adjoint
+    shape = (256, 256, 128)
+    steps = int(os.environ.get("C4_STEPS", "200"))
+    rng = np.random.default_rng(1)
+    eps_np = np.ones(shape)
+    eps_np[96:160, 96:160, 48:80] = 1 + 4.95 * rng.random((64, 64, 32))
+    prof = np.zeros(shape); prof[30, 123:133, 61:67] = 1.0
+    mask = np.zeros(shape); mask[226, 123:133, 61:67] = 1.0
+    t = np.arange(steps)
+    wave = 5 * np.exp(-(t - 60) ** 2 / (2 * 20 ** 2)) * np.cos(0.2 * t)
+    for dtype, name in ((torch.float64, "f64"), (torch.float32, "f32")):
+        eps = torch.as_tensor(eps_np).cuda().requires_grad_(True)
+        F = ceviche_b200.fdtd(eps, DL, [20, 20, 20], dtype=dtype)
+        def fwd():
+            F.initialize_fields()
+            return F.run(steps, [("z", prof, wave)], [("Ez", mask)])
+        s_f, series = timed(fwd)
+        L = (series ** 2).sum()
+        s_b, _ = timed(lambda: torch.autograd.grad(L, eps))
+        cells = shape[0] * shape[1] * shape[2]
+        print(json.dumps({"config": "c4 reverse-mode gradient 256x256x128 npml 20, %d steps, checkpoint every sqrt(steps)" % steps,
+                          "dtype": name, "forward_s": s_f, "backward_s": s_b,
+                          "forward_gcell_per_s": cells * steps / s_f / 1e9,
+                          "backward_gcell_per_s_incl_recompute": cells * steps / s_b / 1e9,
+                          "total_3sweeps_gcell_per_s": 3 * cells * steps / (s_f + s_b) / 1e9,
+                          "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}), flush=True)
+        del F, eps, series, L
+        torch.cuda.empty_cache()
+
+if "c5" in which:
+    # config 5: forward-mode JVP over 16 eps_r perturbations on a 2-D 2048x2048 grating-like grid
+    shape = (2048, 2048, 1)
+    steps = int(os.environ.get("C5_STEPS", "300"))
+    B = 16
+    eps_np = np.full(shape, 1.44 ** 2)
+    eps_np[:, 1000:1048, 0] = 3.48 ** 2
+    V = np.zeros((B,) + shape)
+    for b in range(B):
+        x0 = 200 + b * 100
+        eps_np[x0:x0 + 50, 1048:1070, 0] = 3.48 ** 2
+        V[b, x0:x0 + 50, 1048:1070, 0] = 1.0
+    prof = np.zeros(shape); prof[100, 1000:1048, 0] = 1.0
+    mask = np.zeros(shape); mask[200:1800, 1300, 0] = 1.0
+    t = np.arange(steps)
+    wave = np.exp(-(t - 100) ** 2 / (2 * 30 ** 2)) * np.cos(0.15 * t)
+    for dtype, name in ((torch.float64, "f64"), (torch.float32, "f32")):
+        F = ceviche_b200.fdtd(eps_np, DL, [20, 20, 0], dtype=dtype)
+        Vt = torch.as_tensor(V)
+        F.jvp_run(10, Vt, [("z", prof, wave[:10])], [("Ez", mask)])
+        F.initialize_fields()
+        s, _ = timed(lambda: F.jvp_run(steps, Vt, [("z", prof, wave)], [("Ez", mask)]))
+        cells = shape[0] * shape[1]
+        F2 = ceviche_b200.fdtd(eps_np, DL, [20, 20, 0], dtype=dtype)
+        F2.run(10, [("z", prof, wave[:10])], [("Ez", mask)])
+        F2.initialize_fields()
+        s1, _ = timed(lambda: F2.run(steps, [("z", prof, wave)], [("Ez", mask)]))
+        print(json.dumps({"config": "c5 batched JVP, 16 tangents + primal, 2-D 2048x2048 npml [20,20,0], %d steps" % steps,
+                          "dtype": name, "seconds": s, "gcell_per_s_incl_tangents": cells * steps * (1 + B) / s / 1e9,
+                          "primal_only_seconds": s1, "primal_only_gcell_per_s": cells * steps / s1 / 1e9}), flush=True)
+        del F, F2
+        torch.cuda.empty_cache()

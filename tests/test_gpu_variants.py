@@ -21,13 +21,14 @@ def _case(shape, npml, steps, seed):
     return dict(eps=eps, dL=cases.DL, npml=list(npml), steps=steps, sources=src, probes=probes)
 
 
-def _run(case, dtype, variant, xchunk=0, per_step=False, lanes_z=8, prefetch=1):
+def _run(case, dtype, variant, xchunk=0, per_step=False, lanes_z=8, prefetch=1, split=0):
     import ceviche_b200
     F = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"], dtype=dtype)
     F.set_option("kernel_variant", variant)
     F.set_option("xchunk", xchunk)
     F.set_option("lanes_z", lanes_z)
     F.set_option("prefetch_planes", prefetch)
+    F.set_option("split_launch", split)
     if per_step:
         profs = [(c, torch.as_tensor(p).cuda()) for c, p, _ in case["sources"]]
         for t in range(case["steps"]):
@@ -42,7 +43,7 @@ def _run(case, dtype, variant, xchunk=0, per_step=False, lanes_z=8, prefetch=1):
 
 
 SHAPES = [((20, 18, 136), (4, 3, 6)), ((9, 7, 64), (2, 0, 5)), ((3, 5, 24), (0, 2, 2)), ((33, 40, 1), (5, 6, 0)),
-          ((6, 10, 260), (2, 3, 20))]
+          ((6, 10, 260), (2, 3, 20)), ((44, 38, 136), (6, 5, 8)), ((40, 48, 100), (5, 0, 7))]   # the last two split interior / shell
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
@@ -50,8 +51,8 @@ SHAPES = [((20, 18, 136), (4, 3, 6)), ((9, 7, 64), (2, 0, 5)), ((3, 5, 24), (0, 
 def test_marching_equals_baseline_bitwise(shape, npml, dtype):
     case = _case(shape, npml, 40, 7)
     s1, f1, p1 = _run(case, dtype, 1)
-    for xchunk, lanes_z, pf in ((0, 8, 1), (1, 16, 0), (3, 32, 2), (1000, 8, 5), (5, 32, 1)):
-        s2, f2, p2 = _run(case, dtype, 2, xchunk, lanes_z=lanes_z, prefetch=pf)
+    for xchunk, lanes_z, pf, split in ((0, 8, 1, 1), (1, 16, 0, 1), (3, 32, 2, 0), (1000, 8, 5, 1), (5, 32, 1, 1), (0, 8, 1, 0)):
+        s2, f2, p2 = _run(case, dtype, 2, xchunk, lanes_z=lanes_z, prefetch=pf, split=split)
         for k in FIELD_KEYS:
             assert np.array_equal(f1[k], f2[k]), (k, xchunk)
         for a, b in zip(p1, p2):
