@@ -240,7 +240,8 @@ def run_ours(args):
     ms = ev0.elapsed_time(ev1)
     ms_per_step = ms / args.steps
     value = cells * chunk * args.steps / (ms * 1e-3) / 1e9
-    launches = args.steps * (chunk * 3 + 2)
+    launches = args.steps * (chunk * 2 + 4)     # per run(): 2 half-step kernels per time step (sources and probes ride
+                                                # inside them) + the trailing probe launch + 3 E-materialisation launches
 
     # ---- per-kernel timing of the two half-step kernels (events on the launch stream) ----
     import ctypes as C
@@ -442,7 +443,7 @@ def run_slabs(args, dist, dev, local, rank, world, dtype, w, hbm_peak, peak_src)
                 "e2e": {"value": cells * chunk / e2e_s / 1e9, "unit": "Gcell/s",
                         "h2d_bytes_per_step": int(eps_host.numel() * 8 * world + wave.size * 8 * world),
                         "d2h_bytes_per_step": int(chunk * len(probes) * 8 * world), "ms_per_step": e2e_s * 1e3},
-                "gpu_launches": int(args.steps * chunk * 5 + args.steps), "clocks": clk.summary()}
+                "gpu_launches": int(args.steps * (chunk * 4 + 1)), "clocks": clk.summary()}
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()

@@ -25,3 +25,42 @@ def measure_fields(F, source, steps, probes, component='Ez'):
         for probe_index, mask in enumerate(masks):
             measured[t_index, probe_index] = float(torch.sum(fields[component].double() * mask))
     return measured
+
+
+# ---- spectra of probe series (ceviche/utils.py:350-403).  torch.fft is differentiable in both modes,
+# so the reference's hand-registered `my_fft` primitive (utils.py:350-370) needs no counterpart.
+def my_fft(x):
+    """FFT along axis 0... of a 1-D series, like np.fft.fft (utils.py:350-356)."""
+    return torch.fft.fft(x)
+
+
+def get_spectrum(series, dt):
+    """ Get FFT of series: Hamming-windowed, along time (utils.py:373-388).  Returns (freqs, signal_f)
+    with signal_f of shape (steps, n).  Accepts numpy or torch; stays on the input's device.
+    Deviation, on purpose: the reference reshapes to (steps, -1) and then calls np.fft.fft, which
+    transforms the LAST axis (length 1 for a single series, i.e. a no-op); the transform here is along
+    time, which is what the function documents. """
+    if not torch.is_tensor(series):
+        series = torch.as_tensor(np.asarray(series))
+    steps = series.shape[0]
+    series = series.reshape((steps, -1))
+    window = torch.as_tensor(np.hamming(steps).reshape((steps, 1)), dtype=series.real.dtype, device=series.device)
+    signal_f = torch.fft.fft(window * series, dim=0)
+    freqs = torch.as_tensor(np.fft.fftfreq(steps, d=dt), device=series.device)
+    return freqs, signal_f
+
+
+def get_max_power_freq(series, dt):
+    """utils.py:391-394 (argmax over the flattened spectrum's real part ordering, as numpy does for complex)."""
+    freqs, signal_f = get_spectrum(series, dt)
+    flat = signal_f.reshape(-1)
+    # numpy's argmax on complex arrays orders lexicographically by (real, imag)
+    key = flat.real.double()
+    idx = int(torch.argmax(key))
+    return freqs[idx % freqs.shape[0]] if signal_f.shape[1] == 1 else freqs[idx // signal_f.shape[1]]
+
+
+def get_spectral_power(series, dt):
+    """utils.py:397-400."""
+    freqs, signal_f = get_spectrum(series, dt)
+    return freqs, torch.square(torch.abs(signal_f))
