@@ -60,7 +60,6 @@ constexpr int V2_BY = 4;        // warps per CTA; a warp covers LZ lanes along z
 // time (no address of the parameter struct is taken: it stays in the constant bank).
 template <typename T, typename AT, int V, bool IS_H>
 struct PmlCtx {
-    AT ux, rx, uy, ry, uz[V], rz[V];
     Vec<T, V> I0, I1;     // old Icurl_x / Icurl_y runs
     T I2[V];              // old Icurl_z cells
     int ic0, ic1;         // run offsets (or -1)
@@ -69,10 +68,6 @@ struct PmlCtx {
     __device__ __forceinline__ void load(const StepArgs<T, AT>& a, int i, int j, int k0, int mx, int my, const int* mz) {
         const int n1 = IS_H ? a.nH[1] : a.nD[1], n2 = IS_H ? a.nH[2] : a.nD[2];
         T* const* Ic = IS_H ? a.ICE : a.ICH;
-        ux = CEV_TAB(a, u, 0)[i];
-        rx = CEV_TAB(a, r, 0)[i];
-        uy = CEV_TAB(a, u, 1)[j];
-        ry = CEV_TAB(a, r, 1)[j];
         ic0 = mx >= 0 ? (mx * a.Ny + j) * a.Nz + k0 : -1;      // Icurl_x (nCx,Ny,Nz)
         ic1 = my >= 0 ? (i * n1 + my) * a.Nz + k0 : -1;        // Icurl_y (Nx,nCy,Nz)
 #ifdef CEV_EXP_NO_RMW
@@ -81,11 +76,8 @@ struct PmlCtx {
         if (ic0 >= 0) I0 = ldv<T, V>(Ic[0] + ic0);
         if (ic1 >= 0) I1 = ldv<T, V>(Ic[1] + ic1);
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-            uz[e] = CEV_TAB(a, u, 2)[k0 + e];
-            rz[e] = CEV_TAB(a, r, 2)[k0 + e];
+        for (int e = 0; e < V; ++e)
             if (mz[e] >= 0) I2[e] = Ic[2][(i * a.Ny + j) * n2 + mz[e]];   // Icurl_z (Nx,Ny,nCz)
-        }
     }
 
     // pull the curl integrals of plane ip (a later iteration of this thread) into L2: without it they
@@ -109,6 +101,16 @@ struct PmlCtx {
         const int n1 = IS_H ? a.nH[1] : a.nD[1], n2 = IS_H ? a.nH[2] : a.nD[2];
         T* const* Ic = IS_H ? a.ICE : a.ICH;
         T* const* Is = IS_H ? a.IH : a.ID;
+        // the tiny per-axis tables are L1-resident: fetched here, after the long-latency loads were consumed,
+        // so they do not hold registers while the thread waits for HBM
+        const AT ux = CEV_TAB(a, u, 0)[i], rx = CEV_TAB(a, r, 0)[i];
+        const AT uy = CEV_TAB(a, u, 1)[j], ry = CEV_TAB(a, r, 1)[j];
+        AT uz[V], rz[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            uz[e] = CEV_TAB(a, u, 2)[k0 + e];
+            rz[e] = CEV_TAB(a, r, 2)[k0 + e];
+        }
         Vec<T, V> n0, n1v;
 #pragma unroll
         for (int e = 0; e < V; ++e) {
