@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "step_v1.cuh"
 #include "step_v2.cuh"
+#include "step_v3.cuh"
 #include "adjoint.cuh"
 
 namespace {
@@ -72,7 +73,7 @@ struct cev_fdtd {
     int N[3] = {0, 0, 0};        // internal extents
     double dL = 0, dt = 0, cdt = 0;
     int nH[3] = {0, 0, 0}, nD[3] = {0, 0, 0};   // internal compact counts
-    int variant = 0;             // 0 auto, 1 force baseline kernels, 2 force marching kernels
+    int variant = 0;             // 0 auto, 1 baseline kernels, 2 marching kernels, 3 TMA-staged marching kernels
     int xchunk = 0;              // 0 auto
     int pf_dist = 1;             // L2 prefetch distance of the marching kernels (planes)
     int lz = 8;                  // lanes of a warp along z in the marching kernels (8, 16 or 32)
@@ -208,15 +209,15 @@ bool can_march(const cev_fdtd* p, const StepArgs<T, AT>& a, bool isH) {
             return false;
     }
     (void)isH;
-    return p->variant == 2 || a.Nz >= 2 * V;
+    return p->variant >= 2 || a.Nz >= 2 * V;
 }
 
 // Tiling of one marching launch over a list of boxes.  part: 0 = the whole range [x0,x1) x Ny x Nz in one
 // box (general kernel); 1 = the PML-free interior box clipped to [x0,x1); 2 = the shell = the rest, as up to six slabs.
 template <typename T, typename AT>
-void set_tiles_v2(const cev_fdtd* p, StepArgs<T, AT>& a, int64_t x0, int64_t x1, int part) {
+void set_tiles_v2(const cev_fdtd* p, StepArgs<T, AT>& a, int64_t x0, int64_t x1, int part, int lz_override = 0) {
     constexpr int V = vec_width<T>();
-    const int LZ = p->lz, rows = V2_BY * (32 / LZ);
+    const int LZ = lz_override ? lz_override : p->lz, rows = V2_BY * (32 / LZ);
     a.x0 = (int)x0;
     a.x1 = (int)x1;
     int chunk = p->xchunk;
@@ -225,6 +226,7 @@ void set_tiles_v2(const cev_fdtd* p, StepArgs<T, AT>& a, int64_t x0, int64_t x1,
         // and give the scheduler many CTAs to balance; tuned on B200 (scripts/tune.py)
         const int cols = ((a.Nz + LZ * V - 1) / (LZ * V)) * ((a.Ny + rows - 1) / rows);
         chunk = cols >= 512 ? 8 : 4;
+        if (lz_override) chunk = 16;      // TMA-staged kernels: longer chunks amortise the pipeline fill
     }
     a.xchunk = chunk;
     a.pf_dist = p->pf_dist;
@@ -261,6 +263,23 @@ void set_tiles_v2(const cev_fdtd* p, StepArgs<T, AT>& a, int64_t x0, int64_t x1,
     a.nty = a.n_boxes ? a.box[0].nty : 1;
 }
 
+// TMA-staged kernels: rows of 32 vectors, V3_BY rows per CTA
+template <typename T, typename AT>
+void set_tiles_v3(const cev_fdtd* p, StepArgs<T, AT>& a, int64_t x0, int64_t x1) {
+    constexpr int V = vec_width<T>();
+    set_tiles_v2(p, a, x0, x1, 0, 32);
+    // redo the CTA counts with V3_BY rows per CTA
+    int cta = 0;
+    for (int b = 0; b < a.n_boxes; ++b) {
+        Box& B = a.box[b];
+        B.ntz = (B.z1 - B.z0 + 32 * V - 1) / (32 * V);
+        B.nty = (B.y1 - B.y0 + V3_BY - 1) / V3_BY;
+        B.cta0 = cta;
+        cta += B.ntz * B.nty * ((B.x1 - B.x0 + a.xchunk - 1) / a.xchunk);
+    }
+    a.n_tiles = cta;
+}
+
 // Is it worth (and possible) to split [x0,x1) into an interior launch and a shell launch?
 template <typename T>
 bool want_split(const cev_fdtd* p, int64_t x0, int64_t x1) {
@@ -278,14 +297,16 @@ bool want_split(const cev_fdtd* p, int64_t x0, int64_t x1) {
 // Source points of the x-planes [a.x0, a.x1), sorted by the CTA of the marching D kernel that owns
 // their cell (built once per launch geometry, cached in the plan).
 template <typename T, typename AT>
-int attach_sources_v2(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row, int part) {
+int attach_sources_v2(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row, int part, int lz_override = 0,
+                      int rows_override = 0) {
     constexpr int V = vec_width<T>();
+    const int LZ = lz_override ? lz_override : p->lz;
     cev_fdtd::SrcTiling* hit = nullptr;
     for (auto& t : p->src_tilings)
-        if (t->x0 == a.x0 && t->x1 == a.x1 && t->xchunk == a.xchunk && t->lz == p->lz && t->vec == V && t->part == part)
+        if (t->x0 == a.x0 && t->x1 == a.x1 && t->xchunk == a.xchunk && t->lz == LZ && t->vec == V && t->part == part)
             hit = t.get();
     if (!hit) {
-        const int LZ = p->lz, rows = V2_BY * (32 / LZ);
+        const int rows = rows_override ? rows_override : V2_BY * (32 / LZ);
         const int64_t plane = (int64_t)a.Ny * a.Nz;
         std::vector<int> owner;
         std::vector<int64_t> pick;
@@ -317,7 +338,7 @@ int attach_sources_v2(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row, i
         }
         for (int b = 0; b < a.n_tiles; ++b) begin[b + 1] += begin[b];
         std::unique_ptr<cev_fdtd::SrcTiling> t(new cev_fdtd::SrcTiling());
-        t->x0 = a.x0; t->x1 = a.x1; t->xchunk = a.xchunk; t->lz = p->lz; t->vec = V; t->part = part;
+        t->x0 = a.x0; t->x1 = a.x1; t->xchunk = a.xchunk; t->lz = LZ; t->vec = V; t->part = part;
         const size_t mm = (size_t)(m > 0 ? m : 1);
         if (t->begin.alloc(begin.size() * 4) || t->comp.alloc(mm * 4) || t->id.alloc(mm * 4) || t->cell.alloc(mm * 4) ||
             t->w.alloc(mm * 8))
@@ -373,6 +394,20 @@ int launch_H(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, void* con
     }
     constexpr int V = vec_width<T>();
     const dim3 blk(32, V2_BY);
+    if (p->variant == 3) {       // TMA-staged kernel: one launch, rows of 32 vectors
+        set_tiles_v3(p, a, x0, x1);
+        const int aux = attach_probes(p, a, 0, probe_t, partials);
+        if (a.n_tiles + aux == 0) return 0;
+        static bool attr_done = false;
+        const size_t smem = V3Layout<T, V>::h_bytes();
+        if (!attr_done) {
+            CUDA_TRY(cudaFuncSetAttribute(k_step_H_v3<T, AT, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done = true;
+        }
+        k_step_H_v3<T, AT, V><<<a.n_tiles + aux, dim3(32, V3_BY), smem, s>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     const bool split = want_split<T>(p, x0, x1);
     bool probes_done = false;
     for (int part = split ? 1 : 0; part <= (split ? 2 : 0); ++part) {
@@ -437,6 +472,23 @@ int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const
     constexpr int V = vec_width<T>();
     const dim3 blk(32, V2_BY);
     const bool extras = a.J[0] || a.J[1] || a.J[2] || a.Eout[0] || a.Eout[1] || a.Eout[2];
+    // auto: the TMA-staged D kernel wins in fp64 (measured, scripts/tune.py); fp32 and the H half-step stay on the
+    // register-marching kernels
+    if ((p->variant == 3 || (p->variant == 0 && sizeof(T) == 8)) && !extras) {
+        set_tiles_v3(p, a, x0, x1);
+        if (inject && attach_sources_v2(p, a, wave_row, 0, 32, V3_BY)) return -1;
+        const int aux = attach_probes(p, a, 1, probe_t, partials);
+        if (a.n_tiles + aux == 0) return 0;
+        static bool attr_done = false;
+        const size_t smem = V3Layout<T, V>::d_bytes();
+        if (!attr_done) {
+            CUDA_TRY(cudaFuncSetAttribute(k_step_D_v3<T, AT, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done = true;
+        }
+        k_step_D_v3<T, AT, V><<<a.n_tiles + aux, dim3(32, V3_BY), smem, s>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     const bool split = !extras && want_split<T>(p, x0, x1);   // the per-step forward() API keeps one launch
     bool probes_done = false;
     for (int part = split ? 1 : 0; part <= (split ? 2 : 0); ++part) {
@@ -788,7 +840,7 @@ int cev_fdtd_destroy(cev_fdtd* p) {
 int cev_fdtd_set_option(cev_fdtd* p, const char* name, int64_t value) {
     if (!p || !name) return fail("NULL argument");
     if (!strcmp(name, "kernel_variant")) {
-        if (value < 0 || value > 2) return fail("kernel_variant must be 0 (auto), 1 (baseline) or 2 (marching)");
+        if (value < 0 || value > 3) return fail("kernel_variant must be 0 (auto), 1 (baseline), 2 (marching) or 3 (TMA-staged)");
         p->variant = (int)value;
     } else if (!strcmp(name, "prefetch_planes")) {
         if (value < 0 || value > 64) return fail("prefetch_planes must be in [0, 64]");

@@ -51,6 +51,10 @@ SHAPES = [((20, 18, 136), (4, 3, 6)), ((9, 7, 64), (2, 0, 5)), ((3, 5, 24), (0, 
 def test_marching_equals_baseline_bitwise(shape, npml, dtype):
     case = _case(shape, npml, 40, 7)
     s1, f1, p1 = _run(case, dtype, 1)
+    s0, f0, p0 = _run(case, dtype, 0)          # the default (auto) kernel choice
+    for k in FIELD_KEYS:
+        assert np.array_equal(f1[k], f0[k]), (k, 'auto')
+    assert np.array_equal(s1, s0)
     for xchunk, lanes_z, pf, split in ((0, 8, 1, 1), (1, 16, 0, 1), (3, 32, 2, 0), (1000, 8, 5, 1), (5, 32, 1, 1), (0, 8, 1, 0)):
         s2, f2, p2 = _run(case, dtype, 2, xchunk, lanes_z=lanes_z, prefetch=pf, split=split)
         for k in FIELD_KEYS:
@@ -58,6 +62,13 @@ def test_marching_equals_baseline_bitwise(shape, npml, dtype):
         for a, b in zip(p1, p2):
             assert np.array_equal(a, b), xchunk
         assert np.array_equal(s1, s2)
+    for xchunk in (0, 1, 5):       # TMA-staged kernels (kernel_variant = 3)
+        s3, f3, p3 = _run(case, dtype, 3, xchunk)
+        for k in FIELD_KEYS:
+            assert np.array_equal(f1[k], f3[k]), (k, "v3", xchunk)
+        for a, b in zip(p1, p3):
+            assert np.array_equal(a, b), ("v3", xchunk)
+        assert np.array_equal(s1, s3)
 
 
 def test_marching_forward_api_with_dense_J_and_E_output():
