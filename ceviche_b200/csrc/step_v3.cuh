@@ -193,17 +193,19 @@ __global__ void __launch_bounds__(32 * V3_BY) k_step_H_v3(const StepArgs<T, AT> 
     for (int i = xs; i < xe; ++i) {
         if (i + NS - 1 <= xe) issue(i + NS - 1, i + NS - 1 < xe);
         const int q = i - xs;
+        // PML integrals go through the LSU: issue them (and the L2 prefetch of the next plane's) before
+        // blocking on the TMA barriers so that their latency overlaps the wait
+        const int mx = a.mapH[0][i];
+        const bool pml = yz_pml || mx >= 0;
+        PmlCtx<T, AT, V, true> ctx;
+        if (pml && active) ctx.load(a, i, j, k0, mx, my, mz);
+        if (active && i + 1 < a.x1) PmlCtx<T, AT, V, true>::prefetch(a, i + 1, j, k0, my, mz, (lane & 7) == 0);
         mbar_wait(&full[q % NS], (q / NS) & 1);
         mbar_wait(&full[(q + 1) % NS], ((q + 1) / NS) & 1);
         const T* cur = stage0 + (size_t)(q % NS) * L::H_STAGE;
         const T* nxt = stage0 + (size_t)((q + 1) % NS) * L::H_STAGE;
         const int col = lane * V;
         const int pbase = i * plane;
-
-        const int mx = a.mapH[0][i];
-        const bool pml = yz_pml || mx >= 0;
-        PmlCtx<T, AT, V, true> ctx;
-        if (pml && active) ctx.load(a, i, j, k0, mx, my, mz);
 
         AT E[3][V], CE[3][V];
         Vec<T, V> h[3];
@@ -343,17 +345,17 @@ __global__ void __launch_bounds__(32 * V3_BY) k_step_D_v3(const StepArgs<T, AT> 
     for (int i = xs; i < xe; ++i) {
         if (i + NS - 2 < xe) issue(i + NS - 2, true);
         const int q = i - xs;                      // prev plane is use #q, current plane use #(q+1) of the ring
+        const int mx = a.mapD[0][i];
+        const bool pml = yz_pml || mx >= 0;
+        PmlCtx<T, AT, V, false> ctx;
+        if (pml && active) ctx.load(a, i, j, k0, mx, my, mz);
+        if (active && i + 1 < a.x1) PmlCtx<T, AT, V, false>::prefetch(a, i + 1, j, k0, my, mz, (lane & 7) == 0);
         mbar_wait(&full[q % NS], (q / NS) & 1);
         mbar_wait(&full[(q + 1) % NS], ((q + 1) / NS) & 1);
         const T* prv = stage0 + (size_t)(q % NS) * L::D_STAGE;
         const T* cur = stage0 + (size_t)((q + 1) % NS) * L::D_STAGE;
         const int col = V + lane * V;
         const int pbase = i * plane;
-
-        const int mx = a.mapD[0][i];
-        const bool pml = yz_pml || mx >= 0;
-        PmlCtx<T, AT, V, false> ctx;
-        if (pml && active) ctx.load(a, i, j, k0, mx, my, mz);
 
         Vec<T, V> h[3], d[3];
 #pragma unroll
