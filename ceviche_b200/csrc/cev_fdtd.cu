@@ -77,6 +77,7 @@ struct cev_fdtd {
     int xchunk = 0;              // 0 auto
     int pf_dist = 1;             // L2 prefetch distance of the marching kernels (planes)
     int lz = 8;                  // lanes of a warp along z in the marching kernels (8, 16 or 32)
+    bool smem_attr_H = false, smem_attr_D = false;   // dynamic-smem opt-in done for this plan's device / dtype
     int split = 0;               // 1: separate launches for the PML-free interior box and the PML shell
     int in_lo[3] = {0, 0, 0}, in_hi[3] = {0, 0, 0};   // per internal axis: longest index run off the PML (H and D sampling)
     DeviceBuf tables;            // u/r (f32 + f64) and maps for 3 axes x {H, D}
@@ -398,11 +399,10 @@ int launch_H(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, void* con
         set_tiles_v3(p, a, x0, x1);
         const int aux = attach_probes(p, a, 0, probe_t, partials);
         if (a.n_tiles + aux == 0) return 0;
-        static bool attr_done = false;
         const size_t smem = V3Layout<T, V>::h_bytes();
-        if (!attr_done) {
+        if (!p->smem_attr_H) {      // per plan: a plan has one device and one (T, AT)
             CUDA_TRY(cudaFuncSetAttribute(k_step_H_v3<T, AT, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_done = true;
+            p->smem_attr_H = true;
         }
         k_step_H_v3<T, AT, V><<<a.n_tiles + aux, dim3(32, V3_BY), smem, s>>>(a);
         CUDA_TRY(cudaGetLastError());
@@ -479,11 +479,10 @@ int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const
         if (inject && attach_sources_v2(p, a, wave_row, 0, 32, V3_BY)) return -1;
         const int aux = attach_probes(p, a, 1, probe_t, partials);
         if (a.n_tiles + aux == 0) return 0;
-        static bool attr_done = false;
         const size_t smem = V3Layout<T, V>::d_bytes();
-        if (!attr_done) {
+        if (!p->smem_attr_D) {
             CUDA_TRY(cudaFuncSetAttribute(k_step_D_v3<T, AT, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_done = true;
+            p->smem_attr_D = true;
         }
         k_step_D_v3<T, AT, V><<<a.n_tiles + aux, dim3(32, V3_BY), smem, s>>>(a);
         CUDA_TRY(cudaGetLastError());
