@@ -915,6 +915,7 @@ int cev_fdtd_jvp_run(cev_fdtd* p, const cev_state* st, int B, const cev_state* t
                      int64_t nsteps, const double* waveform, double* partials, double* tangent_partials, void* stream) {
     if (!p || !st || B < 0 || (B > 0 && (!tangents || !tans))) return fail("bad jvp arguments");
     if (nsteps < 0) return fail("nsteps must be >= 0");
+    if (nsteps == 0) return 0;
     if (p->n_src_pts > 0 && !waveform) return fail("plan has sources but waveform is NULL");
     if (p->n_slots > 0 && (!partials || (B > 0 && !tangent_partials))) return fail("plan has probes but partials is NULL");
     DeviceGuard guard(p->device);
@@ -1073,6 +1074,7 @@ int cev_fdtd_probe_slots(const cev_fdtd* p, int32_t* slot_probe) {
 int cev_fdtd_run(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* waveform, double* partials, void* stream) {
     if (!p || !st) return fail("NULL argument");
     if (nsteps < 0) return fail("nsteps must be >= 0");
+    if (nsteps == 0) return 0;
     if (p->n_src_pts > 0 && !waveform) return fail("plan has sources but waveform is NULL");
     if (p->n_slots > 0 && !partials) return fail("plan has probes but partials is NULL");
     if (st->D_xhi[1] || st->D_xhi[2] || st->H_xlo[1] || st->H_xlo[2]) return fail("cev_fdtd_run steps a whole (periodic) grid; slabs are driven per half-step");

@@ -150,3 +150,28 @@ def test_reference_api_quirks():
     O = OracleFDTD(eps, 5e-8, [2, 2, 0])
     assert np.array_equal(F.eps_xx.cpu().numpy() / 2, O.eps_yee[0])
     assert repr(F) == "FDTD(eps_r.shape=(10, 9, 1), dL=5e-08, NPML=[2, 2, 0])"
+
+
+def test_edge_cases_empty_inputs():
+    """Zero steps, probes / sources with no points, no probes at all, a run continued after forward()."""
+    import ceviche_b200
+    shape = (9, 8, 16)
+    eps = 1 + np.random.default_rng(4).random(shape)
+    F = ceviche_b200.fdtd(eps, 5e-8, [2, 0, 3])
+    zero = np.zeros(shape)
+    hot = np.zeros(shape); hot[4, 4, 8] = 1.0
+    s = F.run(0, [("z", hot, np.zeros(0))], [("Ez", hot)])
+    assert tuple(s.shape) == (0, 1) and F.t_index == 0
+    s = F.run(5, [("z", zero, np.ones(5)), ("x", hot, np.ones(5))], [("Ez", zero), ("Hy", hot)])
+    assert tuple(s.shape) == (5, 2) and float(s[:, 0].abs().max()) == 0.0 and float(s[:, 1].abs().max()) > 0.0
+    s = F.run(3, sources=(), probes=())            # no sources, no probes: free evolution
+    assert tuple(s.shape) == (3, 0) and F.t_index == 8
+    O = OracleFDTD(eps, 5e-8, [2, 0, 3])
+    for t in range(5):
+        O.step(Jx=hot * 1.0)
+    for t in range(3):
+        O.step()
+    f = F.forward(Jy=hot)                          # per-step call continues the fused run's state
+    g = O.step(Jy=hot)
+    for k in FIELD_KEYS:
+        assert rel_l2(f[k].cpu().numpy(), g[k]) <= 1e-12, k
