@@ -180,6 +180,7 @@ class _RunFn(torch.autograd.Function):
             sim._refresh_E()
         ctx.mE = [m.clone() for m in sim._mE]
         ctx.n_probes = sim._n_probes
+        ctx.active = sim._active
         return torch.cat(chunks) if chunks else torch.zeros((0, sim._n_probes), dtype=torch.float64, device=sim.device)
 
     @staticmethod
@@ -188,6 +189,7 @@ class _RunFn(torch.autograd.Function):
         plan = sim._ensure_plan()
         lib, h, s = plan.lib, plan.handle, sim._stream()
         shapes = plan.pml_shapes
+        sim._apply_active(ctx.active)       # the recomputation runs the forward kernels: same component set
         with torch.cuda.device(sim.device):
             gbar = gbar.detach().to(torch.float64).contiguous()
             zf = lambda: [torch.zeros(sim.grid_shape, dtype=sim.dtype, device=sim.device) for _ in range(3)]
@@ -215,6 +217,7 @@ class _RunFn(torch.autograd.Function):
                     fwd = _state(hist[k - 1], hist[k - 1], ctx.mE, [None] * 12)
                     _lib.check(lib.cev_fdtd_adjoint_step(h, C.byref(fwd), C.byref(adj), s))
                 del hist
+        sim._apply_active(sim._active)
         return (None, None, None, None, *G)
 
 

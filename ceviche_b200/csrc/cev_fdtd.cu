@@ -77,6 +77,7 @@ struct cev_fdtd {
     int xchunk = 0;              // 0 auto
     int pf_dist = 1;             // L2 prefetch distance of the marching kernels (planes)
     int lz = 8;                  // lanes of a warp along z in the marching kernels (8, 16 or 32)
+    unsigned on = 63u;           // internal component mask (bits 0-2 E/D, 3-5 H): see StepArgs::on
     bool smem_attr_H = false, smem_attr_D = false;   // dynamic-smem opt-in done for this plan's device / dtype
     int split = 0;               // 1: separate launches for the PML-free interior box and the PML shell
     int in_lo[3] = {0, 0, 0}, in_hi[3] = {0, 0, 0};   // per internal axis: longest index run off the PML (H and D sampling)
@@ -176,6 +177,7 @@ int fill_args(const cev_fdtd* p, const cev_state* st, StepArgs<T, AT>& a, const 
     }
     a.cdt = (AT)p->cdt;
     a.inv_dL = (AT)(1.0 / p->dL);
+    a.on = p->on;
     fill_probe_table(p, a.pr);
     a.t_probe = -1;
     return 0;
@@ -379,11 +381,13 @@ int launch_H(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, void* con
              int64_t probe_t, double* partials, cudaStream_t s) {
     StepArgs<T, AT> a;
     if (fill_args(p, st, a, tan)) return -1;
-    if (H_out)
+    if (H_out) {
+        a.on = 63u;              // out-of-place: every output array is written
         for (int A = 0; A < 3; ++A) {
             a.Hout[A] = (T*)H_out[p->to_logical(A)];
             if (!a.Hout[A]) return fail("H_out entries must be non-NULL");
         }
+    }
     const bool march = can_march(p, a, true);
     if (!march) {
         set_tiles_v1(a, x0, x1);
@@ -395,7 +399,7 @@ int launch_H(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, void* con
     }
     constexpr int V = vec_width<T>();
     const dim3 blk(32, V2_BY);
-    if (p->variant == 3) {       // TMA-staged kernel: one launch, rows of 32 vectors
+    if (p->variant == 3 && a.on == 63u) {       // TMA-staged kernel: one launch, rows of 32 vectors
         set_tiles_v3(p, a, x0, x1);
         const int aux = attach_probes(p, a, 0, probe_t, partials);
         if (a.n_tiles + aux == 0) return 0;
@@ -458,6 +462,7 @@ int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const
         if (J_scale) a.Jscale[A] = (AT)J_scale[L];
         if (J_wave) a.Jwave[A] = J_wave[L];
     }
+    if (D_out) a.on = 63u;       // out-of-place: every output array is written
     const bool march = can_march(p, a, false);
     const bool inject = wave_row && p->n_src_pts > 0 && x1 > x0;
     if (!march) {
@@ -472,9 +477,10 @@ int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const
     constexpr int V = vec_width<T>();
     const dim3 blk(32, V2_BY);
     const bool extras = a.J[0] || a.J[1] || a.J[2] || a.Eout[0] || a.Eout[1] || a.Eout[2];
+    if (extras) a.on = 63u;
     // auto: the TMA-staged D kernel wins in fp64 (measured, scripts/tune.py); fp32 and the H half-step stay on the
     // register-marching kernels
-    if ((p->variant == 3 || (p->variant == 0 && sizeof(T) == 8)) && !extras) {
+    if ((p->variant == 3 || (p->variant == 0 && sizeof(T) == 8 && x1 - x0 >= 4)) && !extras && a.on == 63u) {
         set_tiles_v3(p, a, x0, x1);
         if (inject && attach_sources_v2(p, a, wave_row, 0, 32, V3_BY)) return -1;
         const int aux = attach_probes(p, a, 1, probe_t, partials);
@@ -844,6 +850,15 @@ int cev_fdtd_set_option(cev_fdtd* p, const char* name, int64_t value) {
     } else if (!strcmp(name, "prefetch_planes")) {
         if (value < 0 || value > 64) return fail("prefetch_planes must be in [0, 64]");
         p->pf_dist = (int)value;
+    } else if (!strcmp(name, "active_components")) {
+        // logical bits 0-2: D/E x,y,z may be non-zero; bits 3-5: H x,y,z.  The caller guarantees the others are and stay 0.
+        if (value < 0 || value > 63) return fail("active_components is a 6-bit mask");
+        unsigned m = 0;
+        for (int c = 0; c < 3; ++c) {
+            if (value & (1 << c)) m |= 1u << p->to_internal(c);
+            if (value & (8 << c)) m |= 8u << p->to_internal(c);
+        }
+        p->on = m;
     } else if (!strcmp(name, "split_launch")) {
         if (value != 0 && value != 1) return fail("split_launch must be 0 or 1");
         p->split = (int)value;

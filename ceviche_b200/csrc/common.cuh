@@ -12,6 +12,23 @@ __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+// a*b + c: two roundings (the reference's numpy sequence) by default; -DCEV_FMA fuses them (experiment:
+// fewer FP64 instructions / less power, results still within the parity tolerance but not the reference's
+// rounding sequence)
+__device__ __forceinline__ double muladd(double a, double b, double c) {
+#ifdef CEV_FMA
+    return __fma_rn(a, b, c);
+#else
+    return __dadd_rn(__dmul_rn(a, b), c);
+#endif
+}
+__device__ __forceinline__ float muladd(float a, float b, float c) {
+#ifdef CEV_FMA
+    return __fmaf_rn(a, b, c);
+#else
+    return __fadd_rn(__fmul_rn(a, b), c);
+#endif
+}
 
 // Sampling of probe point sets: one CTA per "slot" (a chunk of one probe's points) does a
 // fixed-order reduction and writes ONE partial sum -> deterministic series, no atomics.
@@ -82,6 +99,9 @@ struct StepArgs {
     const double*  src_w;
     const double*  src_wave;
     // tiling + auxiliary probe CTAs appended to the grid
+    // components known to be identically zero are skipped (2-D TM / TE runs): bits 0-2 = E/D component active,
+    // bits 3-5 = H component active (internal order).  The caller guarantees the inactive ones are and stay zero.
+    unsigned on;
     int n_tiles, ntz, nty, xchunk;
     int n_boxes;
     Box box[MAX_BOXES];
@@ -136,7 +156,7 @@ __device__ void probe_block(const StepArgs<T, AT>& a, int slot) {
 // (a1-a0)/dL - (b1-b0)/dL, both quotients rounded before the subtraction (derivatives.py:16-30)
 template <typename AT>
 __device__ __forceinline__ AT curl2(AT a1, AT a0, AT b1, AT b0, AT inv) {
-    return add_rn(mul_rn(a1 - a0, inv), -mul_rn(b1 - b0, inv));
+    return muladd(a1 - a0, inv, -mul_rn(b1 - b0, inv));
 }
 
 // Coefficients of fdtd.py:272-311 rewritten division-free from the per-axis tables
@@ -161,16 +181,16 @@ __device__ __forceinline__ void coef12(AT ua, AT ra, AT ub, AT rb, AT scdt, AT& 
 template <typename T, typename AT>
 __device__ __forceinline__ AT update_cell(AT old, AT curl, AT m1, AT m2, AT ua, AT ra, AT ub, AT rb, AT uc, AT scdt,
                                           T* Icurl, int64_t icurl, T* Iself, int64_t iself) {
-    AT v = add_rn(mul_rn(m1, old), mul_rn(m2, curl));
+    AT v = muladd(m1, old, mul_rn(m2, curl));
     if (icurl >= 0) {
         const AT I = (AT)Icurl[icurl] + curl;
         Icurl[icurl] = (T)I;
-        v = add_rn(v, mul_rn(mul_rn(mul_rn(scdt, uc + uc), mul_rn(ra, rb)), I));
+        v = muladd(mul_rn(mul_rn(scdt, uc + uc), mul_rn(ra, rb)), I, v);
     }
     if (iself >= 0) {
         const AT I = (AT)Iself[iself] + old;
         Iself[iself] = (T)I;
-        v = add_rn(v, mul_rn(mul_rn(mul_rn(mul_rn(AT(-4), ua), ub), mul_rn(ra, rb)), I));
+        v = muladd(mul_rn(mul_rn(mul_rn(AT(-4), ua), ub), mul_rn(ra, rb)), I, v);
     }
     return v;
 }

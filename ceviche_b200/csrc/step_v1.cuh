@@ -37,23 +37,36 @@ __global__ void __launch_bounds__(V1_TZ* V1_TY) k_step_H_v1(const StepArgs<T, AT
     const int64_t o_kp = i * plane + (int64_t)j * a.Nz + kp;
     const bool last = (i + 1 == a.Nx);
 
-#define E_AT(c, off)                                                                        \
-    (a.dmE[c] ? add_rn(mul_rn((AT)a.mE[c][off], (AT)a.Din[c][off]), mul_rn((AT)a.dmE[c][off], (AT)a.Dp[c][off])) \
-              : mul_rn((AT)a.mE[c][off], (AT)a.Din[c][off]))
-    const AT Ex = E_AT(0, o), Ey = E_AT(1, o), Ez = E_AT(2, o);
-    const AT Ex_jp = E_AT(0, o_jp), Ez_jp = E_AT(2, o_jp);
-    const AT Ex_kp = E_AT(0, o_kp), Ey_kp = E_AT(1, o_kp);
-    AT Ey_ip, Ez_ip;
-    if (!last) {
-        Ey_ip = E_AT(1, o + plane);
-        Ez_ip = E_AT(2, o + plane);
-    } else {
-        Ey_ip = mul_rn((AT)a.mEhi[1][o_in], (AT)a.Dhi[1][o_in]);
-        Ez_ip = mul_rn((AT)a.mEhi[2][o_in], (AT)a.Dhi[2][o_in]);
-        if (a.dmE[1]) Ey_ip = add_rn(Ey_ip, mul_rn((AT)a.dmEhi[1][o_in], (AT)a.Dphi[1][o_in]));
-        if (a.dmE[2]) Ez_ip = add_rn(Ez_ip, mul_rn((AT)a.dmEhi[2][o_in], (AT)a.Dphi[2][o_in]));
-    }
-#undef E_AT
+    // Every load is issued first, predicated on the (kernel-uniform) component mask and tangent flag, and the
+    // arithmetic follows: branches around dependent load/multiply pairs would serialise the memory latency.
+    struct ERaw { AT m, d, dm, dp; };
+    auto e_load = [&](int c, const T* M, const T* D, const T* dM, const T* Dp, int64_t off) {
+        const bool on = (a.on >> c) & 1u, tan = on && a.dmE[c];
+        ERaw r;
+        r.m = on ? (AT)M[off] : AT(0);
+        r.d = on ? (AT)D[off] : AT(0);
+        r.dm = tan ? (AT)dM[off] : AT(0);
+        r.dp = tan ? (AT)Dp[off] : AT(0);
+        return r;
+    };
+    auto e_val = [&](int c, const ERaw& r) {      // E = mE*D (+ dmE*D_primal for a tangent state)
+        const AT e = mul_rn(r.m, r.d);
+        return a.dmE[c] ? add_rn(e, mul_rn(r.dm, r.dp)) : e;
+    };
+#define E_HERE(c, off) e_load(c, a.mE[c], a.Din[c], a.dmE[c], a.Dp[c], off)
+    const ERaw rx0 = E_HERE(0, o), ry0 = E_HERE(1, o), rz0 = E_HERE(2, o);
+    const ERaw rxj = E_HERE(0, o_jp), rzj = E_HERE(2, o_jp);
+    const ERaw rxk = E_HERE(0, o_kp), ryk = E_HERE(1, o_kp);
+#undef E_HERE
+    const int64_t o_ip = last ? o_in : o + plane;     // x+1 plane: inside the array, or the halo / wrap plane
+    const ERaw ryi = e_load(1, last ? a.mEhi[1] : a.mE[1], last ? a.Dhi[1] : a.Din[1], last ? a.dmEhi[1] : a.dmE[1],
+                            last ? a.Dphi[1] : a.Dp[1], o_ip);
+    const ERaw rzi = e_load(2, last ? a.mEhi[2] : a.mE[2], last ? a.Dhi[2] : a.Din[2], last ? a.dmEhi[2] : a.dmE[2],
+                            last ? a.Dphi[2] : a.Dp[2], o_ip);
+    const AT Ex = e_val(0, rx0), Ey = e_val(1, ry0), Ez = e_val(2, rz0);
+    const AT Ex_jp = e_val(0, rxj), Ez_jp = e_val(2, rzj);
+    const AT Ex_kp = e_val(0, rxk), Ey_kp = e_val(1, ryk);
+    const AT Ey_ip = e_val(1, ryi), Ez_ip = e_val(2, rzi);
     const AT inv = a.inv_dL;
     const AT CEx = curl2<AT>(Ez_jp, Ez, Ey_kp, Ey, inv);
     const AT CEy = curl2<AT>(Ex_kp, Ex, Ez_ip, Ez, inv);
@@ -64,23 +77,30 @@ __global__ void __launch_bounds__(V1_TZ* V1_TY) k_step_H_v1(const StepArgs<T, AT
     const int mx = a.mapH[0][i], my = a.mapH[1][j], mz = a.mapH[2][k];
     const AT s = -a.cdt;
 
+    // A masked-out component keeps its loads, integral updates and store predicated off (straight-line code: the
+    // three updates overlap their memory latency).
+    const bool hx_on = a.on & 8u, hy_on = a.on & 16u, hz_on = a.on & 32u;
+    const AT Hx0 = hx_on ? (AT)a.Hin[0][o] : AT(0), Hy0 = hy_on ? (AT)a.Hin[1][o] : AT(0), Hz0 = hz_on ? (AT)a.Hin[2][o] : AT(0);
     // x component: (a,b) = (y,z), own = x.   ICE_x (nHx,Ny,Nz), IH_x (Nx,nHy,nHz)
     {
-        const int64_t ic = (mx >= 0) ? ((int64_t)mx * a.Ny + j) * a.Nz + k : -1;
-        const int64_t is = (my >= 0 && mz >= 0) ? ((int64_t)i * a.nH[1] + my) * a.nH[2] + mz : -1;
-        a.Hout[0][o] = (T)update_component<T, AT>((AT)a.Hin[0][o], CEx, uy, ry, uz, rz, ux, s, a.ICE[0], ic, a.IH[0], is);
+        const int64_t ic = (mx >= 0 && hx_on) ? ((int64_t)mx * a.Ny + j) * a.Nz + k : -1;
+        const int64_t is = (my >= 0 && mz >= 0 && hx_on) ? ((int64_t)i * a.nH[1] + my) * a.nH[2] + mz : -1;
+        const AT v = update_component<T, AT>(Hx0, CEx, uy, ry, uz, rz, ux, s, a.ICE[0], ic, a.IH[0], is);
+        if (hx_on) a.Hout[0][o] = (T)v;
     }
     // y component: (a,b) = (x,z), own = y.   ICE_y (Nx,nHy,Nz), IH_y (nHx,Ny,nHz)
     {
-        const int64_t ic = (my >= 0) ? ((int64_t)i * a.nH[1] + my) * a.Nz + k : -1;
-        const int64_t is = (mx >= 0 && mz >= 0) ? ((int64_t)mx * a.Ny + j) * a.nH[2] + mz : -1;
-        a.Hout[1][o] = (T)update_component<T, AT>((AT)a.Hin[1][o], CEy, ux, rx, uz, rz, uy, s, a.ICE[1], ic, a.IH[1], is);
+        const int64_t ic = (my >= 0 && hy_on) ? ((int64_t)i * a.nH[1] + my) * a.Nz + k : -1;
+        const int64_t is = (mx >= 0 && mz >= 0 && hy_on) ? ((int64_t)mx * a.Ny + j) * a.nH[2] + mz : -1;
+        const AT v = update_component<T, AT>(Hy0, CEy, ux, rx, uz, rz, uy, s, a.ICE[1], ic, a.IH[1], is);
+        if (hy_on) a.Hout[1][o] = (T)v;
     }
     // z component: (a,b) = (x,y), own = z.   ICE_z (Nx,Ny,nHz), IH_z (nHx,nHy,Nz)
     {
-        const int64_t ic = (mz >= 0) ? ((int64_t)i * a.Ny + j) * a.nH[2] + mz : -1;
-        const int64_t is = (mx >= 0 && my >= 0) ? ((int64_t)mx * a.nH[1] + my) * a.Nz + k : -1;
-        a.Hout[2][o] = (T)update_component<T, AT>((AT)a.Hin[2][o], CEz, ux, rx, uy, ry, uz, s, a.ICE[2], ic, a.IH[2], is);
+        const int64_t ic = (mz >= 0 && hz_on) ? ((int64_t)i * a.Ny + j) * a.nH[2] + mz : -1;
+        const int64_t is = (mx >= 0 && my >= 0 && hz_on) ? ((int64_t)mx * a.nH[1] + my) * a.Nz + k : -1;
+        const AT v = update_component<T, AT>(Hz0, CEz, ux, rx, uy, ry, uz, s, a.ICE[2], ic, a.IH[2], is);
+        if (hz_on) a.Hout[2][o] = (T)v;
     }
 }
 
@@ -109,17 +129,19 @@ __global__ void __launch_bounds__(V1_TZ* V1_TY) k_step_D_v1(const StepArgs<T, AT
     const int64_t o_jm = i * plane + (int64_t)jm * a.Nz + k;
     const int64_t o_km = i * plane + (int64_t)j * a.Nz + km;
 
-    const AT Hx = (AT)a.Hin[0][o], Hy = (AT)a.Hin[1][o], Hz = (AT)a.Hin[2][o];
-    const AT Hx_jm = (AT)a.Hin[0][o_jm], Hz_jm = (AT)a.Hin[2][o_jm];
-    const AT Hx_km = (AT)a.Hin[0][o_km], Hy_km = (AT)a.Hin[1][o_km];
+#define H_AT(c, ptr, off) (((a.on >> (3 + (c))) & 1u) ? (AT)(ptr)[off] : AT(0))
+    const AT Hx = H_AT(0, a.Hin[0], o), Hy = H_AT(1, a.Hin[1], o), Hz = H_AT(2, a.Hin[2], o);
+    const AT Hx_jm = H_AT(0, a.Hin[0], o_jm), Hz_jm = H_AT(2, a.Hin[2], o_jm);
+    const AT Hx_km = H_AT(0, a.Hin[0], o_km), Hy_km = H_AT(1, a.Hin[1], o_km);
     AT Hy_im, Hz_im;
     if (i > 0) {
-        Hy_im = (AT)a.Hin[1][o - plane];
-        Hz_im = (AT)a.Hin[2][o - plane];
+        Hy_im = H_AT(1, a.Hin[1], o - plane);
+        Hz_im = H_AT(2, a.Hin[2], o - plane);
     } else {
-        Hy_im = (AT)a.Hlo[1][o_in];
-        Hz_im = (AT)a.Hlo[2][o_in];
+        Hy_im = H_AT(1, a.Hlo[1], o_in);
+        Hz_im = H_AT(2, a.Hlo[2], o_in);
     }
+#undef H_AT
     const AT inv = a.inv_dL;
     const AT CHx = curl2<AT>(Hz, Hz_jm, Hy, Hy_km, inv);
     const AT CHy = curl2<AT>(Hx, Hx_km, Hz, Hz_im, inv);
@@ -129,24 +151,28 @@ __global__ void __launch_bounds__(V1_TZ* V1_TY) k_step_D_v1(const StepArgs<T, AT
     const AT rx = a.rD[0][i], ry = a.rD[1][j], rz = a.rD[2][k];
     const int mx = a.mapD[0][i], my = a.mapD[1][j], mz = a.mapD[2][k];
     const AT s = a.cdt;
+    // masked-out components: loads and integral updates predicated off, straight-line code (see k_step_H_v1)
+    const bool dx_on = a.on & 1u, dy_on = a.on & 2u, dz_on = a.on & 4u;
+    const AT Dx0 = dx_on ? (AT)a.Din[0][o] : AT(0), Dy0 = dy_on ? (AT)a.Din[1][o] : AT(0), Dz0 = dz_on ? (AT)a.Din[2][o] : AT(0);
     AT Dn[3];
     {
-        const int64_t ic = (mx >= 0) ? ((int64_t)mx * a.Ny + j) * a.Nz + k : -1;
-        const int64_t is = (my >= 0 && mz >= 0) ? ((int64_t)i * a.nD[1] + my) * a.nD[2] + mz : -1;
-        Dn[0] = update_component<T, AT>((AT)a.Din[0][o], CHx, uy, ry, uz, rz, ux, s, a.ICH[0], ic, a.ID[0], is);
+        const int64_t ic = (mx >= 0 && dx_on) ? ((int64_t)mx * a.Ny + j) * a.Nz + k : -1;
+        const int64_t is = (my >= 0 && mz >= 0 && dx_on) ? ((int64_t)i * a.nD[1] + my) * a.nD[2] + mz : -1;
+        Dn[0] = update_component<T, AT>(Dx0, CHx, uy, ry, uz, rz, ux, s, a.ICH[0], ic, a.ID[0], is);
     }
     {
-        const int64_t ic = (my >= 0) ? ((int64_t)i * a.nD[1] + my) * a.Nz + k : -1;
-        const int64_t is = (mx >= 0 && mz >= 0) ? ((int64_t)mx * a.Ny + j) * a.nD[2] + mz : -1;
-        Dn[1] = update_component<T, AT>((AT)a.Din[1][o], CHy, ux, rx, uz, rz, uy, s, a.ICH[1], ic, a.ID[1], is);
+        const int64_t ic = (my >= 0 && dy_on) ? ((int64_t)i * a.nD[1] + my) * a.Nz + k : -1;
+        const int64_t is = (mx >= 0 && mz >= 0 && dy_on) ? ((int64_t)mx * a.Ny + j) * a.nD[2] + mz : -1;
+        Dn[1] = update_component<T, AT>(Dy0, CHy, ux, rx, uz, rz, uy, s, a.ICH[1], ic, a.ID[1], is);
     }
     {
-        const int64_t ic = (mz >= 0) ? ((int64_t)i * a.Ny + j) * a.nD[2] + mz : -1;
-        const int64_t is = (mx >= 0 && my >= 0) ? ((int64_t)mx * a.nD[1] + my) * a.Nz + k : -1;
-        Dn[2] = update_component<T, AT>((AT)a.Din[2][o], CHz, ux, rx, uy, ry, uz, s, a.ICH[2], ic, a.ID[2], is);
+        const int64_t ic = (mz >= 0 && dz_on) ? ((int64_t)i * a.Ny + j) * a.nD[2] + mz : -1;
+        const int64_t is = (mx >= 0 && my >= 0 && dz_on) ? ((int64_t)mx * a.nD[1] + my) * a.Nz + k : -1;
+        Dn[2] = update_component<T, AT>(Dz0, CHz, ux, rx, uy, ry, uz, s, a.ICH[2], ic, a.ID[2], is);
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
+        if (!((a.on >> c) & 1u)) continue;      // identically-zero component: nothing to read or write
         AT d = Dn[c];
         if (a.J[c]) {
             const AT sc = a.Jwave[c] ? (AT)(*a.Jwave[c]) : a.Jscale[c];

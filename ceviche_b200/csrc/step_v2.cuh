@@ -33,6 +33,14 @@ template <typename T, int V>
 __device__ __forceinline__ void stv(T* p, const Vec<T, V>& x) {
     *reinterpret_cast<Vec<T, V>*>(p) = x;
 }
+// load unless the component is known to be identically zero (kernel-uniform condition)
+template <typename T, int V>
+__device__ __forceinline__ Vec<T, V> ldv_if(bool on, const T* p) {
+    Vec<T, V> z;
+#pragma unroll
+    for (int e = 0; e < V; ++e) z.v[e] = T(0);
+    return on ? ldv<T, V>(p) : z;
+}
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -65,11 +73,12 @@ struct PmlCtx {
     int ic0, ic1;         // run offsets (or -1)
 
 #define CEV_TAB(a, name, ax) (IS_H ? (a).name##H[ax] : (a).name##D[ax])
-    __device__ __forceinline__ void load(const StepArgs<T, AT>& a, int i, int j, int k0, int mx, int my, const int* mz) {
+    __device__ __forceinline__ void load(const StepArgs<T, AT>& a, int i, int j, int k0, int mx, int my, const int* mz,
+                                         unsigned on3) {
         const int n1 = IS_H ? a.nH[1] : a.nD[1], n2 = IS_H ? a.nH[2] : a.nD[2];
         T* const* Ic = IS_H ? a.ICE : a.ICH;
-        ic0 = mx >= 0 ? (mx * a.Ny + j) * a.Nz + k0 : -1;      // Icurl_x (nCx,Ny,Nz)
-        ic1 = my >= 0 ? (i * n1 + my) * a.Nz + k0 : -1;        // Icurl_y (Nx,nCy,Nz)
+        ic0 = (mx >= 0 && (on3 & 1)) ? (mx * a.Ny + j) * a.Nz + k0 : -1;      // Icurl_x (nCx,Ny,Nz)
+        ic1 = (my >= 0 && (on3 & 2)) ? (i * n1 + my) * a.Nz + k0 : -1;        // Icurl_y (Nx,nCy,Nz)
 #ifdef CEV_EXP_NO_RMW
         ic0 = ic1 = -1;
 #endif
@@ -77,7 +86,7 @@ struct PmlCtx {
         if (ic1 >= 0) I1 = ldv<T, V>(Ic[1] + ic1);
 #pragma unroll
         for (int e = 0; e < V; ++e)
-            if (mz[e] >= 0) I2[e] = Ic[2][(i * a.Ny + j) * n2 + mz[e]];   // Icurl_z (Nx,Ny,nCz)
+            if (mz[e] >= 0 && (on3 & 4)) I2[e] = Ic[2][(i * a.Ny + j) * n2 + mz[e]];   // Icurl_z (Nx,Ny,nCz)
     }
 
     // pull the curl integrals of plane ip (a later iteration of this thread) into L2: without it they
@@ -97,7 +106,7 @@ struct PmlCtx {
 
     // old[c][e], curl[c][e] -> out[c].v[e]
     __device__ __forceinline__ void apply(const StepArgs<T, AT>& a, int i, int j, int k0, int mx, int my, const int* mz,
-                                          AT s, const Vec<T, V>* old, const AT (*curl)[V], Vec<T, V>* out) {
+                                          AT s, const Vec<T, V>* old, const AT (*curl)[V], Vec<T, V>* out, unsigned on3) {
         const int n1 = IS_H ? a.nH[1] : a.nD[1], n2 = IS_H ? a.nH[2] : a.nD[2];
         T* const* Ic = IS_H ? a.ICE : a.ICH;
         T* const* Is = IS_H ? a.IH : a.ID;
@@ -116,56 +125,56 @@ struct PmlCtx {
         for (int e = 0; e < V; ++e) {
             const int k = k0 + e;
             // x: (a,b) = (y,z), own x.   Iself_x (Nx,nCy,nCz)
-            {
+            if (on3 & 1) {
                 AT m1, m2;
                 coef12<AT>(uy, ry, uz[e], rz[e], s, m1, m2);
-                AT v = add_rn(mul_rn(m1, (AT)old[0].v[e]), mul_rn(m2, curl[0][e]));
+                AT v = muladd(m1, (AT)old[0].v[e], mul_rn(m2, curl[0][e]));
                 if (ic0 >= 0) {
                     const AT I = (AT)I0.v[e] + curl[0][e];
                     n0.v[e] = (T)I;
-                    v = add_rn(v, mul_rn(mul_rn(mul_rn(s, ux + ux), mul_rn(ry, rz[e])), I));
+                    v = muladd(mul_rn(mul_rn(s, ux + ux), mul_rn(ry, rz[e])), I, v);
                 }
                 if (my >= 0 && mz[e] >= 0) {
                     T* q = Is[0] + (i * n1 + my) * n2 + mz[e];
                     const AT I = (AT)*q + (AT)old[0].v[e];
                     *q = (T)I;
-                    v = add_rn(v, mul_rn(mul_rn(mul_rn(mul_rn(AT(-4), uy), uz[e]), mul_rn(ry, rz[e])), I));
+                    v = muladd(mul_rn(mul_rn(mul_rn(AT(-4), uy), uz[e]), mul_rn(ry, rz[e])), I, v);
                 }
                 out[0].v[e] = (T)v;
             }
             // y: (a,b) = (x,z), own y.   Iself_y (nCx,Ny,nCz)
-            {
+            if (on3 & 2) {
                 AT m1, m2;
                 coef12<AT>(ux, rx, uz[e], rz[e], s, m1, m2);
-                AT v = add_rn(mul_rn(m1, (AT)old[1].v[e]), mul_rn(m2, curl[1][e]));
+                AT v = muladd(m1, (AT)old[1].v[e], mul_rn(m2, curl[1][e]));
                 if (ic1 >= 0) {
                     const AT I = (AT)I1.v[e] + curl[1][e];
                     n1v.v[e] = (T)I;
-                    v = add_rn(v, mul_rn(mul_rn(mul_rn(s, uy + uy), mul_rn(rx, rz[e])), I));
+                    v = muladd(mul_rn(mul_rn(s, uy + uy), mul_rn(rx, rz[e])), I, v);
                 }
                 if (mx >= 0 && mz[e] >= 0) {
                     T* q = Is[1] + (mx * a.Ny + j) * n2 + mz[e];
                     const AT I = (AT)*q + (AT)old[1].v[e];
                     *q = (T)I;
-                    v = add_rn(v, mul_rn(mul_rn(mul_rn(mul_rn(AT(-4), ux), uz[e]), mul_rn(rx, rz[e])), I));
+                    v = muladd(mul_rn(mul_rn(mul_rn(AT(-4), ux), uz[e]), mul_rn(rx, rz[e])), I, v);
                 }
                 out[1].v[e] = (T)v;
             }
             // z: (a,b) = (x,y), own z.   Iself_z (nCx,nCy,Nz)
-            {
+            if (on3 & 4) {
                 AT m1, m2;
                 coef12<AT>(ux, rx, uy, ry, s, m1, m2);
-                AT v = add_rn(mul_rn(m1, (AT)old[2].v[e]), mul_rn(m2, curl[2][e]));
-                if (mz[e] >= 0) {
+                AT v = muladd(m1, (AT)old[2].v[e], mul_rn(m2, curl[2][e]));
+                if (mz[e] >= 0) {   // (on3 & 4 holds here)
                     const AT I = (AT)I2[e] + curl[2][e];
                     Ic[2][(i * a.Ny + j) * n2 + mz[e]] = (T)I;
-                    v = add_rn(v, mul_rn(mul_rn(mul_rn(s, uz[e] + uz[e]), mul_rn(rx, ry)), I));
+                    v = muladd(mul_rn(mul_rn(s, uz[e] + uz[e]), mul_rn(rx, ry)), I, v);
                 }
                 if (mx >= 0 && my >= 0) {
                     T* q = Is[2] + (mx * n1 + my) * a.Nz + k;
                     const AT I = (AT)*q + (AT)old[2].v[e];
                     *q = (T)I;
-                    v = add_rn(v, mul_rn(mul_rn(mul_rn(mul_rn(AT(-4), ux), uy), mul_rn(rx, ry)), I));
+                    v = muladd(mul_rn(mul_rn(mul_rn(AT(-4), ux), uy), mul_rn(rx, ry)), I, v);
                 }
                 out[2].v[e] = (T)v;
             }
@@ -226,6 +235,7 @@ k_step_H_v2(const StepArgs<T, AT> a) {
     }
     const AT s = -a.cdt;
     const AT inv = a.inv_dL;
+    const unsigned onE = a.on & 7u, onH = (a.on >> 3) & 7u;
 
     // E = mE*D of the current plane (own cells)
     AT Ecur[3][V];
@@ -233,7 +243,8 @@ k_step_H_v2(const StepArgs<T, AT> a) {
         const int o = xs * plane + orow;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const Vec<T, V> d = ldv<T, V>(a.Din[c] + o), m = ldv<T, V>(a.mE[c] + o);
+            const bool oc = (onE >> c) & 1u;
+            const Vec<T, V> d = ldv_if<T, V>(oc, a.Din[c] + o), m = ldv_if<T, V>(oc, a.mE[c] + o);
 #pragma unroll
             for (int e = 0; e < V; ++e) Ecur[c][e] = mul_rn((AT)m.v[e], (AT)d.v[e]);
         }
@@ -248,17 +259,17 @@ k_step_H_v2(const StepArgs<T, AT> a) {
         for (int c = 0; c < 3; ++c) {
             const T* Dn = last ? a.Dhi[c] : a.Din[c] + pbase + plane;
             const T* Mn = last ? a.mEhi[c] : a.mE[c] + pbase + plane;
-            dn[c] = ldv<T, V>(Dn + orow);
-            mn[c] = ldv<T, V>(Mn + orow);
-            h[c] = ldv<T, V>(a.Hin[c] + pbase + orow);
+            dn[c] = ldv_if<T, V>((onE >> c) & 1u, Dn + orow);
+            mn[c] = ldv_if<T, V>((onE >> c) & 1u, Mn + orow);
+            h[c] = ldv_if<T, V>((onH >> c) & 1u, a.Hin[c] + pbase + orow);
         }
-        const Vec<T, V> dxj = ldv<T, V>(a.Din[0] + pbase + orow_jp), mxj = ldv<T, V>(a.mE[0] + pbase + orow_jp);
-        const Vec<T, V> dzj = ldv<T, V>(a.Din[2] + pbase + orow_jp), mzj = ldv<T, V>(a.mE[2] + pbase + orow_jp);
+        const Vec<T, V> dxj = ldv_if<T, V>(onE & 1u, a.Din[0] + pbase + orow_jp), mxj = ldv_if<T, V>(onE & 1u, a.mE[0] + pbase + orow_jp);
+        const Vec<T, V> dzj = ldv_if<T, V>(onE & 4u, a.Din[2] + pbase + orow_jp), mzj = ldv_if<T, V>(onE & 4u, a.mE[2] + pbase + orow_jp);
         AT ex_kp = __shfl_down_sync(0xffffffffu, Ecur[0][0], 1);
         AT ey_kp = __shfl_down_sync(0xffffffffu, Ecur[1][0], 1);
         if (z_edge) {
-            ex_kp = mul_rn((AT)a.mE[0][pbase + okp], (AT)a.Din[0][pbase + okp]);
-            ey_kp = mul_rn((AT)a.mE[1][pbase + okp], (AT)a.Din[1][pbase + okp]);
+            if (onE & 1u) ex_kp = mul_rn((AT)a.mE[0][pbase + okp], (AT)a.Din[0][pbase + okp]);
+            if (onE & 2u) ey_kp = mul_rn((AT)a.mE[1][pbase + okp], (AT)a.Din[1][pbase + okp]);
         }
         if (a.pf_dist > 0 && i + a.pf_dist < a.x1) {   // next plane(s) of every stream into L2, also across the chunk end
             const int ip = i + a.pf_dist;
@@ -266,8 +277,8 @@ k_step_H_v2(const StepArgs<T, AT> a) {
                 const int po = ip * plane + orow;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    prefetch_l2(a.Hin[c] + po);
-                    if (ip + 1 < a.Nx) {
+                    if ((onH >> c) & 1u) prefetch_l2(a.Hin[c] + po);
+                    if (ip + 1 < a.Nx && ((onE >> c) & 1u)) {
                         prefetch_l2(a.Din[c] + po + plane);
                         prefetch_l2(a.mE[c] + po + plane);
                     }
@@ -282,7 +293,7 @@ k_step_H_v2(const StepArgs<T, AT> a) {
         const bool pml = !INTERIOR && (yz_pml || mx >= 0);
 #endif
         PmlCtx<T, AT, V, true> ctx;
-        if (pml) ctx.load(a, i, j, k0, mx, my, mz);
+        if (pml) ctx.load(a, i, j, k0, mx, my, mz, onH);
 
         // ---- curls (consume the neighbour loads); E of the next plane becomes current
         AT CE[3][V];
@@ -314,12 +325,13 @@ k_step_H_v2(const StepArgs<T, AT> a) {
                 for (int c = 0; c < 3; ++c)
 #pragma unroll
                     for (int e = 0; e < V; ++e)   // m1 = 1, m2 = -C0 dt: exactly what the general formula gives off the PML
-                        out[c].v[e] = (T)add_rn((AT)h[c].v[e], mul_rn(s, CE[c][e]));
+                        out[c].v[e] = (T)muladd(s, CE[c][e], (AT)h[c].v[e]);
             } else {
-                ctx.apply(a, i, j, k0, mx, my, mz, s, h, CE, out);
+                ctx.apply(a, i, j, k0, mx, my, mz, s, h, CE, out, onH);
             }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) stv<T, V>(a.Hout[c] + pbase + orow, out[c]);
+            for (int c = 0; c < 3; ++c)
+                if ((onH >> c) & 1u) stv<T, V>(a.Hout[c] + pbase + orow, out[c]);
         }
     }
 }
@@ -373,13 +385,14 @@ __global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS :
     }
     const AT s = a.cdt;
     const AT inv = a.inv_dL;
+    const unsigned onE = a.on & 7u, onH = (a.on >> 3) & 7u;
 
     // H of the previous plane (own cells), y and z components
     AT Hprev[2][V];
     {
         const T* P1 = (xs > 0) ? a.Hin[1] + (xs - 1) * plane : a.Hlo[1];
         const T* P2 = (xs > 0) ? a.Hin[2] + (xs - 1) * plane : a.Hlo[2];
-        const Vec<T, V> p1 = ldv<T, V>(P1 + orow), p2 = ldv<T, V>(P2 + orow);
+        const Vec<T, V> p1 = ldv_if<T, V>(onH & 2u, P1 + orow), p2 = ldv_if<T, V>(onH & 4u, P2 + orow);
 #pragma unroll
         for (int e = 0; e < V; ++e) {
             Hprev[0][e] = (AT)p1.v[e];
@@ -392,17 +405,17 @@ __global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS :
         Vec<T, V> h[3], d[3], jv[3], mev[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            h[c] = ldv<T, V>(a.Hin[c] + pbase + orow);
-            d[c] = ldv<T, V>(a.Din[c] + pbase + orow);
+            h[c] = ldv_if<T, V>((onH >> c) & 1u, a.Hin[c] + pbase + orow);
+            d[c] = ldv_if<T, V>((onE >> c) & 1u, a.Din[c] + pbase + orow);
             if (EXTRAS && a.J[c]) jv[c] = ldv<T, V>(a.J[c] + pbase + orow);
             if (EXTRAS && a.Eout[c]) mev[c] = ldv<T, V>(a.mE[c] + pbase + orow);
         }
-        const Vec<T, V> hxj = ldv<T, V>(a.Hin[0] + pbase + orow_jm), hzj = ldv<T, V>(a.Hin[2] + pbase + orow_jm);
+        const Vec<T, V> hxj = ldv_if<T, V>(onH & 1u, a.Hin[0] + pbase + orow_jm), hzj = ldv_if<T, V>(onH & 4u, a.Hin[2] + pbase + orow_jm);
         AT hx_km = __shfl_up_sync(0xffffffffu, (AT)h[0].v[V - 1], 1);
         AT hy_km = __shfl_up_sync(0xffffffffu, (AT)h[1].v[V - 1], 1);
         if (z_edge) {
-            hx_km = (AT)a.Hin[0][pbase + okm];
-            hy_km = (AT)a.Hin[1][pbase + okm];
+            if (onH & 1u) hx_km = (AT)a.Hin[0][pbase + okm];
+            if (onH & 2u) hy_km = (AT)a.Hin[1][pbase + okm];
         }
         if (a.pf_dist > 0 && i + a.pf_dist < a.x1) {
             const int ip = i + a.pf_dist;
@@ -410,8 +423,8 @@ __global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS :
                 const int po = ip * plane + orow;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    prefetch_l2(a.Hin[c] + po);
-                    prefetch_l2(a.Din[c] + po);
+                    if ((onH >> c) & 1u) prefetch_l2(a.Hin[c] + po);
+                    if ((onE >> c) & 1u) prefetch_l2(a.Din[c] + po);
                 }
             }
             if (!INTERIOR) PmlCtx<T, AT, V, false>::prefetch(a, ip, j, k0, my, mz, (lz & 7) == 0);
@@ -423,7 +436,7 @@ __global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS :
         const bool pml = !INTERIOR && (yz_pml || mx >= 0);
 #endif
         PmlCtx<T, AT, V, false> ctx;
-        if (pml) ctx.load(a, i, j, k0, mx, my, mz);
+        if (pml) ctx.load(a, i, j, k0, mx, my, mz, onE);
 
         AT CH[3][V];
 #pragma unroll
@@ -444,9 +457,9 @@ __global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS :
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
 #pragma unroll
-                    for (int e = 0; e < V; ++e) out[c].v[e] = (T)add_rn((AT)d[c].v[e], mul_rn(s, CH[c][e]));
+                    for (int e = 0; e < V; ++e) out[c].v[e] = (T)muladd(s, CH[c][e], (AT)d[c].v[e]);
             } else {
-                ctx.apply(a, i, j, k0, mx, my, mz, s, d, CH, out);
+                ctx.apply(a, i, j, k0, mx, my, mz, s, d, CH, out, onE);
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -462,7 +475,7 @@ __global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS :
                     }
                     if (a.Eout[c]) stv<T, V>(a.Eout[c] + pbase + orow, eo);
                 }
-                stv<T, V>(a.Dout[c] + pbase + orow, out[c]);
+                if ((onE >> c) & 1u) stv<T, V>(a.Dout[c] + pbase + orow, out[c]);
             }
         }
     }

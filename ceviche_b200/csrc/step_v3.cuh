@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(32 * V3_BY) k_step_H_v3(const StepArgs<T, AT> 
         const int mx = a.mapH[0][i];
         const bool pml = yz_pml || mx >= 0;
         PmlCtx<T, AT, V, true> ctx;
-        if (pml && active) ctx.load(a, i, j, k0, mx, my, mz);
+        if (pml && active) ctx.load(a, i, j, k0, mx, my, mz, 7u);
         if (active && i + 1 < a.x1) PmlCtx<T, AT, V, true>::prefetch(a, i + 1, j, k0, my, mz, (lane & 7) == 0);
         mbar_wait(&full[q % NS], (q / NS) & 1);
         mbar_wait(&full[(q + 1) % NS], ((q + 1) / NS) & 1);
@@ -246,9 +246,9 @@ __global__ void __launch_bounds__(32 * V3_BY) k_step_H_v3(const StepArgs<T, AT> 
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
 #pragma unroll
-                    for (int e = 0; e < V; ++e) out[c].v[e] = (T)add_rn((AT)h[c].v[e], mul_rn(s, CE[c][e]));
+                    for (int e = 0; e < V; ++e) out[c].v[e] = (T)muladd(s, CE[c][e], (AT)h[c].v[e]);
             } else {
-                ctx.apply(a, i, j, k0, mx, my, mz, s, h, CE, out);
+                ctx.apply(a, i, j, k0, mx, my, mz, s, h, CE, out, 7u);
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) stv<T, V>(a.Hout[c] + pbase + orow, out[c]);
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(32 * V3_BY) k_step_D_v3(const StepArgs<T, AT> 
         const int mx = a.mapD[0][i];
         const bool pml = yz_pml || mx >= 0;
         PmlCtx<T, AT, V, false> ctx;
-        if (pml && active) ctx.load(a, i, j, k0, mx, my, mz);
+        if (pml && active) ctx.load(a, i, j, k0, mx, my, mz, 7u);
         if (active && i + 1 < a.x1) PmlCtx<T, AT, V, false>::prefetch(a, i + 1, j, k0, my, mz, (lane & 7) == 0);
         mbar_wait(&full[q % NS], (q / NS) & 1);
         mbar_wait(&full[(q + 1) % NS], ((q + 1) / NS) & 1);
@@ -386,9 +386,9 @@ __global__ void __launch_bounds__(32 * V3_BY) k_step_D_v3(const StepArgs<T, AT> 
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
 #pragma unroll
-                    for (int e = 0; e < V; ++e) out[c].v[e] = (T)add_rn((AT)d[c].v[e], mul_rn(s, CH[c][e]));
+                    for (int e = 0; e < V; ++e) out[c].v[e] = (T)muladd(s, CH[c][e], (AT)d[c].v[e]);
             } else {
-                ctx.apply(a, i, j, k0, mx, my, mz, s, d, CH, out);
+                ctx.apply(a, i, j, k0, mx, my, mz, s, d, CH, out, 7u);
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) stv<T, V>(a.Dout[c] + pbase + orow, out[c]);

@@ -53,6 +53,26 @@ def sigma_profiles(shape, npml, dt):
     return sH, sD
 
 
+def coupled_components(shape, mask):
+    """Closure of a 6-bit component mask (bits 0-2: D/E x,y,z; bits 3-5: H x,y,z) under the curl
+    couplings of ceviche/derivatives.py:16-30.  A periodic difference along an axis of extent 1 is
+    identically zero, so on 2-D / 1-D grids the step splits into uncoupled polarisations
+    (Nz = 1: TM = {Ez, Hx, Hy}, TE = {Ex, Ey, Hz}); on a full 3-D grid any source reaches all six."""
+    live = [n > 1 for n in shape]
+    # H_c is driven by E_a through d/d(b) and by E_b through d/d(a), with (a, b) the other two axes
+    # (and D_c by H_a, H_b the same way)
+    while True:
+        new = mask
+        for c in range(3):
+            a, b = (c + 1) % 3, (c + 2) % 3
+            for src, dst in ((0, 3), (3, 0)):
+                if ((mask >> (src + a)) & 1 and live[b]) or ((mask >> (src + b)) & 1 and live[a]):
+                    new |= 1 << (dst + c)
+        if new == mask:
+            return mask
+        mask = new
+
+
 def _ptr(t):
     return None if t is None or t.numel() == 0 else t.data_ptr()
 
@@ -110,6 +130,8 @@ class fdtd:
         self.arith_f64 = True if dtype == torch.float64 else (arith in ("f64", torch.float64))
         self._options = {}
         self._plan = None
+        # skip field components that are provably zero (2-D TM / TE, 1-D): see coupled_components()
+        self.specialise_components = True
 
         eps_r = self._as_eps(eps_r, pad=True)
         self.Nx, self.Ny, self.Nz = self.grid_shape = tuple(eps_r.shape)
@@ -204,6 +226,7 @@ class fdtd:
             for name, value in self._options.items():
                 _lib.check(self._plan.lib.cev_fdtd_set_option(self._plan.handle, name.encode(), int(value)))
             self._n_sources = self._n_probes = self._n_slots = 0
+            self._source_mask = 0
             self._slot_fold = None
         return self._plan
 
@@ -213,6 +236,17 @@ class fdtd:
         if self._plan is not None:
             _lib.check(self._plan.lib.cev_fdtd_set_option(self._plan.handle, name.encode(), int(value)))
 
+    def _drive(self, d_mask):
+        """Record that the D components in `d_mask` (bits 0-2) are being driven and tell the plan which
+        components can be non-zero from now on (the in-place kernels skip the others entirely)."""
+        self._active = coupled_components(self.grid_shape, self._active | int(d_mask))
+        self._apply_active(self._active)
+
+    def _apply_active(self, mask):
+        mask = int(mask) if self.specialise_components else 63
+        if self._options.get("active_components", 63) != mask:
+            self.set_option("active_components", mask)
+
     def _alloc_pml(self):
         shapes = self._plan.pml_shapes
         z = lambda s: torch.zeros(s, dtype=self.dtype, device=self.device)
@@ -221,6 +255,7 @@ class fdtd:
     def initialize_fields(self):
         """fdtd.py:147-211: zero state, t_index = 0, a NEW fields dict."""
         self.t_index = 0
+        self._active = 0            # components that may be non-zero (bits 0-2 D/E, 3-5 H)
         z = lambda: [torch.zeros(self.grid_shape, dtype=self.dtype, device=self.device) for _ in range(3)]
         self._H, self._D, self._E = z(), z(), z()
         if self._plan is not None:
@@ -286,6 +321,7 @@ class fdtd:
         plan = self._ensure_plan()
         self.t_index += 1
         J = [self._as_J(j) for j in (Jx, Jy, Jz)]
+        self._drive(sum(1 << c for c in range(3) if J[c] is not None))
         if autodiff.needs_grad(self, J):
             self._H, self._D, self._E, self._pml = autodiff.step(self, J)
             self._publish()
@@ -334,6 +370,7 @@ class fdtd:
         with torch.cuda.device(self.device):
             _lib.check(plan.lib.cev_fdtd_set_sources(plan.handle, len(sources), pts))
         self._n_sources = len(sources)
+        self._source_mask = sum({1 << _COMP[comp] for comp, _ in sources})
 
     def set_probes(self, probes):
         """probes: [(field key 'Ex'..'Hz', mask array)].  series[t, p] = sum(field_p * mask_p)."""
@@ -385,6 +422,7 @@ class fdtd:
         waveforms = waveforms.to(device=self.device, dtype=torch.float64).contiguous()
         if tuple(waveforms.shape) != (steps, n_src):
             raise ValueError("waveforms must have shape (steps, n_sources) = {}".format((steps, n_src)))
+        self._drive(self._source_mask)
         return waveforms
 
     def run(self, steps, sources=None, probes=None, waveforms=None, checkpoint_every=None):

@@ -110,7 +110,10 @@ int cev_fdtd_destroy(cev_fdtd* plan);
 /* Tuning / test knobs: "kernel_variant" 0 auto | 1 baseline (one thread per cell) | 2 marching;
  * "xchunk" x-planes per CTA of the marching kernels (0 = auto); "lanes_z" 8|16|32 lanes of a warp along z;
  * "prefetch_planes" L2 prefetch distance; "split_launch" 0|1 separate launches for the PML-free interior and
- * the PML shell.  Results do not depend on them (bit-identical). */
+ * the PML shell.  Results do not depend on them (bit-identical).
+ * "active_components": 6-bit mask (bits 0-2: D/E x,y,z; bits 3-5: H x,y,z) of the components that may be non-zero;
+ * the kernels neither read nor write the others (2-D TM / TE runs move 10-11 instead of 21 words per cell).  The
+ * caller guarantees that the masked-out components are identically zero and are not driven. */
 int cev_fdtd_set_option(cev_fdtd* plan, const char* name, int64_t value);
 
 /* Logical shapes of the 12 compact PML integral arrays, order ICE[3], IH[3], ICH[3], ID[3]. */

@@ -94,3 +94,76 @@ def test_marching_against_oracle_midsize():
     series32, fields32, _ = _run(case, torch.float32, 2)
     for k in FIELD_KEYS:
         assert rel_l2(fields32[k], O.fields()[k]) <= 1e-5, k
+
+
+# ---- provably-zero components skipped on 2-D / 1-D grids (active_components)
+def _polarised_case(shape, npml, comp, steps=120, seed=4):
+    rng = np.random.default_rng(seed)
+    eps = 1 + 3 * rng.random(shape)
+    mid = tuple(n // 2 for n in shape)
+    src = [(comp, cases.one_hot(shape, mid, 3.0), cases.modulated(steps, steps / 3, steps / 8, 9.0, 2.0)),
+           (comp, rng.random(shape) * (rng.random(shape) < 0.05), cases.gaussian(steps, steps / 4, steps / 10))]
+    probes = [(k, rng.random(shape)) for k in ("Ex", "Ey", "Ez", "Hx", "Hy", "Hz", "Dz")]
+    return dict(eps=eps, dL=cases.DL, npml=list(npml), steps=steps, sources=src, probes=probes)
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("shape,npml,comp,expect", [
+    ((48, 64, 1), (5, 6, 0), "z", 0b011100),      # TM: Ez, Hx, Hy
+    ((48, 64, 1), (5, 6, 0), "x", 0b100011),      # TE: Ex, Ey, Hz
+    ((48, 64, 1), (5, 6, 0), "y", 0b100011),
+    ((33, 17, 1), (4, 3, 0), "z", 0b011100),      # odd contiguous extent: baseline kernels
+    ((96, 1, 1), (8, 0, 0), "z", 0b010100),       # 1-D: Ez, Hy
+    ((1, 24, 40), (0, 3, 4), "x", 0b110001),      # Nx = 1: Ex, Hy, Hz
+    ((12, 10, 16), (2, 2, 3), "z", 0b111111),     # 3-D: everything couples
+])
+def test_component_specialisation_is_exact(shape, npml, comp, expect, dtype):
+    import ceviche_b200
+    case = _polarised_case(shape, npml, comp)
+    out = []
+    for spec in (False, True):
+        F = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"], dtype=dtype)
+        F.specialise_components = spec
+        series = F.run(case["steps"], case["sources"], case["probes"]).cpu().numpy()
+        if spec:
+            assert F._active == expect and F._options.get("active_components", 63) == expect
+        # a second leg through the same object: the mask must persist / widen correctly
+        series2 = F.run(30, [(c, p, w[:30]) for c, p, w in case["sources"]], case["probes"]).cpu().numpy()
+        out.append((series, series2, {k: F.fields[k].cpu().numpy() for k in FIELD_KEYS},
+                    [t.cpu().numpy() for fam in ("ICE", "IH", "ICH", "ID") for t in F._pml[fam]]))
+    (s0, t0, f0, p0), (s1, t1, f1, p1) = out
+    assert np.array_equal(s0, s1) and np.array_equal(t0, t1)
+    for k in FIELD_KEYS:
+        assert np.array_equal(f0[k], f1[k]), k
+    for a, b in zip(p0, p1):
+        assert np.array_equal(a, b)
+    if dtype == torch.float64:
+        O = OracleFDTD(case["eps"], case["dL"], case["npml"])
+        o_series, _ = O.run(case["steps"], case["sources"], case["probes"])
+        for p in range(s1.shape[1]):
+            assert rel_l2(s1[:, p], o_series[:, p]) <= 1e-10
+
+
+def test_component_mask_widens_when_a_new_polarisation_is_driven():
+    """TM run, then a TE source on the same object, then the per-step API: the skipped set must shrink."""
+    import ceviche_b200
+    shape, npml = (40, 48, 1), (4, 5, 0)
+    rng = np.random.default_rng(8)
+    eps = 1 + rng.random(shape)
+    pz, px = cases.one_hot(shape, (20, 24, 0)), cases.one_hot(shape, (11, 30, 0))
+    w = cases.gaussian(50, 20, 6)
+    res = []
+    for spec in (False, True):
+        F = ceviche_b200.fdtd(eps, cases.DL, npml)
+        F.specialise_components = spec
+        F.run(50, [("z", pz, w)], [])
+        a1 = F._active
+        F.run(50, [("x", px, w)], [])
+        a2 = F._active
+        F.forward(Jy=torch.as_tensor(px).cuda() * 0.3)
+        res.append({k: F.fields[k].cpu().numpy() for k in FIELD_KEYS})
+        if spec:
+            assert (a1, a2) == (0b011100, 0b111111)
+    for k in FIELD_KEYS:
+        assert np.array_equal(res[0][k], res[1][k]), k
+    assert all(np.abs(res[1][k]).max() > 0 for k in FIELD_KEYS)

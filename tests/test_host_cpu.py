@@ -82,3 +82,25 @@ def test_spectrum_helpers_match_numpy_formulas():
     np.testing.assert_allclose(freqs.numpy(), np.fft.fftfreq(64, d=dt))
     f2, pw = utils.get_spectral_power(series[:, 0], dt)
     np.testing.assert_allclose(pw.numpy()[:, 0], np.abs(ref[:, 0]) ** 2, rtol=1e-12)
+
+
+def test_coupled_components_closure():
+    """Which field components a source can reach (curl couplings of ceviche/derivatives.py:16-30 on
+    grids with singleton axes), checked against what the numpy oracle actually produces."""
+    from ceviche_b200.fdtd import coupled_components
+    assert coupled_components((200, 200, 1), 0b100) == 0b011100      # TM: Ez, Hx, Hy
+    assert coupled_components((200, 200, 1), 0b001) == 0b100011      # TE: Ex, Ey, Hz
+    assert coupled_components((64, 1, 1), 0b100) == 0b010100
+    assert coupled_components((64, 1, 1), 0b001) == 0b000001
+    assert coupled_components((8, 8, 8), 0b010) == 0b111111
+    assert coupled_components((8, 8, 8), 0) == 0
+    for shape in ((7, 6, 1), (9, 1, 1), (1, 6, 5), (1, 1, 8), (5, 1, 4), (4, 3, 5)):
+        for c, comp in enumerate("xyz"):
+            prof = np.zeros(shape)
+            prof[tuple(n // 2 for n in shape)] = 1.0
+            O = onp.OracleFDTD(1 + np.random.default_rng(1).random(shape), 5e-8, [0, 0, 0])
+            O.run(12, [(comp, prof, np.ones(12))], [])
+            f = O.fields()
+            seen = sum(1 << q for q, n in enumerate("xyz") if np.any(f["D" + n])) | \
+                sum(8 << q for q, n in enumerate("xyz") if np.any(f["H" + n]))
+            assert seen == coupled_components(shape, 1 << c), (shape, comp)
