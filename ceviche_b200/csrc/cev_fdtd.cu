@@ -18,6 +18,7 @@
 #include "step_v1.cuh"
 #include "step_v2.cuh"
 #include "step_v3.cuh"
+#include "step_v4.cuh"
 #include "adjoint.cuh"
 
 namespace {
@@ -73,7 +74,9 @@ struct cev_fdtd {
     int N[3] = {0, 0, 0};        // internal extents
     double dL = 0, dt = 0, cdt = 0;
     int nH[3] = {0, 0, 0}, nD[3] = {0, 0, 0};   // internal compact counts
-    int variant = 0;             // 0 auto, 1 baseline kernels, 2 marching kernels, 3 TMA-staged marching kernels
+    int variant = 0;             // 0 auto, 1 baseline kernels, 2 marching kernels, 3 TMA-staged marching kernels,
+                                 // 4 fused full-step kernel wherever it applies (cev_fdtd_run_fused)
+    int fused_shape = 0;         // tile shape of the fused kernel: 0 auto, else LZ*100 + BY
     int xchunk = 0;              // 0 auto
     int pf_dist = 1;             // L2 prefetch distance of the marching kernels (planes)
     int lz = 8;                  // lanes of a warp along z in the marching kernels (8, 16 or 32)
@@ -96,7 +99,7 @@ struct cev_fdtd {
     std::vector<int64_t> h_src_cell;
     std::vector<double> h_src_w;
     struct SrcTiling {                              // source points sorted by owning CTA of one launch geometry
-        int x0, x1, xchunk, lz, vec, part;
+        int x0, x1, xchunk, lz, vec, part, rows;
         DeviceBuf begin, comp, id, cell, w;
     };
     std::vector<std::unique_ptr<SrcTiling>> src_tilings;
@@ -302,14 +305,17 @@ bool want_split(const cev_fdtd* p, int64_t x0, int64_t x1) {
 template <typename T, typename AT>
 int attach_sources_v2(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row, int part, int lz_override = 0,
                       int rows_override = 0) {
+    // lz_override < 0: fused kernel, a CTA owns rows_override rows x (-lz_override) vectors
     constexpr int V = vec_width<T>();
     const int LZ = lz_override ? lz_override : p->lz;
     cev_fdtd::SrcTiling* hit = nullptr;
+    const int rows = rows_override ? rows_override : V2_BY * (32 / LZ);
     for (auto& t : p->src_tilings)
-        if (t->x0 == a.x0 && t->x1 == a.x1 && t->xchunk == a.xchunk && t->lz == LZ && t->vec == V && t->part == part)
+        if (t->x0 == a.x0 && t->x1 == a.x1 && t->xchunk == a.xchunk && t->lz == LZ && t->vec == V && t->part == part &&
+            t->rows == rows)
             hit = t.get();
     if (!hit) {
-        const int rows = rows_override ? rows_override : V2_BY * (32 / LZ);
+        const int zcells = (LZ < 0 ? -LZ : LZ) * V;
         const int64_t plane = (int64_t)a.Ny * a.Nz;
         std::vector<int> owner;
         std::vector<int64_t> pick;
@@ -319,7 +325,7 @@ int attach_sources_v2(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row, i
             for (int b = 0; b < a.n_boxes; ++b) {
                 const Box& B = a.box[b];
                 if (i < B.x0 || i >= B.x1 || j < B.y0 || j >= B.y1 || k < B.z0 || k >= B.z1) continue;
-                owner.push_back(B.cta0 + (((i - B.x0) / a.xchunk) * B.nty + (j - B.y0) / rows) * B.ntz + (k - B.z0) / (LZ * V));
+                owner.push_back(B.cta0 + (((i - B.x0) / a.xchunk) * B.nty + (j - B.y0) / rows) * B.ntz + (k - B.z0) / zcells);
                 pick.push_back(q);
                 break;
             }
@@ -341,7 +347,7 @@ int attach_sources_v2(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row, i
         }
         for (int b = 0; b < a.n_tiles; ++b) begin[b + 1] += begin[b];
         std::unique_ptr<cev_fdtd::SrcTiling> t(new cev_fdtd::SrcTiling());
-        t->x0 = a.x0; t->x1 = a.x1; t->xchunk = a.xchunk; t->lz = LZ; t->vec = V; t->part = part;
+        t->x0 = a.x0; t->x1 = a.x1; t->xchunk = a.xchunk; t->lz = LZ; t->vec = V; t->part = part; t->rows = rows;
         const size_t mm = (size_t)(m > 0 ? m : 1);
         if (t->begin.alloc(begin.size() * 4) || t->comp.alloc(mm * 4) || t->id.alloc(mm * 4) || t->cell.alloc(mm * 4) ||
             t->w.alloc(mm * 8))
@@ -480,7 +486,7 @@ int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const
     if (extras) a.on = 63u;
     // auto: the TMA-staged D kernel wins in fp64 (measured, scripts/tune.py); fp32 and the H half-step stay on the
     // register-marching kernels
-    if ((p->variant == 3 || (p->variant == 0 && sizeof(T) == 8 && x1 - x0 >= 4)) && !extras && a.on == 63u) {
+    if ((p->variant == 3 || ((p->variant == 0 || p->variant == 4) && sizeof(T) == 8 && x1 - x0 >= 4)) && !extras && a.on == 63u) {
         set_tiles_v3(p, a, x0, x1);
         if (inject && attach_sources_v2(p, a, wave_row, 0, 32, V3_BY)) return -1;
         const int aux = attach_probes(p, a, 1, probe_t, partials);
@@ -613,6 +619,133 @@ int jvp_loop(cev_fdtd* p, const cev_state* st, int B, const cev_state* tst, cons
         if (launch_probe_only<T, AT>(p, st, nullptr, 0, nsteps - 1, partials, s)) return -1;
         for (int b = 0; b < B; ++b)
             if (launch_probe_only<T, AT>(p, &tst[b], &tan[b], 0, nsteps - 1, tpartials ? tpartials + b * stride : nullptr, s)) return -1;
+    }
+    return 0;
+}
+
+
+// ---- fused full-step kernel (step_v4.cuh): one launch per time step, state ping-ponged between `in` and `out`
+template <typename T, typename AT>
+bool can_fuse(const cev_fdtd* p, const StepArgs<T, AT>& a) {
+    constexpr int V = vec_width<T>();
+    if (p->on != 63u || a.dmE[0]) return false;
+    if (a.Nz % V != 0 || a.Nz / V < 2) return false;
+    auto ok = [](const void* q) { return q == nullptr || ((uintptr_t)q % 16) == 0; };
+    for (int c = 0; c < 3; ++c)
+        if (!ok(a.Hin[c]) || !ok(a.Hout[c]) || !ok(a.Din[c]) || !ok(a.Dout[c]) || !ok(a.mE[c]) || !ok(a.ICE[c]) ||
+            !ok(a.ICEout[c]) || !ok(a.ICH[c]))
+            return false;
+    return true;
+}
+
+template <typename T, typename AT, int LZ, int BY>
+int launch_fused_shape(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row, int n_aux_slots, int64_t probe_t,
+                       double* partials, cudaStream_t s) {
+    constexpr int V = vec_width<T>();
+    constexpr int OY = BY * (32 / LZ) - 1, OZ = LZ - 1;
+    a.x0 = 0;
+    a.x1 = a.Nx;
+    int chunk = p->xchunk > 0 ? p->xchunk : 16;   // the pre-roll plane costs 1/chunk extra H work
+    a.xchunk = chunk;
+    a.pf_dist = p->pf_dist;
+    a.ntz = (a.Nz / V + OZ - 1) / OZ;
+    a.nty = (a.Ny + OY - 1) / OY;
+    a.n_tiles = a.ntz * a.nty * ((a.Nx + chunk - 1) / chunk);
+    a.n_boxes = 1;
+    Box& B = a.box[0];
+    B.x0 = 0; B.x1 = a.Nx; B.y0 = 0; B.y1 = a.Ny; B.z0 = 0; B.z1 = a.Nz;
+    B.cta0 = 0; B.ntz = a.ntz; B.nty = a.nty;
+    if (wave_row && p->n_src_pts > 0 && attach_sources_v2(p, a, wave_row, 4, -OZ, OY)) return -1;
+    int aux = 0;
+    if (probe_t >= 0 && partials && n_aux_slots > 0) {
+        a.aux_slot0 = 0;
+        a.t_probe = probe_t;
+        a.partials = partials;
+        aux = n_aux_slots;
+    }
+    k_step_fused<T, AT, V, LZ, BY><<<a.n_tiles + aux, dim3(32, BY), 0, s>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// One fused step in -> out.  n_aux_slots: how many probe slots (from slot 0: the E/D family comes first) are sampled
+// on the INPUT state, into row probe_t of partials.
+template <typename T, typename AT>
+int launch_fused(cev_fdtd* p, const cev_state* in, const cev_state* out, const double* wave_row, int n_aux_slots,
+                 int64_t probe_t, double* partials, cudaStream_t s, bool* done) {
+    StepArgs<T, AT> a;
+    *done = false;
+    if (fill_args(p, in, a)) return -1;
+    for (int A = 0; A < 3; ++A) {
+        const int L = p->to_logical(A);
+        a.Hout[A] = (T*)out->H[L];
+        a.Dout[A] = (T*)out->D[L];
+        a.ICEout[A] = (T*)out->ICE[L];
+        a.IHout[A] = (T*)out->IH[L];
+        if (!a.Hout[A] || !a.Dout[A]) return fail("fused step: the shadow state needs H and D");
+        if ((a.ICE[A] && !a.ICEout[A]) || (a.IH[A] && !a.IHout[A])) return fail("fused step: the shadow state needs ICE / IH wherever the state has them");
+    }
+    if (!can_fuse(p, a)) return 0;
+    int shape = p->fused_shape;
+    if (shape == 0) shape = 1604;
+    switch (shape) {
+        case 1604: if (launch_fused_shape<T, AT, 16, 4>(p, a, wave_row, n_aux_slots, probe_t, partials, s)) return -1; break;
+        case 1608: if (launch_fused_shape<T, AT, 16, 8>(p, a, wave_row, n_aux_slots, probe_t, partials, s)) return -1; break;
+        case 3204: if (launch_fused_shape<T, AT, 32, 4>(p, a, wave_row, n_aux_slots, probe_t, partials, s)) return -1; break;
+        case 3208: if (launch_fused_shape<T, AT, 32, 8>(p, a, wave_row, n_aux_slots, probe_t, partials, s)) return -1; break;
+        case 804:  if (launch_fused_shape<T, AT, 8, 4>(p, a, wave_row, n_aux_slots, probe_t, partials, s)) return -1; break;
+        default: return fail("fused_shape must be one of 804, 1604, 1608, 3204, 3208");
+    }
+    *done = true;
+    return 0;
+}
+
+// nsteps time steps; the result ends up in `st` (an odd step count starts with one two-kernel step).
+template <typename T, typename AT>
+int run_loop_fused(cev_fdtd* p, const cev_state* st, const cev_state* shadow, int64_t nsteps, const double* waveform,
+                   double* partials, cudaStream_t s) {
+    const int64_t Nx = p->N[0];
+    cev_state B = *st;            // same 1/eps and D-side integrals, shadow H / D / ICE / IH
+    for (int c = 0; c < 3; ++c) {
+        B.H[c] = shadow->H[c];
+        B.D[c] = shadow->D[c];
+        B.ICE[c] = shadow->ICE[c];
+        B.IH[c] = shadow->IH[c];
+    }
+    const cev_state* cur = st;
+    const cev_state* nxt = &B;
+    int64_t n = 0;
+    bool h_probes_pending = false;       // H-family probes of step n-1 not sampled yet
+    auto two_kernel_step = [&](int64_t t) -> int {
+        if (h_probes_pending && launch_probe_only<T, AT>(p, cur, nullptr, 1, t - 1, partials, s)) return -1;
+        if (launch_H<T, AT>(p, cur, nullptr, nullptr, 0, Nx, t - 1, partials, s)) return -1;
+        if (launch_D<T, AT>(p, cur, nullptr, nullptr, nullptr, nullptr, nullptr, waveform ? waveform + t * p->nsrc : nullptr, 0,
+                            Nx, t, partials, s))
+            return -1;
+        h_probes_pending = false;
+        return 0;
+    };
+    if (nsteps & 1) {
+        if (two_kernel_step(0)) return -1;
+        n = 1;
+    }
+    for (; n < nsteps; ++n) {
+        bool done = false;
+        const int slots = h_probes_pending ? p->n_slots : p->n_slots_ED;   // E/D probes of step n-1 always ride here
+        if (launch_fused<T, AT>(p, cur, nxt, waveform ? waveform + n * p->nsrc : nullptr, slots, n - 1, partials, s, &done)) return -1;
+        if (!done) {              // not fusable (geometry / alignment): finish with the two-kernel path, in `st`
+            if (cur != st) return fail("internal: fused fallback on the shadow state");
+            for (; n < nsteps; ++n)
+                if (two_kernel_step(n)) return -1;
+            break;
+        }
+        h_probes_pending = true;
+        std::swap(cur, nxt);
+    }
+    if (cur != st) return fail("internal: fused run ended on the shadow state");
+    if (nsteps > 0) {
+        if (launch_probe_only<T, AT>(p, st, nullptr, 0, nsteps - 1, partials, s)) return -1;
+        if (h_probes_pending && launch_probe_only<T, AT>(p, st, nullptr, 1, nsteps - 1, partials, s)) return -1;
     }
     return 0;
 }
@@ -845,8 +978,12 @@ int cev_fdtd_destroy(cev_fdtd* p) {
 int cev_fdtd_set_option(cev_fdtd* p, const char* name, int64_t value) {
     if (!p || !name) return fail("NULL argument");
     if (!strcmp(name, "kernel_variant")) {
-        if (value < 0 || value > 3) return fail("kernel_variant must be 0 (auto), 1 (baseline), 2 (marching) or 3 (TMA-staged)");
+        if (value < 0 || value > 4) return fail("kernel_variant must be 0 (auto), 1 (baseline), 2 (marching), 3 (TMA-staged) or 4 (fused)");
         p->variant = (int)value;
+    } else if (!strcmp(name, "fused_shape")) {
+        if (value != 0 && value != 804 && value != 1604 && value != 1608 && value != 3204 && value != 3208)
+            return fail("fused_shape must be 0 (auto) or one of 804, 1604, 1608, 3204, 3208 (lanes_z*100 + warps)");
+        p->fused_shape = (int)value;
     } else if (!strcmp(name, "prefetch_planes")) {
         if (value < 0 || value > 64) return fail("prefetch_planes must be in [0, 64]");
         p->pf_dist = (int)value;
@@ -1095,6 +1232,19 @@ int cev_fdtd_run(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double*
     if (st->D_xhi[1] || st->D_xhi[2] || st->H_xlo[1] || st->H_xlo[2]) return fail("cev_fdtd_run steps a whole (periodic) grid; slabs are driven per half-step");
     DeviceGuard guard(p->device);
     return DISPATCH(p, run_loop, p, st, nsteps, p->n_src_pts > 0 ? waveform : nullptr, partials, (cudaStream_t)stream);
+}
+
+int cev_fdtd_run_fused(cev_fdtd* p, const cev_state* st, const cev_state* shadow, int64_t nsteps, const double* waveform,
+                       double* partials, void* stream) {
+    if (!p || !st || !shadow) return fail("NULL argument");
+    if (nsteps < 0) return fail("nsteps must be >= 0");
+    if (nsteps == 0) return 0;
+    if (p->n_src_pts > 0 && !waveform) return fail("plan has sources but waveform is NULL");
+    if (p->n_slots > 0 && !partials) return fail("plan has probes but partials is NULL");
+    if (st->D_xhi[1] || st->D_xhi[2] || st->H_xlo[1] || st->H_xlo[2]) return fail("cev_fdtd_run_fused steps a whole (periodic) grid; slabs are driven per half-step");
+    DeviceGuard guard(p->device);
+    return DISPATCH(p, run_loop_fused, p, st, shadow, nsteps, p->n_src_pts > 0 ? waveform : nullptr, partials,
+                    (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -71,6 +71,8 @@ struct StepArgs {
     T* IH[3];
     T* ICH[3];
     T* ID[3];
+    T* ICEout[3];       // fused full-step kernel only (step_v4.cuh): the H-side integrals are ping-ponged
+    T* IHout[3];
     const int* mapH[3];
     const int* mapD[3];
     int nH[3], nD[3];

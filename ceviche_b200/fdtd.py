@@ -130,6 +130,7 @@ class fdtd:
         self.arith_f64 = True if dtype == torch.float64 else (arith in ("f64", torch.float64))
         self._options = {}
         self._plan = None
+        self._fused_step = True
         # skip field components that are provably zero (2-D TM / TE, 1-D): see coupled_components()
         self.specialise_components = True
 
@@ -232,6 +233,9 @@ class fdtd:
 
     def set_option(self, name, value):
         """Kernel tuning / test knobs of the C ABI ('kernel_variant', 'xchunk'); results do not change."""
+        if name == "fused_step":        # host-side switch: 0 = run() never uses the fused full-step kernel
+            self._fused_step = bool(value)
+            return
         self._options[name] = int(value)
         if self._plan is not None:
             _lib.check(self._plan.lib.cev_fdtd_set_option(self._plan.handle, name.encode(), int(value)))
@@ -251,10 +255,12 @@ class fdtd:
         shapes = self._plan.pml_shapes
         z = lambda s: torch.zeros(s, dtype=self.dtype, device=self.device)
         self._pml = {fam: [z(shapes[f * 3 + c]) for c in range(3)] for f, fam in enumerate(_PML_FAMILIES)}
+        self._shadow = None
 
     def initialize_fields(self):
         """fdtd.py:147-211: zero state, t_index = 0, a NEW fields dict."""
         self.t_index = 0
+        self._shadow = None         # ping-pong scratch of the fused kernel (allocated on first use)
         self._active = 0            # components that may be non-zero (bits 0-2 D/E, 3-5 H)
         z = lambda: [torch.zeros(self.grid_shape, dtype=self.dtype, device=self.device) for _ in range(3)]
         self._H, self._D, self._E = z(), z(), z()
@@ -458,14 +464,42 @@ class fdtd:
                 self._published = False
             partials = torch.zeros((steps, self._n_slots), dtype=torch.float64, device=self.device)
             st = self._state()
-            _lib.check(plan.lib.cev_fdtd_run(plan.handle, C.byref(st), steps, _ptr(waveforms), _ptr(partials),
-                                             self._stream()))
+            if self._use_fused(steps):
+                # one kernel per time step (H and D half-steps fused): needs ping-pong scratch for H, D, ICE, IH
+                sh = self._shadow_state()
+                _lib.check(plan.lib.cev_fdtd_run_fused(plan.handle, C.byref(st), C.byref(sh), steps, _ptr(waveforms),
+                                                       _ptr(partials), self._stream()))
+            else:
+                _lib.check(plan.lib.cev_fdtd_run(plan.handle, C.byref(st), steps, _ptr(waveforms), _ptr(partials),
+                                                 self._stream()))
             self.t_index += steps
             if refresh:
                 self._refresh_E()
             if self._n_probes == 0:
                 return torch.zeros((steps, 0), dtype=torch.float64, device=self.device)
             return partials @ self._slot_fold
+
+    def _use_fused(self, steps):
+        """The fused full-step kernel (step_v4.cuh) serves whole grids with every component live.  It moves 15
+        instead of 21 words per cell but recomputes a halo and is latency-bound in the PML: measured on B200 it
+        only wins for fp32 storage on large grids (512^3: +6 %), so `kernel_variant` 0 (auto) uses it there and
+        4 forces it wherever it applies."""
+        kv = self._options.get("kernel_variant", 0)
+        if kv not in (0, 4) or steps < 2 or not self._fused_step:
+            return False
+        if self._options.get("active_components", 63) != 63:
+            return False
+        if kv == 4:
+            return True
+        return self.dtype == torch.float32 and not self.arith_f64 and min(self.grid_shape) >= 384
+
+    def _shadow_state(self):
+        if self._shadow is None:
+            self._shadow = ([torch.empty_like(t) for t in self._H], [torch.empty_like(t) for t in self._D],
+                            [torch.empty_like(t) for t in self._pml["ICE"]], [torch.empty_like(t) for t in self._pml["IH"]])
+        sh = _lib.cev_state()
+        sh.H, sh.D, sh.ICE, sh.IH = (_ptr3(ts) for ts in self._shadow)
+        return sh
 
     def _refresh_E(self):
         plan = self._ensure_plan()

@@ -107,7 +107,8 @@ int cev_fdtd_create(cev_fdtd** plan, int device, int dtype, int arith_f64,
                     const double* sH[3], const double* sD[3]);
 int cev_fdtd_destroy(cev_fdtd* plan);
 
-/* Tuning / test knobs: "kernel_variant" 0 auto | 1 baseline (one thread per cell) | 2 marching;
+/* Tuning / test knobs: "kernel_variant" 0 auto | 1 baseline (one thread per cell) | 2 marching | 3 TMA-staged |
+ * 4 fused full-step kernel in cev_fdtd_run_fused (0 also fuses there); "fused_shape" 0 auto | lanes_z*100 + warps;
  * "xchunk" x-planes per CTA of the marching kernels (0 = auto); "lanes_z" 8|16|32 lanes of a warp along z;
  * "prefetch_planes" L2 prefetch distance; "split_launch" 0|1 separate launches for the PML-free interior and
  * the PML shell.  Results do not depend on them (bit-identical).
@@ -156,6 +157,15 @@ int cev_fdtd_probe_slots(const cev_fdtd* plan, int32_t* slot_probe);
  * (series[t, p] = sum of the slots of p, in slot order: deterministic). */
 int cev_fdtd_run(cev_fdtd* plan, const cev_state* st, int64_t nsteps,
                  const double* waveform, double* partials, void* stream);
+
+/* Same contract and bit-identical results, with ONE kernel per time step: the H and the D half-step of
+ * fdtd.py:80-127 are fused, so the state is read once and written once per step (15 instead of 21 words per
+ * cell).  That needs ping-pong buffers: `shadow` carries caller-owned scratch arrays of the same shapes in its
+ * H, D, ICE and IH members (contents irrelevant, other members ignored).  The result always ends up in `st`.
+ * Grids the fused kernel does not serve (contiguous extent not a multiple of the 16-byte vector, masked
+ * components) silently take the two-kernel path of cev_fdtd_run. */
+int cev_fdtd_run_fused(cev_fdtd* plan, const cev_state* st, const cev_state* shadow, int64_t nsteps,
+                       const double* waveform, double* partials, void* stream);
 
 /* Forward mode (replaces one traced re-run per direction, ceviche/jacobians.py:38-51): the primal and
  * B tangent states advance together; tangent_partials is [B, nsteps, n_slots]. */

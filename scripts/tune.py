@@ -40,11 +40,22 @@ def timeit(fn, reps=30):
     return a.elapsed_time(b) / reps
 
 
+RUN_STEPS = int(os.environ.get("TUNE_RUN", "0"))     # > 0: time the fused caller loop run() instead of single half-steps
 for combo in sys.argv[3:]:
     for kv in combo.split(","):
         if kv:
             k, v = kv.split("=")
             F.set_option(k, int(v))
+    if RUN_STEPS:
+        F._active = 63
+        F._apply_active(63)
+        wf = torch.zeros((RUN_STEPS, 0), dtype=torch.float64, device="cuda")
+        F.set_sources([])
+        F.set_probes([])
+        t = timeit(lambda: F._run_raw(RUN_STEPS, wf, refresh=False), reps=3) / RUN_STEPS
+        print("%4d %s %-40s run(): %.4f ms/step  %.2f Gcell/s  21w: %5.0f GB/s  fused=%s" % (
+            N, sys.argv[2], combo, t, cells / t / 1e6, cells * 21 * w / t / 1e6, F._use_fused(RUN_STEPS)), flush=True)
+        continue
     h = timeit(lambda: _lib.check(plan.lib.cev_fdtd_step_H(plan.handle, C.byref(st), None, 0, N, s)))
     d = timeit(lambda: _lib.check(plan.lib.cev_fdtd_step_D(plan.handle, C.byref(st), None, None, None, None, 0, N, s)))
     print("%4d %s %-40s H %.4f ms %6.0f GB/s | D %.4f ms %6.0f GB/s | step %.2f Gcell/s %5.0f GB/s" % (

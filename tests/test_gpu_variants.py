@@ -21,10 +21,13 @@ def _case(shape, npml, steps, seed):
     return dict(eps=eps, dL=cases.DL, npml=list(npml), steps=steps, sources=src, probes=probes)
 
 
-def _run(case, dtype, variant, xchunk=0, per_step=False, lanes_z=8, prefetch=1, split=0):
+def _run(case, dtype, variant, xchunk=0, per_step=False, lanes_z=8, prefetch=1, split=0, fused_shape=0, steps=None):
     import ceviche_b200
+    if steps is not None:
+        case = dict(case, steps=steps, sources=[(c, p, w[:steps]) for c, p, w in case["sources"]])
     F = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"], dtype=dtype)
     F.set_option("kernel_variant", variant)
+    F.set_option("fused_shape", fused_shape)
     F.set_option("xchunk", xchunk)
     F.set_option("lanes_z", lanes_z)
     F.set_option("prefetch_planes", prefetch)
@@ -69,6 +72,45 @@ def test_marching_equals_baseline_bitwise(shape, npml, dtype):
         for a, b in zip(p1, p3):
             assert np.array_equal(a, b), ("v3", xchunk)
         assert np.array_equal(s1, s3)
+
+
+FUSED_SHAPES = SHAPES + [((5, 3, 8), (1, 1, 2)), ((1, 6, 16), (0, 2, 3)), ((17, 1, 36), (3, 0, 4)), ((36, 31, 124), (5, 4, 6)),
+                         ((20, 9, 4), (3, 2, 0))]
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("shape,npml", FUSED_SHAPES)
+def test_fused_step_equals_baseline_bitwise(shape, npml, dtype):
+    """The fused full-step kernel (step_v4.cuh, one launch per time step, ping-ponged state) against the
+    one-thread-per-cell kernels: fields, PML integrals and probe series, even and odd step counts, every
+    tile shape and several x-chunkings (the pre-roll plane, halo rows / lanes and periodic wraps all differ)."""
+    case = _case(shape, npml, 41, 7)
+    ref = {n: _run(case, dtype, 1, steps=n) for n in (41, 40, 2)}
+    for fs, xchunk, n in ((0, 0, 41), (1604, 3, 40), (804, 1, 41), (1608, 1000, 40), (3204, 5, 41), (3208, 2, 2), (0, 7, 2)):
+        s1, f1, p1 = ref[n]
+        s4, f4, p4 = _run(case, dtype, 4, xchunk, fused_shape=fs, steps=n)
+        for k in FIELD_KEYS:
+            assert np.array_equal(f1[k], f4[k]), (k, fs, xchunk, n)
+        for q, (a, b) in enumerate(zip(p1, p4)):
+            assert np.array_equal(a, b), (q, fs, xchunk, n)
+        assert np.array_equal(s1, s4), (fs, xchunk, n)
+
+
+def test_fused_step_keeps_running_across_calls_and_against_oracle():
+    case = _case((24, 22, 72), (4, 3, 5), 60, 5)
+    import ceviche_b200
+    F = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"])
+    F.set_option("kernel_variant", 4)
+    parts = []
+    for t0, t1 in ((0, 7), (7, 8), (8, 30), (30, 60)):          # odd / single / even legs on the same object
+        parts.append(F.run(t1 - t0, [(c, p, w[t0:t1]) for c, p, w in case["sources"]], case["probes"]).cpu().numpy())
+    series = np.concatenate(parts)
+    O = OracleFDTD(case["eps"], case["dL"], case["npml"])
+    o_series, _ = O.run(case["steps"], case["sources"], case["probes"])
+    for k in FIELD_KEYS:
+        assert rel_l2(F.fields[k].cpu().numpy(), O.fields()[k]) <= 1e-10, k
+    for p in range(series.shape[1]):
+        assert rel_l2(series[:, p], o_series[:, p]) <= 1e-10
 
 
 def test_marching_forward_api_with_dense_J_and_E_output():
