@@ -418,7 +418,8 @@ int launch_H(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, void* con
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
-    const bool split = want_split<T>(p, x0, x1);
+    const bool masked = a.on != 63u;       // some components are identically zero: the mask-aware instantiation
+    const bool split = !masked && want_split<T>(p, x0, x1);
     bool probes_done = false;
     for (int part = split ? 1 : 0; part <= (split ? 2 : 0); ++part) {
         set_tiles_v2(p, a, x0, x1, part);
@@ -431,7 +432,11 @@ int launch_H(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, void* con
         }
         const int g = a.n_tiles + aux;
         if (g == 0) continue;
-        if (part == 1) {
+        if (masked) {
+            if (p->lz == 8) k_step_H_v2<T, AT, V, 8, false, true><<<g, blk, 0, s>>>(a);
+            else if (p->lz == 16) k_step_H_v2<T, AT, V, 16, false, true><<<g, blk, 0, s>>>(a);
+            else k_step_H_v2<T, AT, V, 32, false, true><<<g, blk, 0, s>>>(a);
+        } else if (part == 1) {
             if (p->lz == 8) k_step_H_v2<T, AT, V, 8, true><<<g, blk, 0, s>>>(a);
             else if (p->lz == 16) k_step_H_v2<T, AT, V, 16, true><<<g, blk, 0, s>>>(a);
             else k_step_H_v2<T, AT, V, 32, true><<<g, blk, 0, s>>>(a);
@@ -500,7 +505,8 @@ int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
-    const bool split = !extras && want_split<T>(p, x0, x1);   // the per-step forward() API keeps one launch
+    const bool masked = a.on != 63u;       // (never with extras: those force the full mask above)
+    const bool split = !extras && !masked && want_split<T>(p, x0, x1);   // the per-step forward() API keeps one launch
     bool probes_done = false;
     for (int part = split ? 1 : 0; part <= (split ? 2 : 0); ++part) {
         set_tiles_v2(p, a, x0, x1, part);
@@ -514,7 +520,11 @@ int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const
         }
         const int g = a.n_tiles + aux;
         if (g == 0) continue;
-        if (extras) {
+        if (masked) {
+            p->lz == 8 ? k_step_D_v2<T, AT, V, 8, false, false, true><<<g, blk, 0, s>>>(a)
+                       : (p->lz == 16 ? k_step_D_v2<T, AT, V, 16, false, false, true><<<g, blk, 0, s>>>(a)
+                                      : k_step_D_v2<T, AT, V, 32, false, false, true><<<g, blk, 0, s>>>(a));
+        } else if (extras) {
             p->lz == 8 ? k_step_D_v2<T, AT, V, 8, true, false><<<g, blk, 0, s>>>(a)
                        : (p->lz == 16 ? k_step_D_v2<T, AT, V, 16, true, false><<<g, blk, 0, s>>>(a)
                                       : k_step_D_v2<T, AT, V, 32, true, false><<<g, blk, 0, s>>>(a));

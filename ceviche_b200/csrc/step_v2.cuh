@@ -187,7 +187,10 @@ struct PmlCtx {
 
 // INTERIOR = the launch covers only cells off every PML: all PML code is compiled out (few registers,
 // high occupancy); otherwise the general kernel.
-template <typename T, typename AT, int V, int LZ, bool INTERIOR>
+// MASKED = the component mask a.on is honoured (2-D / 1-D runs); otherwise it is the compile-time constant "all six",
+// every mask test folds away and the code is exactly the unmasked kernel (the runtime tests cost the full-vector
+// kernels 20-50 % on B200: measured, profiles/).
+template <typename T, typename AT, int V, int LZ, bool INTERIOR, bool MASKED = false>
 __global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS : (sizeof(T) == 8 ? V2_H_MIN_CTAS : V2_H_MIN_CTAS + 1)))
 k_step_H_v2(const StepArgs<T, AT> a) {
     const int bid = blockIdx.x;
@@ -235,7 +238,7 @@ k_step_H_v2(const StepArgs<T, AT> a) {
     }
     const AT s = -a.cdt;
     const AT inv = a.inv_dL;
-    const unsigned onE = a.on & 7u, onH = (a.on >> 3) & 7u;
+    const unsigned onE = MASKED ? (a.on & 7u) : 7u, onH = MASKED ? ((a.on >> 3) & 7u) : 7u;
 
     // E = mE*D of the current plane (own cells)
     AT Ecur[3][V];
@@ -338,7 +341,7 @@ k_step_H_v2(const StepArgs<T, AT> a) {
 
 // EXTRAS = dense J input and/or E output (the per-step forward() API); the fused run() path
 // instantiates EXTRAS = false and carries neither.
-template <typename T, typename AT, int V, int LZ, bool EXTRAS, bool INTERIOR>
+template <typename T, typename AT, int V, int LZ, bool EXTRAS, bool INTERIOR, bool MASKED = false>
 __global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS : V2_D_MIN_CTAS)) k_step_D_v2(const StepArgs<T, AT> a) {
     const int bid = blockIdx.x;
     if (bid >= a.n_tiles) {
@@ -385,7 +388,7 @@ __global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS :
     }
     const AT s = a.cdt;
     const AT inv = a.inv_dL;
-    const unsigned onE = a.on & 7u, onH = (a.on >> 3) & 7u;
+    const unsigned onE = MASKED ? (a.on & 7u) : 7u, onH = MASKED ? ((a.on >> 3) & 7u) : 7u;
 
     // H of the previous plane (own cells), y and z components
     AT Hprev[2][V];

@@ -480,18 +480,12 @@ class fdtd:
             return partials @ self._slot_fold
 
     def _use_fused(self, steps):
-        """The fused full-step kernel (step_v4.cuh) serves whole grids with every component live.  It moves 15
-        instead of 21 words per cell but recomputes a halo and is latency-bound in the PML: measured on B200 it
-        only wins for fp32 storage on large grids (512^3: +6 %), so `kernel_variant` 0 (auto) uses it there and
-        4 forces it wherever it applies."""
-        kv = self._options.get("kernel_variant", 0)
-        if kv not in (0, 4) or steps < 2 or not self._fused_step:
+        """The fused full-step kernel (step_v4.cuh) moves 15 instead of 21 words per cell but recomputes a halo and
+        runs at 2-3 CTAs per SM: measured on B200 it is 15-40 % SLOWER than the two tuned half-step kernels
+        (profiles/README.md), so it is opt-in only: `set_option('kernel_variant', 4)`."""
+        if self._options.get("kernel_variant", 0) != 4 or steps < 2 or not self._fused_step:
             return False
-        if self._options.get("active_components", 63) != 63:
-            return False
-        if kv == 4:
-            return True
-        return self.dtype == torch.float32 and not self.arith_f64 and min(self.grid_shape) >= 384
+        return self._options.get("active_components", 63) == 63
 
     def _shadow_state(self):
         if self._shadow is None:
