@@ -69,7 +69,12 @@ struct DeviceBuf {
 
 struct cev_fdtd {
     int device = 0, dtype = CEV_F64, arith64 = 1;
-    int rot = 0;                 // internal axis A <-> logical axis (A - rot) mod 3
+    // Internal axis A holds logical axis perm[A] (inv = the inverse map).  Identity for 3-D grids; a 2-D grid
+    // (Nz = 1) is relabelled (x, z, y) so that x stays the marching axis and y becomes the vectorised one -- a swap
+    // of two axes, under which the curl changes sign (parity = -1: C0*dt enters every kernel negated, which is
+    // exact); a 1-D grid (Ny = Nz = 1) is relabelled cyclically (y, z, x).  Memory is untouched in both cases.
+    int perm[3] = {0, 1, 2}, inv[3] = {0, 1, 2};
+    int parity = 1;
     int64_t Nl[3] = {0, 0, 0};   // logical extents
     int N[3] = {0, 0, 0};        // internal extents
     double dL = 0, dt = 0, cdt = 0;
@@ -108,8 +113,9 @@ struct cev_fdtd {
     std::vector<int32_t> slot_probe;
     DeviceBuf pr_field, pr_wbegin, pr_ibegin, pr_cell0, pr_n, pr_idx, pr_weight, pr_owner;
 
-    int to_internal(int logical_axis) const { return (logical_axis + rot) % 3; }
-    int to_logical(int internal_axis) const { return (internal_axis - rot + 3) % 3; }
+    int to_internal(int logical_axis) const { return inv[logical_axis]; }
+    int to_logical(int internal_axis) const { return perm[internal_axis]; }
+    bool x_is_x() const { return perm[0] == 0; }     // logical x-ranges / x-halo planes are internal ones
 };
 
 namespace {
@@ -168,8 +174,8 @@ int fill_args(const cev_fdtd* p, const cev_state* st, StepArgs<T, AT>& a, const 
         }
     }
     if (tan && (st->D_xhi[1] || st->D_xhi[2])) return fail("tangent steps do not support x-halo planes");
-    if (p->rot != 0 && (st->D_xhi[1] || st->D_xhi[2] || st->H_xlo[1] || st->H_xlo[2]))
-        return fail("x-halo planes need Nz > 1 (no slab decomposition of a rotated 2-D/1-D grid)");
+    if (!p->x_is_x() && (st->D_xhi[1] || st->D_xhi[2] || st->H_xlo[1] || st->H_xlo[2]))
+        return fail("x-halo planes need Ny > 1 or Nz > 1 (no slab decomposition of a 1-D grid)");
     // PML integral arrays must exist wherever the kernels will touch them
     for (int A = 0; A < 3; ++A) {
         const int B = (A + 1) % 3, C = (A + 2) % 3;
@@ -178,7 +184,7 @@ int fill_args(const cev_fdtd* p, const cev_state* st, StepArgs<T, AT>& a, const 
         if (p->nH[B] > 0 && p->nH[C] > 0 && !a.IH[A]) return fail("cev_state: IH missing for a PML corner");
         if (p->nD[B] > 0 && p->nD[C] > 0 && !a.ID[A]) return fail("cev_state: ID missing for a PML corner");
     }
-    a.cdt = (AT)p->cdt;
+    a.cdt = (AT)(p->parity * p->cdt);
     a.inv_dL = (AT)(1.0 / p->dL);
     a.on = p->on;
     fill_probe_table(p, a.pr);
@@ -186,13 +192,20 @@ int fill_args(const cev_fdtd* p, const cev_state* st, StepArgs<T, AT>& a, const 
     return 0;
 }
 
+// block shape of the baseline kernels: 64 x 4 cells, or one row of 256 for single-row planes (2-D grids)
+template <typename T, typename AT>
+dim3 v1_block(const StepArgs<T, AT>& a) {
+    return a.Ny == 1 ? dim3(V1_TZ * V1_TY, 1) : dim3(V1_TZ, V1_TY);
+}
+
 template <typename T, typename AT>
 void set_tiles_v1(StepArgs<T, AT>& a, int64_t x0, int64_t x1) {
     a.x0 = (int)x0;
     a.x1 = (int)x1;
     a.xchunk = 1;
-    a.ntz = (a.Nz + V1_TZ - 1) / V1_TZ;
-    a.nty = (a.Ny + V1_TY - 1) / V1_TY;
+    const dim3 blk = v1_block(a);
+    a.ntz = (a.Nz + blk.x - 1) / blk.x;
+    a.nty = (a.Ny + blk.y - 1) / blk.y;
     a.n_tiles = a.ntz * a.nty * (int)(x1 - x0);
 }
 
@@ -205,13 +218,14 @@ constexpr int vec_width() {
 // array 16-byte aligned (torch allocations are; odd Nz falls back to the baseline kernels).
 template <typename T, typename AT>
 bool can_march(const cev_fdtd* p, const StepArgs<T, AT>& a, bool isH) {
-    if (p->variant == 1 || a.dmE[0]) return false;    // tangent steps use the baseline kernels
+    if (p->variant == 1) return false;
     constexpr int V = vec_width<T>();
     if (a.Nz % V != 0) return false;
     auto ok = [](const void* q) { return q == nullptr || ((uintptr_t)q % 16) == 0; };
     for (int c = 0; c < 3; ++c) {
         if (!ok(a.Hin[c]) || !ok(a.Hout[c]) || !ok(a.Din[c]) || !ok(a.Dout[c]) || !ok(a.mE[c]) || !ok(a.Eout[c]) ||
-            !ok(a.Dhi[c]) || !ok(a.mEhi[c]) || !ok(a.Hlo[c]) || !ok(a.J[c]))
+            !ok(a.Dhi[c]) || !ok(a.mEhi[c]) || !ok(a.Hlo[c]) || !ok(a.J[c]) || !ok(a.dmE[c]) || !ok(a.Dp[c]) ||
+            !ok(a.dmEhi[c]) || !ok(a.Dphi[c]))
             return false;
     }
     (void)isH;
@@ -221,18 +235,27 @@ bool can_march(const cev_fdtd* p, const StepArgs<T, AT>& a, bool isH) {
 // Tiling of one marching launch over a list of boxes.  part: 0 = the whole range [x0,x1) x Ny x Nz in one
 // box (general kernel); 1 = the PML-free interior box clipped to [x0,x1); 2 = the shell = the rest, as up to six slabs.
 template <typename T, typename AT>
-void set_tiles_v2(const cev_fdtd* p, StepArgs<T, AT>& a, int64_t x0, int64_t x1, int part, int lz_override = 0) {
+void set_tiles_v2(const cev_fdtd* p, StepArgs<T, AT>& a, int64_t x0, int64_t x1, int part, int lz_override = 0,
+                  int lz_force = 0) {
     constexpr int V = vec_width<T>();
-    const int LZ = lz_override ? lz_override : p->lz, rows = V2_BY * (32 / LZ);
+    // planes of a single row (2-D grids: internal Ny = 1): one row per warp and the warps side by side along z
+    const bool wz = a.Ny == 1 && part == 0 && !lz_override;
+    const int LZ = lz_override ? lz_override : (wz ? 32 : (lz_force ? lz_force : p->lz));
+    const int rows = wz ? 1 : V2_BY * (32 / LZ), zc = (wz ? V2_BY : 1) * LZ * V;   // cells of a CTA tile
+    a.wz = wz ? 1 : 0;
     a.x0 = (int)x0;
     a.x1 = (int)x1;
     int chunk = p->xchunk;
     if (chunk <= 0) {
         // short chunks keep the concurrently-active working set (CTAs x streams x planes) inside L2
         // and give the scheduler many CTAs to balance; tuned on B200 (scripts/tune.py)
-        const int cols = ((a.Nz + LZ * V - 1) / (LZ * V)) * ((a.Ny + rows - 1) / rows);
+        const int cols = ((a.Nz + zc - 1) / zc) * ((a.Ny + rows - 1) / rows);
         chunk = cols >= 512 ? 8 : 4;
         if (lz_override) chunk = 16;      // TMA-staged kernels: longer chunks amortise the pipeline fill
+        if (wz) {                         // a plane is one row: longer chunks amortise the carried-in plane
+            chunk = 32;
+            while (chunk > 1 && (int64_t)cols * ((x1 - x0 + chunk - 1) / chunk) < 148 * 8) chunk /= 2;
+        }
     }
     a.xchunk = chunk;
     a.pf_dist = p->pf_dist;
@@ -242,7 +265,7 @@ void set_tiles_v2(const cev_fdtd* p, StepArgs<T, AT>& a, int64_t x0, int64_t x1,
         if (bx1 <= bx0 || by1 <= by0 || bz1 <= bz0) return;
         Box& B = a.box[a.n_boxes++];
         B.x0 = bx0; B.x1 = bx1; B.y0 = by0; B.y1 = by1; B.z0 = bz0; B.z1 = bz1;
-        B.ntz = (bz1 - bz0 + LZ * V - 1) / (LZ * V);
+        B.ntz = (bz1 - bz0 + zc - 1) / zc;
         B.nty = (by1 - by0 + rows - 1) / rows;
         B.cta0 = cta;
         cta += B.ntz * B.nty * ((bx1 - bx0 + chunk - 1) / chunk);
@@ -289,7 +312,7 @@ void set_tiles_v3(const cev_fdtd* p, StepArgs<T, AT>& a, int64_t x0, int64_t x1)
 // Is it worth (and possible) to split [x0,x1) into an interior launch and a shell launch?
 template <typename T>
 bool want_split(const cev_fdtd* p, int64_t x0, int64_t x1) {
-    if (!p->split) return false;
+    if (!p->split || p->N[1] == 1) return false;
     constexpr int V = vec_width<T>();
     const int64_t ix = std::min<int64_t>(x1, p->in_hi[0]) - std::max<int64_t>(x0, p->in_lo[0]);
     const int64_t iy = p->in_hi[1] - p->in_lo[1];
@@ -399,12 +422,24 @@ int launch_H(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, void* con
         set_tiles_v1(a, x0, x1);
         const int aux = attach_probes(p, a, 0, probe_t, partials);
         if (a.n_tiles + aux == 0) return 0;
-        k_step_H_v1<T, AT><<<a.n_tiles + aux, dim3(V1_TZ, V1_TY), 0, s>>>(a);
+        k_step_H_v1<T, AT><<<a.n_tiles + aux, v1_block(a), 0, s>>>(a);
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
     constexpr int V = vec_width<T>();
     const dim3 blk(32, V2_BY);
+    if (tan) {      // tangent step E = mE*dD + dmE*D: the marching kernel with 32 lanes along z
+        set_tiles_v2(p, a, x0, x1, 0, 0, 32);
+        const int aux = attach_probes(p, a, 0, probe_t, partials);
+        const int g = a.n_tiles + aux;
+        if (g == 0) return 0;
+        if (a.on == 63u) k_step_H_v2<T, AT, V, 32, false, 63, true><<<g, blk, 0, s>>>(a);
+        else if (a.wz && a.on == (unsigned)MASK_TM) k_step_H_v2<T, AT, V, 32, false, MASK_TM, true><<<g, blk, 0, s>>>(a);
+        else if (a.wz && a.on == (unsigned)MASK_TE) k_step_H_v2<T, AT, V, 32, false, MASK_TE, true><<<g, blk, 0, s>>>(a);
+        else k_step_H_v2<T, AT, V, 32, false, -1, true><<<g, blk, 0, s>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     if (p->variant == 3 && a.on == 63u) {       // TMA-staged kernel: one launch, rows of 32 vectors
         set_tiles_v3(p, a, x0, x1);
         const int aux = attach_probes(p, a, 0, probe_t, partials);
@@ -432,17 +467,20 @@ int launch_H(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, void* con
         }
         const int g = a.n_tiles + aux;
         if (g == 0) continue;
+        const int lz = a.wz ? 32 : p->lz;
         if (masked) {
-            if (p->lz == 8) k_step_H_v2<T, AT, V, 8, false, true><<<g, blk, 0, s>>>(a);
-            else if (p->lz == 16) k_step_H_v2<T, AT, V, 16, false, true><<<g, blk, 0, s>>>(a);
-            else k_step_H_v2<T, AT, V, 32, false, true><<<g, blk, 0, s>>>(a);
+            if (lz == 8) k_step_H_v2<T, AT, V, 8, false, -1><<<g, blk, 0, s>>>(a);
+            else if (lz == 16) k_step_H_v2<T, AT, V, 16, false, -1><<<g, blk, 0, s>>>(a);
+            else if (a.on == (unsigned)MASK_TM) k_step_H_v2<T, AT, V, 32, false, MASK_TM><<<g, blk, 0, s>>>(a);
+            else if (a.on == (unsigned)MASK_TE) k_step_H_v2<T, AT, V, 32, false, MASK_TE><<<g, blk, 0, s>>>(a);
+            else k_step_H_v2<T, AT, V, 32, false, -1><<<g, blk, 0, s>>>(a);
         } else if (part == 1) {
-            if (p->lz == 8) k_step_H_v2<T, AT, V, 8, true><<<g, blk, 0, s>>>(a);
-            else if (p->lz == 16) k_step_H_v2<T, AT, V, 16, true><<<g, blk, 0, s>>>(a);
+            if (lz == 8) k_step_H_v2<T, AT, V, 8, true><<<g, blk, 0, s>>>(a);
+            else if (lz == 16) k_step_H_v2<T, AT, V, 16, true><<<g, blk, 0, s>>>(a);
             else k_step_H_v2<T, AT, V, 32, true><<<g, blk, 0, s>>>(a);
         } else {
-            if (p->lz == 8) k_step_H_v2<T, AT, V, 8, false><<<g, blk, 0, s>>>(a);
-            else if (p->lz == 16) k_step_H_v2<T, AT, V, 16, false><<<g, blk, 0, s>>>(a);
+            if (lz == 8) k_step_H_v2<T, AT, V, 8, false><<<g, blk, 0, s>>>(a);
+            else if (lz == 16) k_step_H_v2<T, AT, V, 16, false><<<g, blk, 0, s>>>(a);
             else k_step_H_v2<T, AT, V, 32, false><<<g, blk, 0, s>>>(a);
         }
     }
@@ -480,7 +518,7 @@ int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const
         set_tiles_v1(a, x0, x1);
         const int aux = attach_probes(p, a, 1, probe_t, partials);
         if (a.n_tiles + aux == 0) return 0;
-        k_step_D_v1<T, AT><<<a.n_tiles + aux, dim3(V1_TZ, V1_TY), 0, s>>>(a);
+        k_step_D_v1<T, AT><<<a.n_tiles + aux, v1_block(a), 0, s>>>(a);
         CUDA_TRY(cudaGetLastError());
         if (inject) return launch_inject<T, AT>(p, st, D_out, wave_row, x0, x1, s);
         return 0;
@@ -491,7 +529,7 @@ int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const
     if (extras) a.on = 63u;
     // auto: the TMA-staged D kernel wins in fp64 (measured, scripts/tune.py); fp32 and the H half-step stay on the
     // register-marching kernels
-    if ((p->variant == 3 || ((p->variant == 0 || p->variant == 4) && sizeof(T) == 8 && x1 - x0 >= 4)) && !extras && a.on == 63u) {
+    if ((p->variant == 3 || ((p->variant == 0 || p->variant == 4) && sizeof(T) == 8 && x1 - x0 >= 4 && a.Ny >= V3_BY)) && !extras && a.on == 63u) {
         set_tiles_v3(p, a, x0, x1);
         if (inject && attach_sources_v2(p, a, wave_row, 0, 32, V3_BY)) return -1;
         const int aux = attach_probes(p, a, 1, probe_t, partials);
@@ -510,7 +548,8 @@ int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const
     bool probes_done = false;
     for (int part = split ? 1 : 0; part <= (split ? 2 : 0); ++part) {
         set_tiles_v2(p, a, x0, x1, part);
-        if (inject && attach_sources_v2(p, a, wave_row, part)) return -1;
+        if (inject && (a.wz ? attach_sources_v2(p, a, wave_row, part, -(V2_BY * 32), 1) : attach_sources_v2(p, a, wave_row, part)))
+            return -1;
         int aux = 0;
         if (!probes_done) {
             aux = attach_probes(p, a, 1, probe_t, partials);
@@ -520,22 +559,25 @@ int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const
         }
         const int g = a.n_tiles + aux;
         if (g == 0) continue;
+        const int lz = a.wz ? 32 : p->lz;
         if (masked) {
-            p->lz == 8 ? k_step_D_v2<T, AT, V, 8, false, false, true><<<g, blk, 0, s>>>(a)
-                       : (p->lz == 16 ? k_step_D_v2<T, AT, V, 16, false, false, true><<<g, blk, 0, s>>>(a)
-                                      : k_step_D_v2<T, AT, V, 32, false, false, true><<<g, blk, 0, s>>>(a));
+            if (lz == 8) k_step_D_v2<T, AT, V, 8, false, false, -1><<<g, blk, 0, s>>>(a);
+            else if (lz == 16) k_step_D_v2<T, AT, V, 16, false, false, -1><<<g, blk, 0, s>>>(a);
+            else if (a.on == (unsigned)MASK_TM) k_step_D_v2<T, AT, V, 32, false, false, MASK_TM><<<g, blk, 0, s>>>(a);
+            else if (a.on == (unsigned)MASK_TE) k_step_D_v2<T, AT, V, 32, false, false, MASK_TE><<<g, blk, 0, s>>>(a);
+            else k_step_D_v2<T, AT, V, 32, false, false, -1><<<g, blk, 0, s>>>(a);
         } else if (extras) {
-            p->lz == 8 ? k_step_D_v2<T, AT, V, 8, true, false><<<g, blk, 0, s>>>(a)
-                       : (p->lz == 16 ? k_step_D_v2<T, AT, V, 16, true, false><<<g, blk, 0, s>>>(a)
-                                      : k_step_D_v2<T, AT, V, 32, true, false><<<g, blk, 0, s>>>(a));
+            lz == 8 ? k_step_D_v2<T, AT, V, 8, true, false><<<g, blk, 0, s>>>(a)
+                    : (lz == 16 ? k_step_D_v2<T, AT, V, 16, true, false><<<g, blk, 0, s>>>(a)
+                                : k_step_D_v2<T, AT, V, 32, true, false><<<g, blk, 0, s>>>(a));
         } else if (part == 1) {
-            p->lz == 8 ? k_step_D_v2<T, AT, V, 8, false, true><<<g, blk, 0, s>>>(a)
-                       : (p->lz == 16 ? k_step_D_v2<T, AT, V, 16, false, true><<<g, blk, 0, s>>>(a)
-                                      : k_step_D_v2<T, AT, V, 32, false, true><<<g, blk, 0, s>>>(a));
+            lz == 8 ? k_step_D_v2<T, AT, V, 8, false, true><<<g, blk, 0, s>>>(a)
+                    : (lz == 16 ? k_step_D_v2<T, AT, V, 16, false, true><<<g, blk, 0, s>>>(a)
+                                : k_step_D_v2<T, AT, V, 32, false, true><<<g, blk, 0, s>>>(a));
         } else {
-            p->lz == 8 ? k_step_D_v2<T, AT, V, 8, false, false><<<g, blk, 0, s>>>(a)
-                       : (p->lz == 16 ? k_step_D_v2<T, AT, V, 16, false, false><<<g, blk, 0, s>>>(a)
-                                      : k_step_D_v2<T, AT, V, 32, false, false><<<g, blk, 0, s>>>(a));
+            lz == 8 ? k_step_D_v2<T, AT, V, 8, false, false><<<g, blk, 0, s>>>(a)
+                    : (lz == 16 ? k_step_D_v2<T, AT, V, 16, false, false><<<g, blk, 0, s>>>(a)
+                                : k_step_D_v2<T, AT, V, 32, false, false><<<g, blk, 0, s>>>(a));
         }
     }
     CUDA_TRY(cudaGetLastError());
@@ -796,7 +838,7 @@ int fill_adj(const cev_fdtd* p, const cev_state* fwd, const cev_adjoint* adj, Ad
         a.uD[A] = (const AT*)p->uD[A][w];
         a.rD[A] = (const AT*)p->rD[A][w];
     }
-    a.cdt = (AT)p->cdt;
+    a.cdt = (AT)(p->parity * p->cdt);
     a.inv_dL = (AT)(1.0 / p->dL);
     return 0;
 }
@@ -845,10 +887,10 @@ struct DeviceGuard {
 };
 
 int check_range(const cev_fdtd* p, int64_t x0, int64_t x1) {
-    // ranges are over the LOGICAL x axis = internal axis `rot`; only unrotated plans may sub-range
+    // ranges are over the LOGICAL x axis; only plans whose internal x is the logical x may sub-range
     const int64_t nx = p->Nl[0];
     if (x0 < 0 || x1 > nx || x0 > x1) return fail("x-range [%lld,%lld) outside [0,%lld)", (long long)x0, (long long)x1, (long long)nx);
-    if (p->rot != 0 && !(x0 == 0 && x1 == nx)) return fail("partial x-ranges need Nz > 1");
+    if (!p->x_is_x() && !(x0 == 0 && x1 == nx)) return fail("partial x-ranges need Ny > 1 or Nz > 1");
     return 0;
 }
 
@@ -884,7 +926,13 @@ int cev_fdtd_create(cev_fdtd** out, int device, int dtype, int arith_f64, int64_
     p->dt = dt;
     p->cdt = (1.0 / std::sqrt(EPSILON_0 * MU_0)) * dt;
     // make the last internal axis the contiguous one with extent > 1 (cyclic relabelling keeps the curl)
-    p->rot = (Nz > 1) ? 0 : (Ny > 1 ? 1 : (nx > 1 ? 2 : 0));
+    if (Nz == 1 && Ny > 1) {              // 2-D: (x, z, y), a swap
+        p->perm[1] = 2; p->perm[2] = 1;
+        p->parity = -1;
+    } else if (Nz == 1 && Ny == 1 && nx > 1) {   // 1-D: (y, z, x), cyclic
+        p->perm[0] = 1; p->perm[1] = 2; p->perm[2] = 0;
+    }
+    for (int A = 0; A < 3; ++A) p->inv[p->perm[A]] = A;
     for (int A = 0; A < 3; ++A) p->N[A] = (int)p->Nl[p->to_logical(A)];
 
     // tables: per internal axis, for H and D sampling: u (f32,f64), r (f32,f64), map (int)
@@ -1041,7 +1089,7 @@ int cev_fdtd_step_H(cev_fdtd* p, const cev_state* st, void* const H_out[3], int6
     if (!p || !st) return fail("NULL argument");
     if (check_range(p, x0, x1)) return -1;
     DeviceGuard guard(p->device);
-    const int64_t a0 = p->rot ? 0 : x0, a1 = p->rot ? p->N[0] : x1;
+    const int64_t a0 = p->x_is_x() ? x0 : 0, a1 = p->x_is_x() ? x1 : p->N[0];
     return DISPATCH(p, launch_H, p, st, (const cev_tangent*)nullptr, H_out, a0, a1, (int64_t)-1, (double*)nullptr, (cudaStream_t)stream);
 }
 
@@ -1050,7 +1098,7 @@ int cev_fdtd_step_H_ex(cev_fdtd* p, const cev_state* st, const cev_tangent* tan,
     if (!p || !st) return fail("NULL argument");
     if (check_range(p, x0, x1)) return -1;
     DeviceGuard guard(p->device);
-    const int64_t a0 = p->rot ? 0 : x0, a1 = p->rot ? p->N[0] : x1;
+    const int64_t a0 = p->x_is_x() ? x0 : 0, a1 = p->x_is_x() ? x1 : p->N[0];
     return DISPATCH(p, launch_H, p, st, tan, H_out, a0, a1, probe_t, partials, (cudaStream_t)stream);
 }
 
@@ -1060,7 +1108,7 @@ int cev_fdtd_step_D_ex(cev_fdtd* p, const cev_state* st, void* const D_out[3], v
     if (!p || !st) return fail("NULL argument");
     if (check_range(p, x0, x1)) return -1;
     DeviceGuard guard(p->device);
-    const int64_t a0 = p->rot ? 0 : x0, a1 = p->rot ? p->N[0] : x1;
+    const int64_t a0 = p->x_is_x() ? x0 : 0, a1 = p->x_is_x() ? x1 : p->N[0];
     return DISPATCH(p, launch_D, p, st, D_out, E_out, J, J_scale, (const double* const*)nullptr, waveform_row, a0, a1,
                     probe_t, partials, (cudaStream_t)stream);
 }
@@ -1102,7 +1150,7 @@ int cev_fdtd_step_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void
     if (!p || !st) return fail("NULL argument");
     if (check_range(p, x0, x1)) return -1;
     DeviceGuard guard(p->device);
-    const int64_t a0 = p->rot ? 0 : x0, a1 = p->rot ? p->N[0] : x1;
+    const int64_t a0 = p->x_is_x() ? x0 : 0, a1 = p->x_is_x() ? x1 : p->N[0];
     return DISPATCH(p, launch_D, p, st, D_out, E_out, J, J_scale, (const double* const*)nullptr, (const double*)nullptr, a0,
                     a1, (int64_t)-1, (double*)nullptr, (cudaStream_t)stream);
 }

@@ -105,6 +105,7 @@ struct StepArgs {
     // bits 3-5 = H component active (internal order).  The caller guarantees the inactive ones are and stay zero.
     unsigned on;
     int n_tiles, ntz, nty, xchunk;
+    int wz;                   // marching kernels: 1 = the warps of a CTA tile z (grids with a single row per plane)
     int n_boxes;
     Box box[MAX_BOXES];
     int pf_dist;              // L2 prefetch distance in x-planes (0 = off)

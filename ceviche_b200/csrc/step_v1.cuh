@@ -24,8 +24,8 @@ __global__ void __launch_bounds__(V1_TZ* V1_TY) k_step_H_v1(const StepArgs<T, AT
     const int rest = bid / a.ntz;
     const int ty = rest % a.nty;
     const int i = a.x0 + rest / a.nty;
-    const int k = tz * V1_TZ + threadIdx.x;
-    const int j = ty * V1_TY + threadIdx.y;
+    const int k = tz * blockDim.x + threadIdx.x;     // block = 64 x 4 threads, or 256 x 1 for single-row planes
+    const int j = ty * blockDim.y + threadIdx.y;
     if (k >= a.Nz || j >= a.Ny) return;
 
     const int64_t plane = (int64_t)a.Ny * a.Nz;
@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(V1_TZ* V1_TY) k_step_D_v1(const StepArgs<T, AT
     const int rest = bid / a.ntz;
     const int ty = rest % a.nty;
     const int i = a.x0 + rest / a.nty;
-    const int k = tz * V1_TZ + threadIdx.x;
-    const int j = ty * V1_TY + threadIdx.y;
+    const int k = tz * blockDim.x + threadIdx.x;     // block = 64 x 4 threads, or 256 x 1 for single-row planes
+    const int j = ty * blockDim.y + threadIdx.y;
     if (k >= a.Nz || j >= a.Ny) return;
 
     const int64_t plane = (int64_t)a.Ny * a.Nz;

@@ -187,11 +187,22 @@ struct PmlCtx {
 
 // INTERIOR = the launch covers only cells off every PML: all PML code is compiled out (few registers,
 // high occupancy); otherwise the general kernel.
-// MASKED = the component mask a.on is honoured (2-D / 1-D runs); otherwise it is the compile-time constant "all six",
-// every mask test folds away and the code is exactly the unmasked kernel (the runtime tests cost the full-vector
-// kernels 20-50 % on B200: measured, profiles/).
-template <typename T, typename AT, int V, int LZ, bool INTERIOR, bool MASKED = false>
-__global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS : (sizeof(T) == 8 ? V2_H_MIN_CTAS : V2_H_MIN_CTAS + 1)))
+// MASK = which components are live (bits 0-2 E/D, 3-5 H, internal order): 63 = all six, a compile-time constant with
+// which every mask test folds away and the code is exactly the unmasked kernel (runtime tests cost the full-vector
+// kernels 20-50 % on B200: measured, profiles/); MASK_TM / MASK_TE = the two polarisations of a 2-D grid, also
+// compile-time (lean kernels: the dead components cost neither registers nor instructions); -1 = read a.on at run time.
+constexpr int MASK_TM = 0b101010;   // 2-D grids are relabelled (x, z, y): logical {Dz, Hx, Hy} = internal {D_y, H_x, H_z}
+constexpr int MASK_TE = 0b010101;   //                                   logical {Dx, Dy, Hz} = internal {D_x, D_z, H_y}
+// TAN = forward-mode tangent step: the state is a TANGENT state and E = mE*D + dmE*D_primal (product rule on
+// fdtd.py:135-137), same rounding sequence as the baseline kernel; with TAN = false the extra loads fold away.
+template <bool TAN, typename T, typename AT, int V>
+__device__ __forceinline__ AT e_of(const Vec<T, V>& m, const Vec<T, V>& d, const Vec<T, V>& dm, const Vec<T, V>& dp, int e) {
+    const AT x = mul_rn((AT)m.v[e], (AT)d.v[e]);
+    return TAN ? add_rn(x, mul_rn((AT)dm.v[e], (AT)dp.v[e])) : x;
+}
+
+template <typename T, typename AT, int V, int LZ, bool INTERIOR, int MASK = 63, bool TAN = false>
+__global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS : ((TAN && MASK != MASK_TM && MASK != MASK_TE) ? 2 : (sizeof(T) == 8 ? V2_H_MIN_CTAS : V2_H_MIN_CTAS + 1))))
 k_step_H_v2(const StepArgs<T, AT> a) {
     const int bid = blockIdx.x;
     if (bid >= a.n_tiles) {
@@ -211,9 +222,10 @@ k_step_H_v2(const StepArgs<T, AT> a) {
     const int rest = lid / B.ntz;
     const int ty = rest % B.nty;
     const int xc = rest / B.nty;
-    const int jraw = B.y0 + (ty * V2_BY + threadIdx.y) * RW + ly;
+    // warps of the CTA stacked along y (default) or, for single-row planes, along z
+    const int jraw = B.y0 + (a.wz ? ty : ty * V2_BY + threadIdx.y) * RW + ly;
     if (jraw - ly >= B.y1) return;               // warp-uniform: the whole warp is outside the box
-    const int k0raw = B.z0 + (tz * LZ + lz) * V;
+    const int k0raw = B.z0 + ((a.wz ? tz * V2_BY + threadIdx.y : tz) * LZ + lz) * V;
     const bool active = k0raw < B.z1 && jraw < B.y1;
     const int j = jraw < B.y1 ? jraw : B.y1 - 1; // inactive lanes shadow a valid cell (loads only)
     const int k0 = k0raw < B.z1 ? k0raw : B.z0;
@@ -238,7 +250,8 @@ k_step_H_v2(const StepArgs<T, AT> a) {
     }
     const AT s = -a.cdt;
     const AT inv = a.inv_dL;
-    const unsigned onE = MASKED ? (a.on & 7u) : 7u, onH = MASKED ? ((a.on >> 3) & 7u) : 7u;
+    const unsigned on_all = MASK < 0 ? a.on : (unsigned)MASK;
+    const unsigned onE = on_all & 7u, onH = (on_all >> 3) & 7u;
 
     // E = mE*D of the current plane (own cells)
     AT Ecur[3][V];
@@ -248,8 +261,13 @@ k_step_H_v2(const StepArgs<T, AT> a) {
         for (int c = 0; c < 3; ++c) {
             const bool oc = (onE >> c) & 1u;
             const Vec<T, V> d = ldv_if<T, V>(oc, a.Din[c] + o), m = ldv_if<T, V>(oc, a.mE[c] + o);
+            Vec<T, V> td, tm;
+            if (TAN) {
+                td = ldv_if<T, V>(oc, a.Dp[c] + o);
+                tm = ldv_if<T, V>(oc, a.dmE[c] + o);
+            }
 #pragma unroll
-            for (int e = 0; e < V; ++e) Ecur[c][e] = mul_rn((AT)m.v[e], (AT)d.v[e]);
+            for (int e = 0; e < V; ++e) Ecur[c][e] = e_of<TAN, T, AT, V>(m, d, tm, td, e);
         }
     }
 
@@ -258,6 +276,7 @@ k_step_H_v2(const StepArgs<T, AT> a) {
         const bool last = (i + 1 == a.Nx);
         // ---- every load of this iteration, up front
         Vec<T, V> dn[3], mn[3], h[3];
+        Vec<T, V> tdn[3], tmn[3], tdxj, tmxj, tdzj, tmzj;     // tangent steps only: D_primal, d(1/eps)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const T* Dn = last ? a.Dhi[c] : a.Din[c] + pbase + plane;
@@ -265,14 +284,30 @@ k_step_H_v2(const StepArgs<T, AT> a) {
             dn[c] = ldv_if<T, V>((onE >> c) & 1u, Dn + orow);
             mn[c] = ldv_if<T, V>((onE >> c) & 1u, Mn + orow);
             h[c] = ldv_if<T, V>((onH >> c) & 1u, a.Hin[c] + pbase + orow);
+            if (TAN) {
+                tdn[c] = ldv_if<T, V>((onE >> c) & 1u, (last ? a.Dphi[c] : a.Dp[c] + pbase + plane) + orow);
+                tmn[c] = ldv_if<T, V>((onE >> c) & 1u, (last ? a.dmEhi[c] : a.dmE[c] + pbase + plane) + orow);
+            }
         }
         const Vec<T, V> dxj = ldv_if<T, V>(onE & 1u, a.Din[0] + pbase + orow_jp), mxj = ldv_if<T, V>(onE & 1u, a.mE[0] + pbase + orow_jp);
         const Vec<T, V> dzj = ldv_if<T, V>(onE & 4u, a.Din[2] + pbase + orow_jp), mzj = ldv_if<T, V>(onE & 4u, a.mE[2] + pbase + orow_jp);
+        if (TAN) {
+            tdxj = ldv_if<T, V>(onE & 1u, a.Dp[0] + pbase + orow_jp);
+            tmxj = ldv_if<T, V>(onE & 1u, a.dmE[0] + pbase + orow_jp);
+            tdzj = ldv_if<T, V>(onE & 4u, a.Dp[2] + pbase + orow_jp);
+            tmzj = ldv_if<T, V>(onE & 4u, a.dmE[2] + pbase + orow_jp);
+        }
         AT ex_kp = __shfl_down_sync(0xffffffffu, Ecur[0][0], 1);
         AT ey_kp = __shfl_down_sync(0xffffffffu, Ecur[1][0], 1);
         if (z_edge) {
-            if (onE & 1u) ex_kp = mul_rn((AT)a.mE[0][pbase + okp], (AT)a.Din[0][pbase + okp]);
-            if (onE & 2u) ey_kp = mul_rn((AT)a.mE[1][pbase + okp], (AT)a.Din[1][pbase + okp]);
+            if (onE & 1u) {
+                ex_kp = mul_rn((AT)a.mE[0][pbase + okp], (AT)a.Din[0][pbase + okp]);
+                if (TAN) ex_kp = add_rn(ex_kp, mul_rn((AT)a.dmE[0][pbase + okp], (AT)a.Dp[0][pbase + okp]));
+            }
+            if (onE & 2u) {
+                ey_kp = mul_rn((AT)a.mE[1][pbase + okp], (AT)a.Din[1][pbase + okp]);
+                if (TAN) ey_kp = add_rn(ey_kp, mul_rn((AT)a.dmE[1][pbase + okp], (AT)a.Dp[1][pbase + okp]));
+            }
         }
         if (a.pf_dist > 0 && i + a.pf_dist < a.x1) {   // next plane(s) of every stream into L2, also across the chunk end
             const int ip = i + a.pf_dist;
@@ -284,6 +319,10 @@ k_step_H_v2(const StepArgs<T, AT> a) {
                     if (ip + 1 < a.Nx && ((onE >> c) & 1u)) {
                         prefetch_l2(a.Din[c] + po + plane);
                         prefetch_l2(a.mE[c] + po + plane);
+                        if (TAN) {
+                            prefetch_l2(a.Dp[c] + po + plane);
+                            prefetch_l2(a.dmE[c] + po + plane);
+                        }
                     }
                 }
             }
@@ -303,21 +342,21 @@ k_step_H_v2(const StepArgs<T, AT> a) {
 #pragma unroll
         for (int e = 0; e < V; ++e) {
             const AT Ex = Ecur[0][e], Ey = Ecur[1][e], Ez = Ecur[2][e];
-            const AT Ex_jp = mul_rn((AT)mxj.v[e], (AT)dxj.v[e]);
-            const AT Ez_jp = mul_rn((AT)mzj.v[e], (AT)dzj.v[e]);
+            const AT Ex_jp = e_of<TAN, T, AT, V>(mxj, dxj, tmxj, tdxj, e);
+            const AT Ez_jp = e_of<TAN, T, AT, V>(mzj, dzj, tmzj, tdzj, e);
             const AT Ex_kp = (e + 1 < V) ? Ecur[0][(e + 1) % V] : ex_kp;
             const AT Ey_kp = (e + 1 < V) ? Ecur[1][(e + 1) % V] : ey_kp;
-            const AT Ey_ip = mul_rn((AT)mn[1].v[e], (AT)dn[1].v[e]);
-            const AT Ez_ip = mul_rn((AT)mn[2].v[e], (AT)dn[2].v[e]);
+            const AT Ey_ip = e_of<TAN, T, AT, V>(mn[1], dn[1], tmn[1], tdn[1], e);
+            const AT Ez_ip = e_of<TAN, T, AT, V>(mn[2], dn[2], tmn[2], tdn[2], e);
             CE[0][e] = curl2<AT>(Ez_jp, Ez, Ey_kp, Ey, inv);
             CE[1][e] = curl2<AT>(Ex_kp, Ex, Ez_ip, Ez, inv);
             CE[2][e] = curl2<AT>(Ey_ip, Ey, Ex_jp, Ex, inv);
         }
 #pragma unroll
         for (int e = 0; e < V; ++e) {
-            Ecur[0][e] = mul_rn((AT)mn[0].v[e], (AT)dn[0].v[e]);
-            Ecur[1][e] = mul_rn((AT)mn[1].v[e], (AT)dn[1].v[e]);
-            Ecur[2][e] = mul_rn((AT)mn[2].v[e], (AT)dn[2].v[e]);
+            Ecur[0][e] = e_of<TAN, T, AT, V>(mn[0], dn[0], tmn[0], tdn[0], e);
+            Ecur[1][e] = e_of<TAN, T, AT, V>(mn[1], dn[1], tmn[1], tdn[1], e);
+            Ecur[2][e] = e_of<TAN, T, AT, V>(mn[2], dn[2], tmn[2], tdn[2], e);
         }
 
         // ---- update
@@ -341,7 +380,7 @@ k_step_H_v2(const StepArgs<T, AT> a) {
 
 // EXTRAS = dense J input and/or E output (the per-step forward() API); the fused run() path
 // instantiates EXTRAS = false and carries neither.
-template <typename T, typename AT, int V, int LZ, bool EXTRAS, bool INTERIOR, bool MASKED = false>
+template <typename T, typename AT, int V, int LZ, bool EXTRAS, bool INTERIOR, int MASK = 63>
 __global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS : V2_D_MIN_CTAS)) k_step_D_v2(const StepArgs<T, AT> a) {
     const int bid = blockIdx.x;
     if (bid >= a.n_tiles) {
@@ -361,9 +400,9 @@ __global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS :
     const int rest = lid / B.ntz;
     const int ty = rest % B.nty;
     const int xc = rest / B.nty;
-    const int jraw = B.y0 + (ty * V2_BY + threadIdx.y) * RW + ly;
+    const int jraw = B.y0 + (a.wz ? ty : ty * V2_BY + threadIdx.y) * RW + ly;
     const bool warp_on = jraw - ly < B.y1;       // warp-uniform; no early return: the CTA meets at a barrier below
-    const int k0raw = B.z0 + (tz * LZ + lz) * V;
+    const int k0raw = B.z0 + ((a.wz ? tz * V2_BY + threadIdx.y : tz) * LZ + lz) * V;
     const bool active = k0raw < B.z1 && jraw < B.y1;
     const int j = jraw < B.y1 ? jraw : B.y1 - 1; // inactive lanes shadow a valid cell (loads only)
     const int k0 = k0raw < B.z1 ? k0raw : B.z0;
@@ -388,7 +427,8 @@ __global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS :
     }
     const AT s = a.cdt;
     const AT inv = a.inv_dL;
-    const unsigned onE = MASKED ? (a.on & 7u) : 7u, onH = MASKED ? ((a.on >> 3) & 7u) : 7u;
+    const unsigned on_all = MASK < 0 ? a.on : (unsigned)MASK;
+    const unsigned onE = on_all & 7u, onH = (on_all >> 3) & 7u;
 
     // H of the previous plane (own cells), y and z components
     AT Hprev[2][V];
