@@ -113,6 +113,25 @@ struct cev_fdtd {
     std::vector<int32_t> slot_probe;
     DeviceBuf pr_field, pr_wbegin, pr_ibegin, pr_cell0, pr_n, pr_idx, pr_weight, pr_owner;
 
+    // CUDA graphs of the caller loop for launch-bound (small) grids: blocks of GRAPH_K time steps captured once
+    // per (state pointers, sources/probes/options epoch) and replayed; waveform rows and probe partial sums go
+    // through plan-owned staging buffers so that the captured launches are completely static.
+    struct RunGraph {
+        cudaGraphExec_t exec = nullptr;
+        cev_state st;
+        uint64_t epoch = 0;
+    };
+    std::vector<RunGraph> graphs;
+    DeviceBuf stage_w, stage_p;
+    cudaStream_t cap_stream = nullptr;
+    uint64_t epoch = 1;          // bumped whenever sources, probes or options change
+    int use_graph = -1;          // -1 auto (small grids), 0 never, 1 whenever possible
+    void drop_graphs() {
+        for (auto& g : graphs)
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+        graphs.clear();
+    }
+
     int to_internal(int logical_axis) const { return inv[logical_axis]; }
     int to_logical(int internal_axis) const { return perm[internal_axis]; }
     bool x_is_x() const { return perm[0] == 0; }     // logical x-ranges / x-halo planes are internal ones
@@ -254,7 +273,7 @@ void set_tiles_v2(const cev_fdtd* p, StepArgs<T, AT>& a, int64_t x0, int64_t x1,
         if (lz_override) chunk = 16;      // TMA-staged kernels: longer chunks amortise the pipeline fill
         if (wz) {                         // a plane is one row: longer chunks amortise the carried-in plane
             chunk = 32;
-            while (chunk > 1 && (int64_t)cols * ((x1 - x0 + chunk - 1) / chunk) < 148 * 8) chunk /= 2;
+            while (chunk > 1 && (int64_t)cols * ((x1 - x0 + chunk - 1) / chunk) < 148 * 4) chunk /= 2;   // tuned: scripts/tune2d.py
         }
     }
     a.xchunk = chunk;
@@ -632,11 +651,85 @@ int launch_compute_E(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, v
     return 0;
 }
 
+constexpr int GRAPH_K = 50;              // time steps per captured block
+constexpr int64_t GRAPH_MAX_CELLS = 1 << 18;   // auto: grids whose half-step kernels are shorter than a launch
+
+// The graph of GRAPH_K steps for this state (captured on first use).  Row q of stage_p stands for step base-1+q.
+template <typename T, typename AT>
+int get_run_graph(cev_fdtd* p, const cev_state* st, cudaGraphExec_t* out) {
+    if (!p->graphs.empty() && p->graphs[0].epoch != p->epoch) p->drop_graphs();
+    for (auto& g : p->graphs)
+        if (!memcmp(&g.st, st, sizeof(cev_state))) {
+            *out = g.exec;
+            return 0;
+        }
+    if (p->graphs.empty()) {
+        if (p->stage_w.alloc((size_t)GRAPH_K * std::max(1, p->nsrc) * 8) ||
+            p->stage_p.alloc((size_t)(GRAPH_K + 1) * std::max(1, p->n_slots) * 8))
+            return -1;
+    }
+    if (!p->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
+    const int64_t Nx = p->N[0];
+    double* sp = (double*)p->stage_p.p;
+    const double* sw = p->n_src_pts > 0 ? (const double*)p->stage_w.p : nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeRelaxed));
+    int rc = 0;
+    for (int r = 0; r < GRAPH_K && !rc; ++r) {
+        rc = launch_H<T, AT>(p, st, nullptr, nullptr, 0, Nx, r, sp, p->cap_stream);
+        if (!rc)
+            rc = launch_D<T, AT>(p, st, nullptr, nullptr, nullptr, nullptr, nullptr, sw ? sw + (int64_t)r * p->nsrc : nullptr, 0,
+                                 Nx, r + 1, sp, p->cap_stream);
+    }
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(p->cap_stream, &graph);
+    if (rc || e != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc ? rc : fail("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    }
+    cev_fdtd::RunGraph g;
+    const cudaError_t e2 = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(e2));
+    g.st = *st;
+    g.epoch = p->epoch;
+    if (p->graphs.size() >= 4) {
+        cudaGraphExecDestroy(p->graphs[0].exec);
+        p->graphs.erase(p->graphs.begin());
+    }
+    p->graphs.push_back(g);
+    *out = g.exec;
+    return 0;
+}
+
 template <typename T, typename AT>
 int run_loop(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* waveform, double* partials,
              cudaStream_t s) {
     const int64_t Nx = p->N[0];
-    for (int64_t n = 0; n < nsteps; ++n) {
+    int64_t n0 = 0;
+    const int64_t cells = (int64_t)p->N[0] * p->N[1] * p->N[2];
+    const bool graphs = p->use_graph == 1 || (p->use_graph < 0 && cells <= GRAPH_MAX_CELLS);
+    if (graphs && nsteps >= 2 * GRAPH_K + 1) {
+        // step 0 the ordinary way (it also builds the source tilings and sets kernel attributes), then whole blocks
+        if (launch_H<T, AT>(p, st, nullptr, nullptr, 0, Nx, -1, partials, s)) return -1;
+        if (launch_D<T, AT>(p, st, nullptr, nullptr, nullptr, nullptr, nullptr, waveform, 0, Nx, 0, partials, s)) return -1;
+        cudaGraphExec_t exec = nullptr;
+        if (get_run_graph<T, AT>(p, st, &exec)) return -1;
+        const int ns = p->n_slots, nED = p->n_slots_ED;
+        for (n0 = 1; n0 + GRAPH_K <= nsteps; n0 += GRAPH_K) {
+            if (waveform)
+                CUDA_TRY(cudaMemcpyAsync(p->stage_w.p, waveform + n0 * p->nsrc, (size_t)GRAPH_K * p->nsrc * 8,
+                                         cudaMemcpyDeviceToDevice, s));
+            CUDA_TRY(cudaGraphLaunch(exec, s));
+            const double* sp = (const double*)p->stage_p.p;
+            if (nED > 0)       // E/D-family slots: staging rows 0..K-1 are steps n0-1 .. n0+K-2
+                CUDA_TRY(cudaMemcpy2DAsync(partials + (n0 - 1) * ns, (size_t)ns * 8, sp, (size_t)ns * 8, (size_t)nED * 8,
+                                           GRAPH_K, cudaMemcpyDeviceToDevice, s));
+            if (ns > nED)      // H-family slots: staging rows 1..K are steps n0 .. n0+K-1
+                CUDA_TRY(cudaMemcpy2DAsync(partials + n0 * ns + nED, (size_t)ns * 8, sp + ns + nED, (size_t)ns * 8,
+                                           (size_t)(ns - nED) * 8, GRAPH_K, cudaMemcpyDeviceToDevice, s));
+        }
+    }
+    for (int64_t n = n0; n < nsteps; ++n) {
         // E/D probes of step n-1 ride on the H launch of step n (D is read-only there);
         // H probes of step n ride on its D launch (H is read-only there).
         if (launch_H<T, AT>(p, st, nullptr, nullptr, 0, Nx, n - 1, partials, s)) return -1;
@@ -1022,6 +1115,9 @@ int cev_fdtd_create(cev_fdtd** out, int device, int dtype, int arith_f64, int64_
 int cev_fdtd_destroy(cev_fdtd* p) {
     if (!p) return 0;
     DeviceGuard guard(p->device);
+    p->drop_graphs();
+    p->stage_w.release(); p->stage_p.release();
+    if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
     p->tables.release();
     p->src_comp.release(); p->src_id.release(); p->src_cell.release(); p->src_weight.release();
     for (auto& t : p->src_tilings) {
@@ -1035,7 +1131,11 @@ int cev_fdtd_destroy(cev_fdtd* p) {
 
 int cev_fdtd_set_option(cev_fdtd* p, const char* name, int64_t value) {
     if (!p || !name) return fail("NULL argument");
-    if (!strcmp(name, "kernel_variant")) {
+    p->epoch++;
+    if (!strcmp(name, "use_graph")) {
+        if (value < -1 || value > 1) return fail("use_graph must be -1 (auto: small grids), 0 or 1");
+        p->use_graph = (int)value;
+    } else if (!strcmp(name, "kernel_variant")) {
         if (value < 0 || value > 4) return fail("kernel_variant must be 0 (auto), 1 (baseline), 2 (marching), 3 (TMA-staged) or 4 (fused)");
         p->variant = (int)value;
     } else if (!strcmp(name, "fused_shape")) {
@@ -1172,6 +1272,7 @@ int cev_fdtd_set_sources(cev_fdtd* p, int nsrc, const cev_points* src) {
         if (src[s].n > ncell) return fail("source %d: more points than cells", s);
         total += src[s].n;
     }
+    p->epoch++;
     p->nsrc = nsrc;
     p->n_src_pts = total;
     if (p->src_comp.alloc(total * 4) || p->src_id.alloc(total * 4) || p->src_cell.alloc(total * 8) || p->src_weight.alloc(total * 8)) return -1;
@@ -1267,6 +1368,7 @@ int cev_fdtd_set_probes(cev_fdtd* p, int nprobe, const cev_points* probe, int64_
         CUDA_TRY(cudaMemcpy((double*)p->pr_weight.p + woff[q], P.weight, P.n * 8, cudaMemcpyDeviceToDevice));
         if (P.idx) CUDA_TRY(cudaMemcpy((int64_t*)p->pr_idx.p + ioff[q], P.idx, P.n * 8, cudaMemcpyDeviceToDevice));
     }
+    p->epoch++;
     p->nprobe = nprobe;
     p->n_slots = ns;
     p->n_slots_ED = nED;

@@ -246,3 +246,41 @@ def test_tangent_marching_equals_baseline_bitwise(shape, npml, comps, dtype):
             assert np.array_equal(x, y)
     for k in FIELD_KEYS:
         assert np.array_equal(f1[k], f0[k]), k
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("shape,npml,comps", [((24, 20, 40), (4, 3, 5), "xyz"), ((60, 48, 1), (6, 5, 0), "z"),
+                                              ((31, 17, 1), (5, 4, 0), "x")])
+def test_graph_replay_equals_plain_launches(shape, npml, comps, dtype):
+    """CUDA-graph replay of the caller loop (blocks of 50 steps through staging buffers) against the plain
+    launch loop: series (both probe families), fields and PML integrals, over several run() legs on one object
+    (graph cache hits, new state pointers, changed sources)."""
+    import ceviche_b200
+    rng = np.random.default_rng(3)
+    steps = 173
+    eps = 1 + 3 * rng.random(shape)
+    mid = tuple(n // 2 for n in shape)
+    src = [(c, cases.one_hot(shape, mid, 2.0) + rng.random(shape) * (rng.random(shape) < 0.03),
+            cases.modulated(steps, steps / 3, steps / 8, 9.0, 2.0)) for c in comps]
+    probes = [(k, rng.random(shape)) for k in ("Ez", "Hx", "Dx", "Hy", "Ey", "Hz")]
+    res = []
+    for graph in (0, 1):
+        F = ceviche_b200.fdtd(eps, cases.DL, list(npml), dtype=dtype)
+        F.set_option("use_graph", graph)
+        legs = [F.run(steps, src, probes).cpu().numpy()]
+        F.prepare(src, probes)
+        wf = torch.as_tensor(np.stack([w for _, _, w in src], 1)).cuda()
+        legs.append(F.run(steps, waveforms=wf).cpu().numpy())          # prepared sources: no epoch change
+        legs.append(F.run(120, waveforms=wf[:120]).cpu().numpy())
+        legs.append(F.run(101, [(c, p * 0.5, w[:101]) for c, p, w in src], probes[:3]).cpu().numpy())   # new tables
+        legs.append(F.run(60, waveforms=wf[:60]).cpu().numpy())         # too short for a graph
+        res.append((legs, {k: F.fields[k].cpu().numpy() for k in FIELD_KEYS},
+                    [t.cpu().numpy() for fam in ("ICE", "IH", "ICH", "ID") for t in F._pml[fam]]))
+    (l0, f0, p0), (l1, f1, p1) = res
+    for a, b in zip(l0, l1):
+        assert np.array_equal(a, b)
+    assert np.abs(l1[0]).max() > 0
+    for k in FIELD_KEYS:
+        assert np.array_equal(f0[k], f1[k]), k
+    for a, b in zip(p0, p1):
+        assert np.array_equal(a, b)
