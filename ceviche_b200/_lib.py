@@ -64,6 +64,8 @@ def _declare(lib):
         "cev_fdtd_set_sources": [C.c_void_p, C.c_int, P(cev_points)],
         "cev_fdtd_set_probes": [C.c_void_p, C.c_int, P(cev_points), P(C.c_int64)],
         "cev_fdtd_probe_slots": [C.c_void_p, P(C.c_int32)],
+        "cev_fdtd_set_monitors": [C.c_void_p, C.c_int, P(cev_points), C.c_int, P(C.c_int64)],
+        "cev_fdtd_bind_monitors": [C.c_void_p, C.c_void_p, C.c_void_p],
         "cev_fdtd_run": [C.c_void_p, P(cev_state), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
         "cev_fdtd_run_fused": [C.c_void_p, P(cev_state), P(cev_state), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
     }
@@ -77,7 +79,7 @@ def _declare(lib):
 EXPORTS = ("cev_last_error", "cev_abi_version", "cev_fdtd_create", "cev_fdtd_destroy", "cev_fdtd_pml_shapes",
            "cev_fdtd_set_option",
            "cev_fdtd_step_H", "cev_fdtd_step_D", "cev_fdtd_compute_E", "cev_fdtd_set_sources",
-           "cev_fdtd_set_probes", "cev_fdtd_probe_slots", "cev_fdtd_run", "cev_fdtd_run_fused", "cev_fdtd_step_H_ex", "cev_fdtd_step_D_ex",
+           "cev_fdtd_set_probes", "cev_fdtd_probe_slots", "cev_fdtd_set_monitors", "cev_fdtd_bind_monitors", "cev_fdtd_run", "cev_fdtd_run_fused", "cev_fdtd_step_H_ex", "cev_fdtd_step_D_ex",
            "cev_fdtd_sample_probes", "cev_fdtd_jvp_run", "cev_fdtd_adjoint_step", "cev_fdtd_adjoint_seed")
 
 

@@ -112,6 +112,12 @@ struct cev_fdtd {
     int nprobe = 0, n_slots = 0, n_slots_ED = 0;
     std::vector<int32_t> slot_probe;
     DeviceBuf pr_field, pr_wbegin, pr_ibegin, pr_cell0, pr_n, pr_idx, pr_weight, pr_owner;
+    // running-DFT monitors
+    int64_t n_mon_pts = 0;
+    int mon_nfreq = 0;
+    DeviceBuf mon_field, mon_cell;
+    const double* mon_phasors = nullptr;   // bound per run: [nsteps, nfreq, 2]
+    double* mon_acc = nullptr;             // [n_mon_pts, nfreq, 2]
 
     // CUDA graphs of the caller loop for launch-bound (small) grids: blocks of GRAPH_K time steps captured once
     // per (state pointers, sources/probes/options epoch) and replayed; waveform rows and probe partial sums go
@@ -651,6 +657,23 @@ int launch_compute_E(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, v
     return 0;
 }
 
+// Monitors see the state after step n (H_n, D_n both final after the D launch).
+template <typename T, typename AT>
+int launch_monitors(cev_fdtd* p, const cev_state* st, int64_t n, cudaStream_t s) {
+    if (p->n_mon_pts == 0 || !p->mon_acc) return 0;
+    StepArgs<T, AT> a;
+    if (fill_args(p, st, a)) return -1;
+    MonitorTable m;
+    m.n = p->n_mon_pts;
+    m.nfreq = p->mon_nfreq;
+    m.field = (const int32_t*)p->mon_field.p;
+    m.cell = (const int64_t*)p->mon_cell.p;
+    const int bs = 128;
+    k_monitor<T, AT><<<(unsigned)((m.n + bs - 1) / bs), bs, 0, s>>>(a, m, p->mon_phasors + n * p->mon_nfreq * 2, p->mon_acc);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 constexpr int GRAPH_K = 50;              // time steps per captured block
 constexpr int64_t GRAPH_MAX_CELLS = 1 << 18;   // auto: grids whose half-step kernels are shorter than a launch
 
@@ -707,7 +730,8 @@ int run_loop(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* wav
     const int64_t Nx = p->N[0];
     int64_t n0 = 0;
     const int64_t cells = (int64_t)p->N[0] * p->N[1] * p->N[2];
-    const bool graphs = p->use_graph == 1 || (p->use_graph < 0 && cells <= GRAPH_MAX_CELLS);
+    const bool monitors = p->n_mon_pts > 0 && p->mon_acc;     // (their phasor row changes every step: no graph replay)
+    const bool graphs = !monitors && (p->use_graph == 1 || (p->use_graph < 0 && cells <= GRAPH_MAX_CELLS));
     if (graphs && nsteps >= 2 * GRAPH_K + 1) {
         // step 0 the ordinary way (it also builds the source tilings and sets kernel attributes), then whole blocks
         if (launch_H<T, AT>(p, st, nullptr, nullptr, 0, Nx, -1, partials, s)) return -1;
@@ -736,6 +760,7 @@ int run_loop(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* wav
         if (launch_D<T, AT>(p, st, nullptr, nullptr, nullptr, nullptr, nullptr, waveform ? waveform + n * p->nsrc : nullptr, 0,
                             Nx, n, partials, s))
             return -1;
+        if (monitors && launch_monitors<T, AT>(p, st, n, s)) return -1;
     }
     if (nsteps > 0 && launch_probe_only<T, AT>(p, st, nullptr, 0, nsteps - 1, partials, s)) return -1;
     return 0;
@@ -1125,6 +1150,7 @@ int cev_fdtd_destroy(cev_fdtd* p) {
     }
     p->pr_field.release(); p->pr_wbegin.release(); p->pr_ibegin.release(); p->pr_cell0.release();
     p->pr_n.release(); p->pr_idx.release(); p->pr_weight.release(); p->pr_owner.release();
+    p->mon_field.release(); p->mon_cell.release();
     delete p;
     return 0;
 }
@@ -1374,6 +1400,46 @@ int cev_fdtd_set_probes(cev_fdtd* p, int nprobe, const cev_points* probe, int64_
     p->n_slots_ED = nED;
     p->slot_probe = owner;
     if (n_slots_out) *n_slots_out = ns;
+    return 0;
+}
+
+int cev_fdtd_set_monitors(cev_fdtd* p, int nmon, const cev_points* mon, int nfreq, int64_t* n_points) {
+    if (!p || nmon < 0 || (nmon > 0 && !mon) || nfreq < 0) return fail("bad monitor arguments");
+    DeviceGuard guard(p->device);
+    const int64_t ncell = p->Nl[0] * p->Nl[1] * p->Nl[2];
+    int64_t total = 0;
+    for (int m = 0; m < nmon; ++m) {
+        if (mon[m].field < 0 || mon[m].field > 8) return fail("monitor %d: field code must be 0..8", m);
+        if (mon[m].n < 0 || (mon[m].n > 0 && !mon[m].idx)) return fail("monitor %d: needs an index array", m);
+        total += mon[m].n;
+    }
+    p->epoch++;
+    p->mon_phasors = nullptr;
+    p->mon_acc = nullptr;
+    p->n_mon_pts = total;
+    p->mon_nfreq = nfreq;
+    if (p->mon_field.alloc(total * 4) || p->mon_cell.alloc(total * 8)) return -1;
+    int64_t off = 0;
+    for (int m = 0; m < nmon; ++m) {
+        if (mon[m].n == 0) continue;
+        std::vector<int32_t> f(mon[m].n, (mon[m].field / 3) * 3 + p->to_internal(mon[m].field % 3));
+        std::vector<int64_t> cells(mon[m].n);
+        CUDA_TRY(cudaMemcpy(cells.data(), mon[m].idx, mon[m].n * 8, cudaMemcpyDeviceToHost));
+        for (int64_t q = 0; q < mon[m].n; ++q)
+            if (cells[q] < 0 || cells[q] >= ncell) return fail("monitor %d: point outside the grid", m);
+        CUDA_TRY(cudaMemcpy((int32_t*)p->mon_field.p + off, f.data(), mon[m].n * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy((int64_t*)p->mon_cell.p + off, mon[m].idx, mon[m].n * 8, cudaMemcpyDeviceToDevice));
+        off += mon[m].n;
+    }
+    if (n_points) *n_points = total;
+    return 0;
+}
+
+int cev_fdtd_bind_monitors(cev_fdtd* p, const double* phasors, double* acc) {
+    if (!p) return fail("NULL argument");
+    if ((phasors == nullptr) != (acc == nullptr)) return fail("phasors and acc must both be given or both be NULL");
+    p->mon_phasors = phasors;
+    p->mon_acc = acc;
     return 0;
 }
 

@@ -221,4 +221,27 @@ __global__ void k_probe_only(const StepArgs<T, AT> a) {
     probe_block<T, AT>(a, a.aux_slot0 + blockIdx.x);
 }
 
+// Running-DFT monitors: acc[q, f] += field(point q) * phasor[f] once per time step (the frequency-domain field
+// of a region without storing its time series; the natural producer of mode-overlap objectives,
+// ceviche/utils.py:373-400 computes the same sums from stored series with an FFT).  One thread per point; the
+// accumulators are complex fp64 (re, im interleaved).
+struct MonitorTable {
+    int64_t        n;        // total points of all monitors
+    int            nfreq;
+    const int32_t* field;    // per point: CEV_FIELD_* + internal component
+    const int64_t* cell;
+};
+template <typename T, typename AT>
+__global__ void k_monitor(const StepArgs<T, AT> a, MonitorTable m, const double* __restrict__ phasor_row,
+                          double* __restrict__ acc) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m.n) return;
+    const double v = (double)probe_value<T, AT>(a, m.field[q], m.cell[q]);
+    double* o = acc + q * m.nfreq * 2;
+    for (int f = 0; f < m.nfreq; ++f) {
+        o[2 * f] += v * phasor_row[2 * f];
+        o[2 * f + 1] += v * phasor_row[2 * f + 1];
+    }
+}
+
 }  // namespace cev

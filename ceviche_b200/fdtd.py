@@ -227,6 +227,7 @@ class fdtd:
             for name, value in self._options.items():
                 _lib.check(self._plan.lib.cev_fdtd_set_option(self._plan.handle, name.encode(), int(value)))
             self._n_sources = self._n_probes = self._n_slots = 0
+            self._n_mon_pts, self._mon_counts, self._mon_acc, self._mon_freqs, self.monitor_points = 0, [], None, None, []
             self._source_mask = 0
             self._slot_fold = None
         return self._plan
@@ -260,6 +261,8 @@ class fdtd:
     def initialize_fields(self):
         """fdtd.py:147-211: zero state, t_index = 0, a NEW fields dict."""
         self.t_index = 0
+        if self.__dict__.get("_mon_acc") is not None:
+            self._mon_acc.zero_()
         self._shadow = None         # ping-pong scratch of the fused kernel (allocated on first use)
         self._active = 0            # components that may be non-zero (bits 0-2 D/E, 3-5 H)
         z = lambda: [torch.zeros(self.grid_shape, dtype=self.dtype, device=self.device) for _ in range(3)]
@@ -397,6 +400,48 @@ class fdtd:
         self._n_probes = len(probes)
         self._n_slots = n_slots.value
 
+    def set_monitors(self, monitors, freqs):
+        """Running-DFT monitors: [(field key 'Ex'..'Hz', mask array)] (the non-zero cells of the mask are monitored)
+        at the frequencies `freqs` (Hz).  While run() advances, F_m(f)[q] = sum_n field_q(n) exp(-2 pi i f n dt)
+        is accumulated on the device (n = time-step index since initialize_fields(), i.e. the convention of
+        np.fft.fft over the stored series, ceviche/utils.py:383-386, without storing the series).
+        Read with monitor_values(); `monitor_points[m]` are the flat cell indices of monitor m."""
+        plan = self._ensure_plan()
+        freqs = np.atleast_1d(np.asarray(freqs, dtype=np.float64))
+        keep = []
+        pts = (_lib.cev_points * max(1, len(monitors)))()
+        self.monitor_points, self._mon_counts = [], []
+        for m, (key, mask) in enumerate(monitors):
+            if not torch.is_tensor(mask):
+                mask = torch.as_tensor(np.asarray(mask))
+            mask = reshape_to_ND(mask.to(self.device), 3).expand(self.grid_shape).reshape(-1)
+            nz = torch.nonzero(mask).reshape(-1).contiguous()
+            pts[m].field, pts[m].n, pts[m].idx, pts[m].cell0, pts[m].weight = _FIELD_CODE[key], nz.numel(), _ptr(nz), 0, None
+            keep.append(nz)
+            self.monitor_points.append(nz)
+            self._mon_counts.append(int(nz.numel()))
+        n_pts = C.c_int64()
+        with torch.cuda.device(self.device):
+            _lib.check(plan.lib.cev_fdtd_set_monitors(plan.handle, len(monitors), pts, len(freqs), C.byref(n_pts)))
+        self._n_mon_pts = n_pts.value
+        self._mon_freqs = freqs
+        self._mon_acc = torch.zeros((self._n_mon_pts, len(freqs), 2), dtype=torch.float64, device=self.device)
+
+    def reset_monitors(self):
+        if self._mon_acc is not None:
+            self._mon_acc.zero_()
+
+    def monitor_values(self):
+        """[complex128 tensor (n_freq, n_points_m) per monitor]: the accumulated DFT sums."""
+        if self._mon_acc is None:
+            return []
+        z = torch.view_as_complex(self._mon_acc)           # (points, freqs)
+        out, off = [], 0
+        for n in self._mon_counts:
+            out.append(z[off:off + n].transpose(0, 1).contiguous())
+            off += n
+        return out
+
     def prepare(self, sources=(), probes=()):
         """Upload source profiles [(component, profile)] and probe masks [(field key, mask)] once;
         later `run(steps, waveforms=...)` calls with sources=None reuse them."""
@@ -431,7 +476,7 @@ class fdtd:
         self._drive(self._source_mask)
         return waveforms
 
-    def run(self, steps, sources=None, probes=None, waveforms=None, checkpoint_every=None):
+    def run(self, steps, sources=None, probes=None, waveforms=None, checkpoint_every=None, monitors=None, freqs=None):
         """`steps` fused time steps: the loop of ceviche/utils.py:325-331 on the device.
 
         sources: [(component, profile, waveform[steps])]  (or (component, profile) with
@@ -443,6 +488,8 @@ class fdtd:
         from . import autodiff
         steps = int(steps)
         waveforms = self._prepare_run(steps, sources, probes, waveforms)
+        if monitors is not None:
+            self.set_monitors(monitors, freqs)
         if autodiff.needs_grad(self, []):
             return autodiff.run(self, steps, waveforms, checkpoint_every)
         return self._run_raw(steps, waveforms)
@@ -464,7 +511,13 @@ class fdtd:
                 self._published = False
             partials = torch.zeros((steps, self._n_slots), dtype=torch.float64, device=self.device)
             st = self._state()
-            if self._use_fused(steps):
+            monitoring = self._n_mon_pts > 0 and steps > 0
+            if monitoring:      # phasors of this leg: exp(-2 pi i f n dt), n counted from initialize_fields()
+                n = torch.arange(self.t_index, self.t_index + steps, dtype=torch.float64, device=self.device)
+                ang = (-2 * np.pi * self.dt) * n[:, None] * torch.as_tensor(self._mon_freqs, device=self.device)[None, :]
+                phasors = torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).contiguous()
+                _lib.check(plan.lib.cev_fdtd_bind_monitors(plan.handle, _ptr(phasors), _ptr(self._mon_acc)))
+            if self._use_fused(steps) and not monitoring:
                 # one kernel per time step (H and D half-steps fused): needs ping-pong scratch for H, D, ICE, IH
                 sh = self._shadow_state()
                 _lib.check(plan.lib.cev_fdtd_run_fused(plan.handle, C.byref(st), C.byref(sh), steps, _ptr(waveforms),
@@ -472,6 +525,8 @@ class fdtd:
             else:
                 _lib.check(plan.lib.cev_fdtd_run(plan.handle, C.byref(st), steps, _ptr(waveforms), _ptr(partials),
                                                  self._stream()))
+            if monitoring:      # detach: other callers of the C loop (the adjoint's recomputation) must not accumulate
+                _lib.check(plan.lib.cev_fdtd_bind_monitors(plan.handle, None, None))
             self.t_index += steps
             if refresh:
                 self._refresh_E()

@@ -152,6 +152,15 @@ int cev_fdtd_set_probes(cev_fdtd* plan, int nprobe, const cev_points* probe, int
 /* slot -> probe map (host array of n_slots ints) so the caller can fold partial sums. */
 int cev_fdtd_probe_slots(const cev_fdtd* plan, int32_t* slot_probe);
 
+/* Running-DFT monitors (frequency-domain fields of a region without storing its time series; replaces
+ * storing field snapshots and transforming them, ceviche/utils.py:316-332 + 373-400).  Each monitor is a
+ * point set (field code + idx; weights unused).  cev_fdtd_bind_monitors attaches, for the following
+ * cev_fdtd_run calls, phasors = device double [nsteps, nfreq, 2] (re, im of exp(-i w_f t_n)) and
+ * acc = device double [n_points, nfreq, 2], points in monitor order: after step n of a run,
+ * acc[q, f] += field_q * phasors[n, f].  Bind (NULL, NULL) to detach. */
+int cev_fdtd_set_monitors(cev_fdtd* plan, int nmon, const cev_points* mon, int nfreq, int64_t* n_points);
+int cev_fdtd_bind_monitors(cev_fdtd* plan, const double* phasors, double* acc);
+
 /* nsteps fused leap-frog steps with in-kernel source injection and probe sampling.
  * waveform: device double [nsteps, nsrc]; partials: device double [nsteps, n_slots]
  * (series[t, p] = sum of the slots of p, in slot order: deterministic). */

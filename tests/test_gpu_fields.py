@@ -175,3 +175,46 @@ def test_edge_cases_empty_inputs():
     g = O.step(Jy=hot)
     for k in FIELD_KEYS:
         assert rel_l2(f[k].cpu().numpy(), g[k]) <= 1e-12, k
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("shape,npml", [((18, 16, 24), (3, 3, 4)), ((40, 36, 1), (5, 4, 0))])
+def test_running_dft_monitors_equal_dft_of_the_time_series(shape, npml, dtype):
+    """Running-DFT monitors against (i) the DFT of the numpy oracle's per-point time series and (ii) np.fft.fft
+    bins (the convention of ceviche/utils.py:383-386), over two run() legs."""
+    import ceviche_b200
+    from oracle import cases
+    from oracle.fdtd_numpy import OracleFDTD, rel_l2
+    rng = np.random.default_rng(2)
+    steps = 96
+    eps = 1 + 2 * rng.random(shape)
+    mid = tuple(n // 2 for n in shape)
+    src = [("z", cases.one_hot(shape, mid, 3.0), cases.modulated(steps, 30, 10, 8.0, 2.0))]
+    # two monitors: a few scattered Ez points and a small Hy patch
+    pts_e = [tuple(int(rng.integers(0, n)) for n in shape) for _ in range(5)] + [mid]
+    m_e = np.zeros(shape); m_h = np.zeros(shape)
+    for q in pts_e:
+        m_e[q] = 1.0
+    m_h[mid[0] - 2:mid[0] + 2, mid[1] - 1:mid[1] + 2, mid[2]] = 1.0
+    F = ceviche_b200.fdtd(eps, cases.DL, list(npml), dtype=dtype)
+    dt = F.dt
+    freqs = np.array([3, 7, 12]) / (steps * dt)          # FFT bins 3, 7, 12 of a 96-sample series
+    F.run(40, [(c, p, w[:40]) for c, p, w in src], [], monitors=[("Ez", m_e), ("Hy", m_h)], freqs=freqs)
+    F.run(steps - 40, [(c, p, w[40:]) for c, p, w in src], [])
+    vals = [v.cpu().numpy() for v in F.monitor_values()]
+    idx = [p.cpu().numpy() for p in F.monitor_points]
+    assert vals[0].shape == (3, len(set(pts_e))) and vals[1].shape == (3, int(m_h.sum()))
+    # oracle: every monitored point as a one-hot probe
+    probes = [("Ez", cases.one_hot(shape, np.unravel_index(q, shape))) for q in idx[0]] + \
+             [("Hy", cases.one_hot(shape, np.unravel_index(q, shape))) for q in idx[1]]
+    O = OracleFDTD(eps, cases.DL, list(npml))
+    series, _ = O.run(steps, src, probes)
+    n = np.arange(steps)
+    dft = np.exp(-2j * np.pi * freqs[:, None] * n[None, :] * dt) @ series          # (freq, point)
+    fft = np.fft.fft(series, axis=0)[[3, 7, 12]]
+    got = np.concatenate(vals, axis=1)
+    tol = 1e-10 if dtype == torch.float64 else 1e-5
+    assert rel_l2(got.real, dft.real) <= tol and rel_l2(got.imag, dft.imag) <= tol
+    assert rel_l2(got.real, fft.real) <= tol * 10 and rel_l2(got.imag, fft.imag) <= tol * 10
+    F.initialize_fields()
+    assert all(float(v.abs().max()) == 0.0 for v in F.monitor_values())
