@@ -171,8 +171,8 @@ class SlabFDTD:
         self.P = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.Nx, self.Ny, self.Nz = self.global_shape = tuple(global_shape)
-        if self.Nz <= 1:
-            raise ValueError("slab decomposition needs a 3-D grid (Nz > 1)")
+        if self.Ny <= 1 and self.Nz <= 1:
+            raise ValueError("slab decomposition needs a 2-D or 3-D grid (Ny > 1 or Nz > 1)")
         self.lo, self.hi = partition(self.Nx, self.P)[self.rank]
         self.nx = self.hi - self.lo
         if self.P > 1 and self.nx < 2:

@@ -17,9 +17,9 @@ def _case(shape, npml, steps, seed):
     rng = np.random.default_rng(seed)
     eps = 1 + 2 * rng.random(shape)
     src = [("z", rng.random(shape) * (rng.random(shape) < 0.02), cases.modulated(steps, steps / 3, steps / 8, 9.0, 2.0)),
-           ("y", cases.one_hot(shape, (0, 1, 2)), cases.gaussian(steps, steps / 4, steps / 10)),
+           ("y", cases.one_hot(shape, (0, 1, min(2, shape[2] - 1))), cases.gaussian(steps, steps / 4, steps / 10)),
            ("x", cases.one_hot(shape, (shape[0] // 2, 0, 0)), cases.gaussian(steps, steps / 5, steps / 10))]
-    probes = [("Ez", rng.random(shape)), ("Hy", cases.one_hot(shape, (shape[0] - 1, 2, 1))), ("Dx", rng.random(shape))]
+    probes = [("Ez", rng.random(shape)), ("Hy", cases.one_hot(shape, (shape[0] - 1, 2, min(1, shape[2] - 1)))), ("Dx", rng.random(shape))]
     return dict(eps=eps, dL=cases.DL, npml=list(npml), steps=steps, sources=src, probes=probes)
 
 
@@ -54,7 +54,8 @@ def _free_port():
 
 
 @pytest.mark.parametrize("dtype_name", ["float64", "float32"])
-@pytest.mark.parametrize("shape,npml", [((24, 20, 72), (4, 3, 6)), ((14, 9, 40), (0, 2, 3))])
+@pytest.mark.parametrize("shape,npml", [((24, 20, 72), (4, 3, 6)), ((14, 9, 40), (0, 2, 3)),
+                                        ((40, 64, 1), (5, 6, 0))])       # the last one: a 2-D grid (relabelled x, z, y)
 def test_slabs_bit_identical_to_single_gpu(shape, npml, dtype_name, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")

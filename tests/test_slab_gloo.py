@@ -21,9 +21,9 @@ def _case(shape, npml, steps, seed):
     rng = np.random.default_rng(seed)
     eps = 1 + 2 * rng.random(shape)
     src = [("z", rng.random(shape) * (rng.random(shape) < 0.05), cases.modulated(steps, steps / 3, steps / 8, 9.0, 2.0)),
-           ("y", cases.one_hot(shape, (0, 1, 2)), cases.gaussian(steps, steps / 4, steps / 10)),
+           ("y", cases.one_hot(shape, (0, 1, min(2, shape[2] - 1))), cases.gaussian(steps, steps / 4, steps / 10)),
            ("x", cases.one_hot(shape, (shape[0] // 2, 0, 0)), cases.gaussian(steps, steps / 5, steps / 10))]
-    probes = [("Ez", rng.random(shape)), ("Hy", cases.one_hot(shape, (shape[0] - 1, 2, 1))), ("Dx", rng.random(shape))]
+    probes = [("Ez", rng.random(shape)), ("Hy", cases.one_hot(shape, (shape[0] - 1, 2, min(1, shape[2] - 1)))), ("Dx", rng.random(shape))]
     return dict(eps=eps, dL=cases.DL, npml=list(npml), steps=steps, sources=src, probes=probes)
 
 
@@ -59,7 +59,8 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world,shape,npml", [(2, (12, 7, 6), (3, 2, 2)), (2, (9, 6, 5), (0, 2, 0)), (3, (11, 5, 6), (2, 0, 2))])
+@pytest.mark.parametrize("world,shape,npml", [(2, (12, 7, 6), (3, 2, 2)), (2, (9, 6, 5), (0, 2, 0)), (3, (11, 5, 6), (2, 0, 2)),
+                                              (2, (10, 9, 1), (2, 3, 0))])      # 2-D grid
 def test_slab_driver_matches_single_domain_oracle(world, shape, npml, tmp_path):
     steps, seed = 40, 5
     out = str(tmp_path / "slab.npz")
