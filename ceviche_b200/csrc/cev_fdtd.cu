@@ -130,6 +130,10 @@ struct cev_fdtd {
     std::vector<RunGraph> graphs;
     DeviceBuf stage_w, stage_p;
     cudaStream_t cap_stream = nullptr;
+    std::vector<cudaStream_t> side;        // forward mode: one side stream (+ event) per tangent state
+    std::vector<cudaEvent_t> side_ev;
+    cudaEvent_t main_ev = nullptr;
+    int jvp_streams = -1;        // -1 auto (grids <= 2^23 cells), 0 never, 1 always
     uint64_t epoch = 1;          // bumped whenever sources, probes or options change
     int use_graph = -1;          // -1 auto (small grids), 0 never, 1 whenever possible
     void drop_graphs() {
@@ -773,23 +777,55 @@ int jvp_loop(cev_fdtd* p, const cev_state* st, int B, const cev_state* tst, cons
              const double* waveform, double* partials, double* tpartials, cudaStream_t s) {
     const int64_t Nx = p->N[0];
     const int64_t stride = nsteps * p->n_slots;
+    // The B tangent states are independent of each other; on grids whose single launches cannot fill the GPU they
+    // run on B side streams (fork / join with events) so that their kernels overlap.  Dependencies: a tangent H
+    // half-step reads the primal D of the previous step (so it waits for the primal D launch, and the next primal D
+    // launch waits for it); a tangent D half-step only touches its own state.
+    const int64_t cells = (int64_t)p->N[0] * p->N[1] * p->N[2];
+    const bool fork = B >= 2 && (p->jvp_streams == 1 || (p->jvp_streams < 0 && cells <= ((int64_t)1 << 23)));
+    if (fork) {
+        while ((int)p->side.size() < B) {
+            cudaStream_t q;
+            cudaEvent_t e;
+            CUDA_TRY(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            p->side.push_back(q);
+            p->side_ev.push_back(e);
+        }
+        if (!p->main_ev) CUDA_TRY(cudaEventCreateWithFlags(&p->main_ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(p->main_ev, s));            // everything queued on the caller's stream so far
+    }
+    auto ts = [&](int b) { return fork ? p->side[b] : s; };
     for (int64_t n = 0; n < nsteps; ++n) {
-        for (int b = 0; b < B; ++b)
-            if (launch_H<T, AT>(p, &tst[b], &tan[b], nullptr, 0, Nx, n - 1, tpartials ? tpartials + b * stride : nullptr, s)) return -1;
+        for (int b = 0; b < B; ++b) {
+            if (fork) CUDA_TRY(cudaStreamWaitEvent(ts(b), p->main_ev, 0));     // primal D of step n-1 is final
+            if (launch_H<T, AT>(p, &tst[b], &tan[b], nullptr, 0, Nx, n - 1, tpartials ? tpartials + b * stride : nullptr, ts(b))) return -1;
+            if (fork) CUDA_TRY(cudaEventRecord(p->side_ev[b], ts(b)));
+        }
         if (launch_H<T, AT>(p, st, nullptr, nullptr, 0, Nx, n - 1, partials, s)) return -1;
+        if (fork)
+            for (int b = 0; b < B; ++b) CUDA_TRY(cudaStreamWaitEvent(s, p->side_ev[b], 0));   // they have read the primal D
         if (launch_D<T, AT>(p, st, nullptr, nullptr, nullptr, nullptr, nullptr, waveform ? waveform + n * p->nsrc : nullptr, 0,
                             Nx, n, partials, s))
             return -1;
+        if (fork) CUDA_TRY(cudaEventRecord(p->main_ev, s));
         for (int b = 0; b < B; ++b)
             if (launch_D<T, AT>(p, &tst[b], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, Nx, n,
-                                tpartials ? tpartials + b * stride : nullptr, s))
+                                tpartials ? tpartials + b * stride : nullptr, ts(b)))
                 return -1;
     }
     if (nsteps > 0) {
         if (launch_probe_only<T, AT>(p, st, nullptr, 0, nsteps - 1, partials, s)) return -1;
-        for (int b = 0; b < B; ++b)
-            if (launch_probe_only<T, AT>(p, &tst[b], &tan[b], 0, nsteps - 1, tpartials ? tpartials + b * stride : nullptr, s)) return -1;
+        for (int b = 0; b < B; ++b) {
+            if (fork) CUDA_TRY(cudaStreamWaitEvent(ts(b), p->main_ev, 0));
+            if (launch_probe_only<T, AT>(p, &tst[b], &tan[b], 0, nsteps - 1, tpartials ? tpartials + b * stride : nullptr, ts(b))) return -1;
+        }
     }
+    if (fork)          // join: the caller's stream continues after every side stream
+        for (int b = 0; b < B; ++b) {
+            CUDA_TRY(cudaEventRecord(p->side_ev[b], ts(b)));
+            CUDA_TRY(cudaStreamWaitEvent(s, p->side_ev[b], 0));
+        }
     return 0;
 }
 
@@ -1143,6 +1179,9 @@ int cev_fdtd_destroy(cev_fdtd* p) {
     p->drop_graphs();
     p->stage_w.release(); p->stage_p.release();
     if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
+    for (auto q : p->side) cudaStreamDestroy(q);
+    for (auto e : p->side_ev) cudaEventDestroy(e);
+    if (p->main_ev) cudaEventDestroy(p->main_ev);
     p->tables.release();
     p->src_comp.release(); p->src_id.release(); p->src_cell.release(); p->src_weight.release();
     for (auto& t : p->src_tilings) {
@@ -1158,7 +1197,10 @@ int cev_fdtd_destroy(cev_fdtd* p) {
 int cev_fdtd_set_option(cev_fdtd* p, const char* name, int64_t value) {
     if (!p || !name) return fail("NULL argument");
     p->epoch++;
-    if (!strcmp(name, "use_graph")) {
+    if (!strcmp(name, "jvp_streams")) {
+        if (value < -1 || value > 1) return fail("jvp_streams must be -1 (auto), 0 or 1");
+        p->jvp_streams = (int)value;
+    } else if (!strcmp(name, "use_graph")) {
         if (value < -1 || value > 1) return fail("use_graph must be -1 (auto: small grids), 0 or 1");
         p->use_graph = (int)value;
     } else if (!strcmp(name, "kernel_variant")) {

@@ -17,7 +17,7 @@ prof = np.zeros(shape); prof[N // 2, N // 2, 0] = 1.0
 mask = np.zeros(shape); mask[N // 3, :, 0] = 1.0
 t = np.arange(steps)
 wave = np.exp(-(t - 60) ** 2 / (2 * 20 ** 2)) * np.cos(0.2 * t)
-B = 4
+B = int(os.environ.get('TUNE_B', '4'))
 V = torch.as_tensor(np.random.default_rng(1).standard_normal((B,) + shape))
 
 

@@ -232,20 +232,22 @@ def test_tangent_marching_equals_baseline_bitwise(shape, npml, comps, dtype):
     probes = [(k, rng.random(shape)) for k in ("Ex", "Ey", "Ez", "Hx", "Hy", "Hz")]
     V = torch.as_tensor(rng.standard_normal((3,) + shape))
     out = []
-    for variant in (1, 0):
+    for variant, streams in ((1, 0), (0, 0), (0, 1)):      # streams: the tangent states on side streams (fork / join)
         F = ceviche_b200.fdtd(eps, cases.DL, list(npml), dtype=dtype)
         F.set_option("kernel_variant", variant)
+        F.set_option("jvp_streams", streams)
         s, ds = F.jvp_run(steps, V, src, probes)
         tangents = [[t.cpu().numpy() for t in tH + tD] for _, tH, tD, _ in F._tangent_states]
         out.append((s.cpu().numpy(), ds.cpu().numpy(), tangents, {k: F.fields[k].cpu().numpy() for k in FIELD_KEYS}))
-    (s1, d1, t1, f1), (s0, d0, t0, f0) = out
-    assert np.array_equal(s1, s0) and np.array_equal(d1, d0)
-    assert np.abs(d0).max() > 0
-    for a, b in zip(t1, t0):
-        for x, y in zip(a, b):
-            assert np.array_equal(x, y)
-    for k in FIELD_KEYS:
-        assert np.array_equal(f1[k], f0[k]), k
+    s1, d1, t1, f1 = out[0]
+    assert np.abs(d1).max() > 0
+    for s0, d0, t0, f0 in out[1:]:
+        assert np.array_equal(s1, s0) and np.array_equal(d1, d0)
+        for a, b in zip(t1, t0):
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
+        for k in FIELD_KEYS:
+            assert np.array_equal(f1[k], f0[k]), k
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
