@@ -154,9 +154,26 @@ def _fields_sum_reference(case, eps):
     return S
 
 
+def make_modes_golden():
+    """Modes of the reference's own self-test ridge (ceviche/modes.py:140-165) from the REFERENCE's get_modes."""
+    modes = ref_loader.load_modes()
+    lambda0 = 1.550e-6
+    dL = lambda0 / 100
+    omega = 2 * np.pi * modes.C_0 / lambda0
+    Nx = int(lambda0 * 10 / dL)
+    eps = np.ones((Nx,))
+    w = int(lambda0 / dL / 2)
+    eps[Nx // 2 - w:Nx // 2 + w] = 4.0
+    vals, vecs = modes.get_modes(eps, omega, dL, 10, m=6)
+    np.savez_compressed(os.path.join(OUT, "modes_ridge.npz"), vals=vals, vecs=vecs, eps=eps, omega=omega, dL=dL)
+    print("modes_ridge", vals)
+
+
 def main(argv):
     os.makedirs(OUT, exist_ok=True)
-    which = argv[1:] or ["fields", "grads"]
+    which = argv[1:] or ["fields", "grads", "modes"]
+    if "modes" in which:
+        make_modes_golden()
     if "fields" in which:
         for name in cases.FIELD_CASES:
             make_field_golden(name)

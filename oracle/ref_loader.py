@@ -67,3 +67,23 @@ def load():
             setattr(pkg, name, mod)
             mods[name] = mod
     return mods["fdtd"]
+
+
+def load_modes():
+    """The reference's ``ceviche.modes`` (get_modes / insert_mode), unmodified.  It imports
+    ``compute_derivative_matrices`` from ``ceviche.fdfd``, which cannot be imported without the real autograd; the
+    function itself lives in ``ceviche/derivatives.py`` (already loaded), so a stand-in ``ceviche.fdfd`` module
+    re-exports it."""
+    load()
+    if "ceviche.modes" in sys.modules:
+        return sys.modules["ceviche.modes"]
+    fdfd = types.ModuleType("ceviche.fdfd")
+    fdfd.compute_derivative_matrices = sys.modules["ceviche.derivatives"].compute_derivative_matrices
+    sys.modules["ceviche.fdfd"] = fdfd
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", SyntaxWarning)
+        spec = importlib.util.spec_from_file_location("ceviche.modes", os.path.join(REFERENCE_DIR, "modes.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["ceviche.modes"] = mod
+        spec.loader.exec_module(mod)
+    return mod

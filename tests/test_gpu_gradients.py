@@ -158,3 +158,25 @@ def test_fp32_gradients_within_tolerance(golden_dir):
     series = F.run(case["steps"], case["sources"], case["probes"])
     (g,) = torch.autograd.grad(_loss(series, case), eps)
     assert rel_l2(g.cpu().numpy(), gold["grad_ad"]) <= 1e-5
+
+
+def test_inverse_design_loop_improves_mode_overlap():
+    """SURVEY 8(f) ranks 3-4 on the real path: mode source + mode-overlap probe (ceviche_b200.modes), gradient through
+    the checkpointed adjoint FDTD, a few ADAM steps (ceviche_b200.optimizers): the objective must go up, and the
+    gradient must agree with a directional finite difference of the same objective."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("optimize_mode_overlap", os.path.join(root, "examples", "optimize_mode_overlap.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    from ceviche_b200.optimizers import adam_optimize
+    P = ex.build(Nx=72, Ny=48, npml=8, steps=260)
+    objective, n = ex.make_objective(P)
+    rho0 = torch.full((n,), 0.5, dtype=torch.float64, device="cuda")
+    v0, g0 = objective(rho0)
+    d = torch.as_tensor(np.random.default_rng(0).standard_normal(n), device="cuda")
+    h = 1e-5
+    fd = (objective(rho0 + h * d)[0] - objective(rho0 - h * d)[0]) / (2 * h)
+    assert abs(float(fd) - float(g0 @ d)) <= 1e-6 * abs(float(fd))
+    rho, hist = adam_optimize(objective, rho0, True, step_size=0.1, Nsteps=4, bounds=(0.0, 1.0), direction="max", verbose=False)
+    assert hist[-1] > hist[0] > 0 and float(rho.min()) >= 0.0 and float(rho.max()) <= 1.0
