@@ -79,7 +79,11 @@ class CudaSlabBackend:
         self.halo = False
         self.n_slots = 0
         self.main = torch.cuda.current_stream(device)
-        self.comm = torch.cuda.Stream(device)
+        # the halo messages ride on a high-priority side stream, so that their few NCCL CTAs are dispatched while the
+        # interior half-step kernel still has thousands of CTAs pending (measured neutral at config-3 sizes on 2 GPUs:
+        # the messages are already hidden; profiles/r1_slab_thin_slabs_2gpu.log)
+        self.comm = torch.cuda.Stream(device, priority=-1)
+        self._st = None
 
     def _state(self):
         st = _lib.cev_state()
@@ -127,11 +131,12 @@ class CudaSlabBackend:
 
     def new_partials(self, steps):
         self.partials = torch.zeros((steps, self.n_slots), dtype=torch.float64, device=self.device)
+        self._st = self._state()          # the pointers do not change during a run(): built once, not per half-step
 
     def step_H(self, x0, x1, probe_t):
         if x1 <= x0:
             return
-        st = self._state()
+        st = self._st or self._state()
         _lib.check(self.plan.lib.cev_fdtd_step_H_ex(self.plan.handle, C.byref(st), None, None, x0, x1, probe_t,
                                                     self.partials.data_ptr() if self.n_slots else None, self._s()))
 
@@ -139,7 +144,7 @@ class CudaSlabBackend:
         """D half-step of planes [x0, x1); the sources lying in those planes are injected in-kernel."""
         if x1 <= x0:
             return
-        st = self._state()
+        st = self._st or self._state()
         _lib.check(self.plan.lib.cev_fdtd_step_D_ex(self.plan.handle, C.byref(st), None, None, None, None,
                                                     wave_row.data_ptr() if self.n_sources else None, x0, x1, probe_t,
                                                     self.partials.data_ptr() if self.n_slots else None, self._s()))
