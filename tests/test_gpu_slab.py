@@ -26,9 +26,10 @@ def _case(shape, npml, steps, seed):
 def _worker(rank, world, port, shape, npml, steps, seed, dtype_name, out):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
-    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"       # (NCCL bootstrap); the store is a file: no port to collide on
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    dist.init_process_group("nccl", init_method="file://" + port, rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
     try:
         from ceviche_b200.slab import SlabFDTD, partition
         case = _case(shape, npml, steps, seed)
@@ -47,10 +48,10 @@ def _worker(rank, world, port, shape, npml, steps, seed, dtype_name, out):
         dist.destroy_process_group()
 
 
-def _free_port():
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
+def _rendezvous(tmp_path):
+    """A fresh file for torch.distributed's FileStore (TCP ports picked in advance can be taken by the time the
+    workers bind them: seen once on an 8-GPU box)."""
+    return str(tmp_path / "rendezvous")
 
 
 @pytest.mark.parametrize("dtype_name", ["float64", "float32"])
@@ -64,7 +65,7 @@ def test_slabs_bit_identical_to_single_gpu(shape, npml, dtype_name, tmp_path):
     world = min(torch.cuda.device_count(), 4)
     steps, seed = 30, 11
     out = str(tmp_path / "slab.npz")
-    mp.spawn(_worker, args=(world, _free_port(), shape, npml, steps, seed, dtype_name, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _rendezvous(tmp_path), shape, npml, steps, seed, dtype_name, out), nprocs=world, join=True)
     got = np.load(out)
     case = _case(shape, npml, steps, seed)
     F = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"], dtype=getattr(torch, dtype_name))

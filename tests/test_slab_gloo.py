@@ -30,8 +30,8 @@ def _case(shape, npml, steps, seed):
 def _worker(rank, world, port, shape, npml, steps, seed, out):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    dist.init_process_group("gloo", init_method="file://" + port, rank=rank, world_size=world)   # file store: no port races
     try:
         from ceviche_b200.slab import SlabFDTD, partition
         from slab_backend_cpu import NumpySlabBackend
@@ -53,10 +53,10 @@ def _worker(rank, world, port, shape, npml, steps, seed, out):
         dist.destroy_process_group()
 
 
-def _free_port():
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
+def _rendezvous(tmp_path):
+    """A fresh file for torch.distributed's FileStore (TCP ports picked in advance can be taken by the time the
+    workers bind them: seen once on an 8-GPU box)."""
+    return str(tmp_path / "rendezvous")
 
 
 @pytest.mark.parametrize("world,shape,npml", [(2, (12, 7, 6), (3, 2, 2)), (2, (9, 6, 5), (0, 2, 0)), (3, (11, 5, 6), (2, 0, 2)),
@@ -64,7 +64,7 @@ def _free_port():
 def test_slab_driver_matches_single_domain_oracle(world, shape, npml, tmp_path):
     steps, seed = 40, 5
     out = str(tmp_path / "slab.npz")
-    mp.spawn(_worker, args=(world, _free_port(), shape, npml, steps, seed, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _rendezvous(tmp_path), shape, npml, steps, seed, out), nprocs=world, join=True)
     got = np.load(out)
     case = _case(shape, npml, steps, seed)
     O = OracleFDTD(case["eps"], case["dL"], case["npml"])
