@@ -869,7 +869,9 @@ int launch_fused_shape(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row, 
         a.partials = partials;
         aux = n_aux_slots;
     }
-    k_step_fused<T, AT, V, LZ, BY><<<a.n_tiles + aux, dim3(32, BY), 0, s>>>(a);
+    const bool nopml = p->nH[0] + p->nH[1] + p->nH[2] + p->nD[0] + p->nD[1] + p->nD[2] == 0;
+    if (nopml && BY == 4 && LZ == 16) k_step_fused<T, AT, V, 16, 4, true><<<a.n_tiles + aux, dim3(32, 4), 0, s>>>(a);
+    else k_step_fused<T, AT, V, LZ, BY><<<a.n_tiles + aux, dim3(32, BY), 0, s>>>(a);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

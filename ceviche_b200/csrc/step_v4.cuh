@@ -124,8 +124,34 @@ struct PmlCtxH4 {
     }
 };
 
-template <typename T, typename AT, int V, int LZ, int BY>
-__global__ void __launch_bounds__(32 * BY, (BY >= 8 ? 1 : V4_MIN_CTAS)) k_step_fused(const StepArgs<T, AT> a) {
+// V4_PML_NOINLINE 1 puts the PML work of the fused kernel behind a call boundary: inlined, the two general PML updates
+// push the kernel to 240+ registers for EVERY thread, while the PML-free kernel needs 128 (4 CTAs per SM) and beats the
+// two-kernel path by 20-25 % (profiles/r1_tune_fused_nopml.log).  Out of line the main path keeps that budget, but the
+// PML iterations then pay the call, the stack traffic and integral loads issued late, and with a barrier per plane the
+// slow warps hold the CTA: measured 14.5 instead of 20.9 Gcell/s at 256^3 fp64 (profiles/r1_tune_fused_pml_noinline.log).
+// Kept as an experiment switch, off.
+#ifndef V4_PML_NOINLINE
+#define V4_PML_NOINLINE 0
+#endif
+template <typename T, typename AT, int V>
+__device__ __noinline__ void v4_pml_H(const StepArgs<T, AT>& a, int i, int j, int k0, int mx, int my, const int* mz, AT s,
+                                      const Vec<T, V>* h, const AT (*CE)[V], Vec<T, V>* out, bool store) {
+    PmlCtxH4<T, AT, V> ctx;
+    ctx.load(a, i, j, k0, mx, my, mz);
+    ctx.apply(a, i, j, k0, mx, my, mz, s, h, CE, out, store);
+}
+template <typename T, typename AT, int V>
+__device__ __noinline__ void v4_pml_D(const StepArgs<T, AT>& a, int i, int j, int k0, int mx, int my, const int* mz, AT s,
+                                      const Vec<T, V>* d, const AT (*CH)[V], Vec<T, V>* out) {
+    PmlCtx<T, AT, V, false> ctx;
+    ctx.load(a, i, j, k0, mx, my, mz, 7u);
+    ctx.apply(a, i, j, k0, mx, my, mz, s, d, CH, out, 7u);
+}
+
+// NOPML = the plan has no PML on any axis: every PML branch is compiled out (the lean kernel: what the fused
+// formulation can do when the register budget is not spent on the PML paths).
+template <typename T, typename AT, int V, int LZ, int BY, bool NOPML = false>
+__global__ void __launch_bounds__(32 * BY, (BY >= 8 ? 1 : ((NOPML || V4_PML_NOINLINE) ? 4 : V4_MIN_CTAS))) k_step_fused(const __grid_constant__ StepArgs<T, AT> a) {
     const int bid = blockIdx.x;
     if (bid >= a.n_tiles) {
         probe_block<T, AT>(a, a.aux_slot0 + (bid - a.n_tiles));
@@ -236,7 +262,7 @@ __global__ void __launch_bounds__(32 * BY, (BY >= 8 ? 1 : V4_MIN_CTAS)) k_step_f
             }
         }
         const int mxH = a.mapH[0][i];
-        if (yz_pmlH || mxH >= 0) ctxH.load(a, i, j, k0, mxH, myH, mzH);
+        if (!NOPML && !V4_PML_NOINLINE && (yz_pmlH || mxH >= 0)) ctxH.load(a, i, j, k0, mxH, myH, mzH);
     };
 
     int buf = 0;
@@ -252,10 +278,10 @@ __global__ void __launch_bounds__(32 * BY, (BY >= 8 ? 1 : V4_MIN_CTAS)) k_step_f
         const int pbase = i * plane;
         const bool st_on = own && !pre;
         const int mxH = a.mapH[0][i], mxD = a.mapD[0][i];
-        const bool pmlH = yz_pmlH || mxH >= 0;
-        const bool pmlD = st_on && (yz_pmlD || mxD >= 0);
+        const bool pmlH = !NOPML && (yz_pmlH || mxH >= 0);
+        const bool pmlD = !NOPML && st_on && (yz_pmlD || mxD >= 0);
         PmlCtx<T, AT, V, false> ctxD;
-        if (pmlD) ctxD.load(a, i, j, k0, mxD, myD, mzD, 7u);   // consumed after the barrier
+        if (pmlD && !V4_PML_NOINLINE) ctxD.load(a, i, j, k0, mxD, myD, mzD, 7u);   // consumed after the barrier
 
         // ---- curl_E and H_new of plane i (own cells + halo row / halo lane)
         AT ex_kp = __shfl_down_sync(0xffffffffu, Ecur[0][0], 1);
@@ -291,7 +317,24 @@ __global__ void __launch_bounds__(32 * BY, (BY >= 8 ? 1 : V4_MIN_CTAS)) k_step_f
 #pragma unroll
                 for (int e = 0; e < V; ++e) hn[c].v[e] = (T)muladd(sH, CE[c][e], (AT)h[c].v[e]);
         } else {
+#if V4_PML_NOINLINE
+            Vec<T, V> h2[3], o2[3];
+            AT ce2[3][V];
+            int mz2[V];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                h2[c] = h[c];
+#pragma unroll
+                for (int e = 0; e < V; ++e) ce2[c][e] = CE[c][e];
+            }
+#pragma unroll
+            for (int e = 0; e < V; ++e) mz2[e] = mzH[e];
+            v4_pml_H<T, AT, V>(a, i, j, k0, mxH, myH, mz2, sH, h2, ce2, o2, st_on);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) hn[c] = o2[c];
+#else
             ctxH.apply(a, i, j, k0, mxH, myH, mzH, sH, h, CE, hn, st_on);
+#endif
         }
         if (st_on) {
 #pragma unroll
@@ -333,7 +376,24 @@ __global__ void __launch_bounds__(32 * BY, (BY >= 8 ? 1 : V4_MIN_CTAS)) k_step_f
 #pragma unroll
                         for (int e = 0; e < V; ++e) out[c].v[e] = (T)muladd(sD, CH[c][e], (AT)dcur[c].v[e]);
                 } else {
+#if V4_PML_NOINLINE
+                    Vec<T, V> d2[3], o2[3];
+                    AT ch2[3][V];
+                    int mz2[V];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        d2[c] = dcur[c];
+#pragma unroll
+                        for (int e = 0; e < V; ++e) ch2[c][e] = CH[c][e];
+                    }
+#pragma unroll
+                    for (int e = 0; e < V; ++e) mz2[e] = mzD[e];
+                    v4_pml_D<T, AT, V>(a, i, j, k0, mxD, myD, mz2, sD, d2, ch2, o2);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) out[c] = o2[c];
+#else
                     ctxD.apply(a, i, j, k0, mxD, myD, mzD, sD, dcur, CH, out, 7u);
+#endif
                 }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) stv<T, V>(a.Dout[c] + pbase + orow, out[c]);

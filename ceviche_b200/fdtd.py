@@ -535,12 +535,18 @@ class fdtd:
             return partials @ self._slot_fold
 
     def _use_fused(self, steps):
-        """The fused full-step kernel (step_v4.cuh) moves 15 instead of 21 words per cell but recomputes a halo and
-        runs at 2-3 CTAs per SM: measured on B200 it is 15-40 % SLOWER than the two tuned half-step kernels
-        (profiles/README.md), so it is opt-in only: `set_option('kernel_variant', 4)`."""
-        if self._options.get("kernel_variant", 0) != 4 or steps < 2 or not self._fused_step:
+        """The fused full-step kernel (step_v4.cuh) moves 15 instead of 21 words per cell but recomputes a halo.
+        With PML code compiled in it needs 168-240 registers and is 15-40 % SLOWER than the two tuned half-step
+        kernels; its PML-free instantiation (128 registers) is 20-25 % FASTER (profiles/README.md).  So: automatic on
+        grids without any PML (periodic on all axes) of >= 2^21 cells, opt-in elsewhere (`kernel_variant` 4)."""
+        kv = self._options.get("kernel_variant", 0)
+        if kv not in (0, 4) or steps < 2 or not self._fused_step:
             return False
-        return self._options.get("active_components", 63) == 63
+        if self._options.get("active_components", 63) != 63:
+            return False
+        if kv == 4:
+            return True
+        return not any(int(p) for p in self.npml) and self.N >= (1 << 21) and min(self.grid_shape) >= 32
 
     def _shadow_state(self):
         if self._shadow is None:

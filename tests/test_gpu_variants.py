@@ -75,7 +75,7 @@ def test_marching_equals_baseline_bitwise(shape, npml, dtype):
 
 
 FUSED_SHAPES = SHAPES + [((5, 3, 8), (1, 1, 2)), ((1, 6, 16), (0, 2, 3)), ((17, 1, 36), (3, 0, 4)), ((36, 31, 124), (5, 4, 6)),
-                         ((20, 9, 4), (3, 2, 0))]
+                         ((20, 9, 4), (3, 2, 0)), ((18, 14, 72), (0, 0, 0))]    # the last: no PML at all = the lean instantiation
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
