@@ -81,6 +81,9 @@ def _ptr3(ts):
     return _lib.c_void_p3(*[_ptr(t) for t in ts])
 
 
+_ONES3 = _lib.c_double3(1.0, 1.0, 1.0)
+
+
 class _Plan:
     """Owner of one C-side plan handle."""
 
@@ -257,10 +260,14 @@ class fdtd:
         z = lambda s: torch.zeros(s, dtype=self.dtype, device=self.device)
         self._pml = {fam: [z(shapes[f * 3 + c]) for c in range(3)] for f, fam in enumerate(_PML_FAMILIES)}
         self._shadow = None
+        self._st_cache = None
 
     def initialize_fields(self):
         """fdtd.py:147-211: zero state, t_index = 0, a NEW fields dict."""
         self.t_index = 0
+        self._st_cache = None
+        # could the state / 1/eps carry an autograd graph?  (eps_r that requires grad; set again by differentiable steps)
+        self._grad_state = any(bool(m.requires_grad) for m in self.__dict__.get("_mE64", ()))
         if self.__dict__.get("_mon_acc") is not None:
             self._mon_acc.zero_()
         self._shadow = None         # ping-pong scratch of the fused kernel (allocated on first use)
@@ -313,6 +320,9 @@ class fdtd:
     def _as_J(self, J):
         if J is None:
             return None
+        if (torch.is_tensor(J) and J.dtype == self.dtype and J.device == self.device and tuple(J.shape) == self.grid_shape
+                and J.is_contiguous()):
+            return J                      # the common case of the reference-style loop: nothing to convert
         if not torch.is_tensor(J):
             J = torch.as_tensor(np.asarray(J))
         if J.is_complex():
@@ -327,25 +337,33 @@ class fdtd:
         """ one time step of FDTD (fdtd.py:74-144).  Returns the (same) `fields` dict holding nine
         FRESH tensors, like the reference hands out fresh arrays each step. """
         from . import autodiff
-        plan = self._ensure_plan()
+        plan = self._plan or self._ensure_plan()
         self.t_index += 1
         J = [self._as_J(j) for j in (Jx, Jy, Jz)]
-        self._drive(sum(1 << c for c in range(3) if J[c] is not None))
-        if autodiff.needs_grad(self, J):
+        d_mask = (J[0] is not None) | ((J[1] is not None) << 1) | ((J[2] is not None) << 2)
+        if d_mask & ~self._active:
+            self._drive(d_mask)
+        # the reference-style loop calls this thousands of times: the host work per call is kept small (the cheap
+        # pre-check below decides whether the full differentiability test is needed at all)
+        if (self._grad_state or autodiff.fwAD._current_level >= 0 or any(j is not None and j.requires_grad for j in J)) \
+                and autodiff.needs_grad(self, J):
             self._H, self._D, self._E, self._pml = autodiff.step(self, J)
+            self._grad_state = True
+            self._st_cache = None
             self._publish()
             return self.fields
         with torch.cuda.device(self.device):
-            Hn = [torch.empty_like(t) for t in self._H]
-            Dn = [torch.empty_like(t) for t in self._D]
-            En = [torch.empty_like(t) for t in self._E]
+            new = torch.empty((9,) + self.grid_shape, dtype=self.dtype, device=self.device).unbind(0)   # nine fresh arrays
+            Hn, Dn, En = new[0:3], new[3:6], new[6:9]
             lib, h, s = plan.lib, plan.handle, self._stream()
-            st = self._state()
+            st = self._st_cache
+            if st is None:                  # 1/eps and PML pointers only change with eps_r / a reset
+                st = self._st_cache = self._state()
+            st.H, st.D = _ptr3(self._H), _ptr3(self._D)
             _lib.check(lib.cev_fdtd_step_H(h, C.byref(st), _ptr3(Hn), 0, self.Nx, s))
             st.H = _ptr3(Hn)
-            _lib.check(lib.cev_fdtd_step_D(h, C.byref(st), _ptr3(Dn), _ptr3(En), _ptr3(J),
-                                           _lib.c_double3(1.0, 1.0, 1.0), 0, self.Nx, s))
-        self._H, self._D, self._E = Hn, Dn, En
+            _lib.check(lib.cev_fdtd_step_D(h, C.byref(st), _ptr3(Dn), _ptr3(En), _ptr3(J), _ONES3, 0, self.Nx, s))
+        self._H, self._D, self._E = list(Hn), list(Dn), list(En)
         self._publish()
         return self.fields
 
