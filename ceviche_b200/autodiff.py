@@ -197,18 +197,22 @@ class _RunFn(torch.autograd.Function):
             lp = [torch.zeros(shapes[q], dtype=sim.dtype, device=sim.device) for q in range(12)]
             G = [torch.zeros(sim.grid_shape, dtype=torch.float64, device=sim.device) for _ in range(3)]
             adj = _adjoint(lH, lD, lp, gC, gC2, G)
-            dummy = torch.zeros((1, max(1, sim._n_slots)), dtype=torch.float64, device=sim.device)
             for t0, t1, H0, D0, P0 in reversed(ctx.checkpoints):
                 # recompute the segment, keeping D after every step (the only forward quantity the
                 # transposed step needs: the step is linear in the state)
                 H = [t.clone() for t in H0]
-                D = [t.clone() for t in D0]
                 P = [t.clone() for t in P0]
-                st = _state(H, D, ctx.mE, P)
-                hist = [[t.clone() for t in D]]
+                # D after every step of the segment: the D half-step writes each new D straight into its history slot
+                # (out of place), so no per-step copies are made
+                hist = [[t.clone() for t in D0]]
                 for t in range(t0, t1):
-                    _lib.check(lib.cev_fdtd_run(h, C.byref(st), 1, _ptr(ctx.waveforms[t:t + 1]), _ptr(dummy), s))
-                    hist.append([x.clone() for x in D])
+                    st = _state(H, hist[-1], ctx.mE, P)
+                    Dn = [torch.empty_like(x) for x in D0]
+                    _lib.check(lib.cev_fdtd_step_H_ex(h, C.byref(st), None, None, 0, sim.Nx, -1, None, s))
+                    _lib.check(lib.cev_fdtd_step_D_ex(h, C.byref(st), _p3(Dn), None, None, None,
+                                                      _ptr(ctx.waveforms[t:t + 1]) if sim._n_sources else None,
+                                                      0, sim.Nx, -1, None, s))
+                    hist.append(Dn)
                 for t in range(t1, t0, -1):          # step number t (1-based in the segment's frame)
                     k = t - t0
                     if ctx.n_probes:
