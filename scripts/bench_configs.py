@@ -83,6 +83,8 @@ if "c4" in which:
         torch.autograd.grad((series ** 2).sum(), eps)
         torch.cuda.reset_peak_memory_stats()
         s_f, series = timed(fwd)
+        s_f2, series = timed(fwd)            # (the first timed forward occasionally eats a caching-allocator refill of
+        s_f = min(s_f, s_f2)                 #  the ~16 GB of checkpoints freed by the warm-up's backward: take the better)
         L = (series ** 2).sum()
         s_b, _ = timed(lambda: torch.autograd.grad(L, eps))
         cells = shape[0] * shape[1] * shape[2]
