@@ -1,6 +1,5 @@
 """x-slab decomposition on real GPUs (needs >= 2): NCCL halo exchange, bit-identical to the 1-GPU run."""
 import os
-import socket
 import sys
 
 import numpy as np

@@ -2,7 +2,6 @@
 backend, against the single-domain oracle.  Covers the ring wrap (npml[0] = 0), uneven partitions,
 sources/probes on slab boundaries and two consecutive run() calls."""
 import os
-import socket
 import sys
 
 import numpy as np
