@@ -265,7 +265,7 @@ bool can_march(const cev_fdtd* p, const StepArgs<T, AT>& a, bool isH) {
 // box (general kernel); 1 = the PML-free interior box clipped to [x0,x1); 2 = the shell = the rest, as up to six slabs.
 template <typename T, typename AT>
 void set_tiles_v2(const cev_fdtd* p, StepArgs<T, AT>& a, int64_t x0, int64_t x1, int part, int lz_override = 0,
-                  int lz_force = 0) {
+                  int lz_force = 0, const int* inner = nullptr /* {x0,x1,y0,y1,z0,z1}: overrides the interior box */) {
     constexpr int V = vec_width<T>();
     // planes of a single row (2-D grids: internal Ny = 1): one row per warp and the warps side by side along z
     const bool wz = a.Ny == 1 && part == 0 && !lz_override;
@@ -301,9 +301,9 @@ void set_tiles_v2(const cev_fdtd* p, StepArgs<T, AT>& a, int64_t x0, int64_t x1,
     };
     const int X0 = (int)x0, X1 = (int)x1;
     // interior box (z limits rounded inwards to the vector width)
-    const int ix0 = std::max(X0, p->in_lo[0]), ix1 = std::min(X1, p->in_hi[0]);
-    const int iy0 = p->in_lo[1], iy1 = p->in_hi[1];
-    const int iz0 = (p->in_lo[2] + V - 1) / V * V, iz1 = p->in_hi[2] / V * V;
+    const int ix0 = std::max(X0, inner ? inner[0] : p->in_lo[0]), ix1 = std::min(X1, inner ? inner[1] : p->in_hi[0]);
+    const int iy0 = inner ? inner[2] : p->in_lo[1], iy1 = inner ? inner[3] : p->in_hi[1];
+    const int iz0 = inner ? inner[4] : (p->in_lo[2] + V - 1) / V * V, iz1 = inner ? inner[5] : p->in_hi[2] / V * V;
     if (part == 0) {
         add(X0, X1, 0, a.Ny, 0, a.Nz);
     } else if (part == 1) {
@@ -558,7 +558,7 @@ int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const
     if (extras) a.on = 63u;
     // auto: the TMA-staged D kernel wins in fp64 (measured, scripts/tune.py); fp32 and the H half-step stay on the
     // register-marching kernels
-    if ((p->variant == 3 || ((p->variant == 0 || p->variant == 4) && sizeof(T) == 8 && x1 - x0 >= 4 && a.Ny >= V3_BY)) && !extras && a.on == 63u) {
+    if ((p->variant == 3 || ((p->variant == 0 || p->variant >= 4) && sizeof(T) == 8 && x1 - x0 >= 4 && a.Ny >= V3_BY)) && !extras && a.on == 63u) {
         set_tiles_v3(p, a, x0, x1);
         if (inject && attach_sources_v2(p, a, wave_row, 0, 32, V3_BY)) return -1;
         const int aux = attach_probes(p, a, 1, probe_t, partials);
@@ -846,7 +846,7 @@ bool can_fuse(const cev_fdtd* p, const StepArgs<T, AT>& a) {
 
 template <typename T, typename AT, int LZ, int BY>
 int launch_fused_shape(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row, int n_aux_slots, int64_t probe_t,
-                       double* partials, cudaStream_t s) {
+                       double* partials, cudaStream_t s, const int* box = nullptr /* PML-free {x0,x1,y0,y1,z0,z1} */) {
     constexpr int V = vec_width<T>();
     constexpr int OY = BY * (32 / LZ) - 1, OZ = LZ - 1;
     a.x0 = 0;
@@ -854,14 +854,15 @@ int launch_fused_shape(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row, 
     int chunk = p->xchunk > 0 ? p->xchunk : 16;   // the pre-roll plane costs 1/chunk extra H work
     a.xchunk = chunk;
     a.pf_dist = p->pf_dist;
-    a.ntz = (a.Nz / V + OZ - 1) / OZ;
-    a.nty = (a.Ny + OY - 1) / OY;
-    a.n_tiles = a.ntz * a.nty * ((a.Nx + chunk - 1) / chunk);
     a.n_boxes = 1;
     Box& B = a.box[0];
     B.x0 = 0; B.x1 = a.Nx; B.y0 = 0; B.y1 = a.Ny; B.z0 = 0; B.z1 = a.Nz;
+    if (box) { B.x0 = box[0]; B.x1 = box[1]; B.y0 = box[2]; B.y1 = box[3]; B.z0 = box[4]; B.z1 = box[5]; }
+    a.ntz = ((B.z1 - B.z0) / V + OZ - 1) / OZ;
+    a.nty = (B.y1 - B.y0 + OY - 1) / OY;
+    a.n_tiles = a.ntz * a.nty * ((B.x1 - B.x0 + chunk - 1) / chunk);
     B.cta0 = 0; B.ntz = a.ntz; B.nty = a.nty;
-    if (wave_row && p->n_src_pts > 0 && attach_sources_v2(p, a, wave_row, 4, -OZ, OY)) return -1;
+    if (wave_row && p->n_src_pts > 0 && attach_sources_v2(p, a, wave_row, box ? 6 : 4, -OZ, OY)) return -1;
     int aux = 0;
     if (probe_t >= 0 && partials && n_aux_slots > 0) {
         a.aux_slot0 = 0;
@@ -869,7 +870,8 @@ int launch_fused_shape(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row, 
         a.partials = partials;
         aux = n_aux_slots;
     }
-    const bool nopml = p->nH[0] + p->nH[1] + p->nH[2] + p->nD[0] + p->nD[1] + p->nD[2] == 0;
+    const bool nopml = box || p->nH[0] + p->nH[1] + p->nH[2] + p->nD[0] + p->nD[1] + p->nD[2] == 0;
+    if (a.n_tiles + aux == 0) return 0;
     if (nopml && BY == 4 && LZ == 16) k_step_fused<T, AT, V, 16, 4, true><<<a.n_tiles + aux, dim3(32, 4), 0, s>>>(a);
     else k_step_fused<T, AT, V, LZ, BY><<<a.n_tiles + aux, dim3(32, BY), 0, s>>>(a);
     CUDA_TRY(cudaGetLastError());
@@ -908,6 +910,78 @@ int launch_fused(cev_fdtd* p, const cev_state* in, const cev_state* out, const d
     return 0;
 }
 
+
+// ---- hybrid step: the lean (PML-free) fused kernel on the interior box, the two general half-step kernels out of
+// place on the six slabs of the PML shell.  The fused box is the PML-free interior shrunk by one cell on the low side of
+// every PML axis, so that the halo cells it recomputes are PML-free too.  Ping-pong of H and D only: the PML integrals
+// are touched by the shell kernels alone, in place.
+template <typename T>
+bool hybrid_box(const cev_fdtd* p, int box[6]) {
+    constexpr int V = vec_width<T>();
+    bool any_pml = false;
+    for (int A = 0; A < 3; ++A) {
+        const bool pml = p->nH[A] + p->nD[A] > 0;
+        any_pml |= pml;
+        box[2 * A] = pml ? p->in_lo[A] + 1 : 0;
+        box[2 * A + 1] = pml ? p->in_hi[A] : p->N[A];
+    }
+    box[4] = (box[4] + V - 1) / V * V;
+    box[5] = box[5] / V * V;
+    if (!any_pml) return false;                       // (no PML: the fused kernel serves the whole grid)
+    for (int A = 0; A < 3; ++A)
+        if (box[2 * A + 1] - box[2 * A] < 16) return false;
+    return true;
+}
+
+template <typename T, typename AT>
+int launch_hybrid_step(cev_fdtd* p, const cev_state* in, const cev_state* out, const int box[6], const double* wave_row,
+                       int n_aux_slots, int64_t probe_t, double* partials, cudaStream_t s) {
+    constexpr int V = vec_width<T>();
+    const dim3 blk(32, V2_BY);
+    // 1. interior: fused H + D, in -> out
+    {
+        StepArgs<T, AT> a;
+        if (fill_args(p, in, a)) return -1;
+        for (int A = 0; A < 3; ++A) {
+            const int L = p->to_logical(A);
+            a.Hout[A] = (T*)out->H[L];
+            a.Dout[A] = (T*)out->D[L];
+        }
+        if (launch_fused_shape<T, AT, 16, 4>(p, a, wave_row, n_aux_slots, probe_t, partials, s, box)) return -1;
+    }
+    // 2. shell, H half-step: reads in.D / in.H, writes out.H
+    {
+        StepArgs<T, AT> a;
+        if (fill_args(p, in, a)) return -1;
+        for (int A = 0; A < 3; ++A) a.Hout[A] = (T*)out->H[p->to_logical(A)];
+        set_tiles_v2(p, a, 0, a.Nx, 2, 0, 0, box);
+        a.t_probe = -1;
+        if (a.n_tiles > 0) {
+            if (p->lz == 8) k_step_H_v2<T, AT, V, 8, false><<<a.n_tiles, blk, 0, s>>>(a);
+            else if (p->lz == 16) k_step_H_v2<T, AT, V, 16, false><<<a.n_tiles, blk, 0, s>>>(a);
+            else k_step_H_v2<T, AT, V, 32, false><<<a.n_tiles, blk, 0, s>>>(a);
+        }
+    }
+    // 3. shell, D half-step: reads out.H (shell cells and their interior neighbours) and in.D, writes out.D
+    {
+        cev_state mid = *in;
+        for (int c = 0; c < 3; ++c) mid.H[c] = out->H[c];
+        StepArgs<T, AT> a;
+        if (fill_args(p, &mid, a)) return -1;
+        for (int A = 0; A < 3; ++A) a.Dout[A] = (T*)out->D[p->to_logical(A)];
+        set_tiles_v2(p, a, 0, a.Nx, 2, 0, 0, box);
+        a.t_probe = -1;
+        if (wave_row && p->n_src_pts > 0 && attach_sources_v2(p, a, wave_row, 5)) return -1;
+        if (a.n_tiles > 0) {
+            if (p->lz == 8) k_step_D_v2<T, AT, V, 8, false, false><<<a.n_tiles, blk, 0, s>>>(a);
+            else if (p->lz == 16) k_step_D_v2<T, AT, V, 16, false, false><<<a.n_tiles, blk, 0, s>>>(a);
+            else k_step_D_v2<T, AT, V, 32, false, false><<<a.n_tiles, blk, 0, s>>>(a);
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // nsteps time steps; the result ends up in `st` (an odd step count starts with one two-kernel step).
 template <typename T, typename AT>
 int run_loop_fused(cev_fdtd* p, const cev_state* st, const cev_state* shadow, int64_t nsteps, const double* waveform,
@@ -937,9 +1011,32 @@ int run_loop_fused(cev_fdtd* p, const cev_state* st, const cev_state* shadow, in
         if (two_kernel_step(0)) return -1;
         n = 1;
     }
+    int hbox[6];
+    bool hybrid = p->variant == 5 && hybrid_box<T>(p, hbox);
+    if (hybrid) {          // same applicability rules as the fused kernel
+        StepArgs<T, AT> probe_args;
+        if (fill_args(p, st, probe_args)) return -1;
+        for (int A = 0; A < 3; ++A) {
+            probe_args.Hout[A] = (T*)B.H[p->to_logical(A)];
+            probe_args.Dout[A] = (T*)B.D[p->to_logical(A)];
+            probe_args.ICEout[A] = probe_args.ICE[A];
+        }
+        hybrid = can_fuse(p, probe_args) && can_march(p, probe_args, true);
+    }
+    if (hybrid)            // only H and D are ping-ponged: the shell kernels update the PML integrals in place
+        for (int c = 0; c < 3; ++c) {
+            B.ICE[c] = st->ICE[c];
+            B.IH[c] = st->IH[c];
+        }
     for (; n < nsteps; ++n) {
         bool done = false;
         const int slots = h_probes_pending ? p->n_slots : p->n_slots_ED;   // E/D probes of step n-1 always ride here
+        if (hybrid) {
+            if (launch_hybrid_step<T, AT>(p, cur, nxt, hbox, waveform ? waveform + n * p->nsrc : nullptr, slots, n - 1, partials, s)) return -1;
+            h_probes_pending = true;
+            std::swap(cur, nxt);
+            continue;
+        }
         if (launch_fused<T, AT>(p, cur, nxt, waveform ? waveform + n * p->nsrc : nullptr, slots, n - 1, partials, s, &done)) return -1;
         if (!done) {              // not fusable (geometry / alignment): finish with the two-kernel path, in `st`
             if (cur != st) return fail("internal: fused fallback on the shadow state");
@@ -1206,7 +1303,7 @@ int cev_fdtd_set_option(cev_fdtd* p, const char* name, int64_t value) {
         if (value < -1 || value > 1) return fail("use_graph must be -1 (auto: small grids), 0 or 1");
         p->use_graph = (int)value;
     } else if (!strcmp(name, "kernel_variant")) {
-        if (value < 0 || value > 4) return fail("kernel_variant must be 0 (auto), 1 (baseline), 2 (marching), 3 (TMA-staged) or 4 (fused)");
+        if (value < 0 || value > 5) return fail("kernel_variant must be 0 (auto), 1 (baseline), 2 (marching), 3 (TMA-staged), 4 (fused) or 5 (hybrid)");
         p->variant = (int)value;
     } else if (!strcmp(name, "fused_shape")) {
         if (value != 0 && value != 804 && value != 1604 && value != 1608 && value != 3204 && value != 3208)

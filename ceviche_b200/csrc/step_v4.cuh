@@ -170,19 +170,22 @@ __global__ void __launch_bounds__(32 * BY, (BY >= 8 ? 1 : ((NOPML || V4_PML_NOIN
     const int ty = rest % a.nty;
     const int xc = rest / a.nty;
 
-    const int Nzv = a.Nz / V;
-    int zv = tz * OZ - 1 + lz;
-    const bool own_z = lz >= 1 && zv < min((tz + 1) * OZ, Nzv);
+    // the launch covers box[0] (the whole grid, or -- hybrid path -- the PML-free interior); tiles are laid out from
+    // the box origin, halo rows / lanes may lie outside the box (they are only read)
+    const Box& B = a.box[0];
+    const int Nzv = a.Nz / V, bz0 = B.z0 / V, bz1 = B.z1 / V;
+    int zv = bz0 + tz * OZ - 1 + lz;
+    const bool own_z = lz >= 1 && zv < min(bz0 + (tz + 1) * OZ, bz1);
     if (zv < 0) zv = Nzv - 1;                    // halo lane of the first tile: periodic wrap
     if (zv >= Nzv) zv = Nzv - 1;                 // lanes past the row shadow a valid vector (no stores)
-    int j = ty * OY - 1 + r;
-    const bool own_y = r >= 1 && j < min((ty + 1) * OY, a.Ny);
+    int j = B.y0 + ty * OY - 1 + r;
+    const bool own_y = r >= 1 && j < min(B.y0 + (ty + 1) * OY, B.y1);
     if (j < 0) j = a.Ny - 1;
     if (j >= a.Ny) j = a.Ny - 1;
     const bool own = own_y && own_z;
     const int k0 = zv * V;
-    const int xs = a.x0 + xc * a.xchunk;
-    const int xe = min(xs + a.xchunk, a.x1);
+    const int xs = B.x0 + xc * a.xchunk;
+    const int xe = min(xs + a.xchunk, B.x1);
 
     const int plane = a.Ny * a.Nz;
     const int jp = (j + 1 == a.Ny) ? 0 : j + 1;

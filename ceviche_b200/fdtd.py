@@ -558,11 +558,11 @@ class fdtd:
         kernels; its PML-free instantiation (128 registers) is 20-25 % FASTER (profiles/README.md).  So: automatic on
         grids without any PML (periodic on all axes) of >= 2^21 cells, opt-in elsewhere (`kernel_variant` 4)."""
         kv = self._options.get("kernel_variant", 0)
-        if kv not in (0, 4) or steps < 2 or not self._fused_step:
+        if kv not in (0, 4, 5) or steps < 2 or not self._fused_step:
             return False
         if self._options.get("active_components", 63) != 63:
             return False
-        if kv == 4:
+        if kv in (4, 5):        # 5 = hybrid: lean fused kernel on the PML-free interior, general kernels on the shell
             return True
         return not any(int(p) for p in self.npml) and self.N >= (1 << 21) and min(self.grid_shape) >= 32
 

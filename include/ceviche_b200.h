@@ -108,7 +108,8 @@ int cev_fdtd_create(cev_fdtd** plan, int device, int dtype, int arith_f64,
 int cev_fdtd_destroy(cev_fdtd* plan);
 
 /* Tuning / test knobs: "kernel_variant" 0 auto | 1 baseline (one thread per cell) | 2 marching | 3 TMA-staged |
- * 4 fused full-step kernel in cev_fdtd_run_fused (0 also fuses there); "fused_shape" 0 auto | lanes_z*100 + warps;
+ * 4 fused full-step kernel in cev_fdtd_run_fused | 5 hybrid there (lean fused kernel on the PML-free interior, the
+ * half-step kernels on the PML shell); "fused_shape" 0 auto | lanes_z*100 + warps; "use_graph" / "jvp_streams" -1 auto | 0 | 1;
  * "xchunk" x-planes per CTA of the marching kernels (0 = auto); "lanes_z" 8|16|32 lanes of a warp along z;
  * "prefetch_planes" L2 prefetch distance; "split_launch" 0|1 separate launches for the PML-free interior and
  * the PML shell.  Results do not depend on them (bit-identical).

@@ -1,0 +1,6 @@
+mkdir -p gpurun_out; rm -f gpurun_out/tune_hybrid.log
+timeout 600 python -m pytest tests/test_gpu_variants.py -x -q -k "fused" 2>&1 | tail -3 >> gpurun_out/tune_hybrid.log
+for d in f64 f32; do for n in 256 512; do
+  TUNE_RUN=20 timeout 300 python scripts/tune.py $n $d "kernel_variant=0,fused_step=0" "kernel_variant=5,fused_step=1" "kernel_variant=5,xchunk=32" >> gpurun_out/tune_hybrid.log 2>&1
+done; done
+cat gpurun_out/tune_hybrid.log

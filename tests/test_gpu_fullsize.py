@@ -66,7 +66,8 @@ def test_full_size_kernel_variants_bitwise(dtype):
     ref_f = {k: ref.fields[k].clone() for k in FIELD_KEYS}
     ref_p = [t.clone() for fam in ("ICE", "IH", "ICH", "ID") for t in ref._pml[fam]]
     del ref
-    for opts in (dict(kernel_variant=0), dict(kernel_variant=2, split_launch=1), dict(kernel_variant=3), dict(kernel_variant=4)):
+    for opts in (dict(kernel_variant=0), dict(kernel_variant=2, split_launch=1), dict(kernel_variant=3), dict(kernel_variant=4),
+                 dict(kernel_variant=5)):
         F, s = _run(eps, sources, probes, steps, dtype, **opts)
         assert np.array_equal(s, s_ref), opts
         for k in FIELD_KEYS:

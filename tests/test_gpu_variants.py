@@ -75,7 +75,8 @@ def test_marching_equals_baseline_bitwise(shape, npml, dtype):
 
 
 FUSED_SHAPES = SHAPES + [((5, 3, 8), (1, 1, 2)), ((1, 6, 16), (0, 2, 3)), ((17, 1, 36), (3, 0, 4)), ((36, 31, 124), (5, 4, 6)),
-                         ((20, 9, 4), (3, 2, 0)), ((18, 14, 72), (0, 0, 0))]    # the last: no PML at all = the lean instantiation
+                         ((20, 9, 4), (3, 2, 0)), ((18, 14, 72), (0, 0, 0)),    # no PML at all = the lean instantiation
+                         ((44, 40, 96), (6, 5, 8)), ((40, 30, 72), (0, 4, 6)), ((52, 24, 64), (7, 0, 0))]   # hybrid boxes
 
 
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
@@ -86,9 +87,10 @@ def test_fused_step_equals_baseline_bitwise(shape, npml, dtype):
     tile shape and several x-chunkings (the pre-roll plane, halo rows / lanes and periodic wraps all differ)."""
     case = _case(shape, npml, 41, 7)
     ref = {n: _run(case, dtype, 1, steps=n) for n in (41, 40, 2)}
-    for fs, xchunk, n in ((0, 0, 41), (1604, 3, 40), (804, 1, 41), (1608, 1000, 40), (3204, 5, 41), (3208, 2, 2), (0, 7, 2)):
+    for fs, xchunk, n in ((0, 0, 41), (1604, 3, 40), (804, 1, 41), (1608, 1000, 40), (3204, 5, 41), (3208, 2, 2), (0, 7, 2),
+                          (-5, 0, 41), (-5, 6, 40)):       # fs = -5: the hybrid path (kernel_variant 5)
         s1, f1, p1 = ref[n]
-        s4, f4, p4 = _run(case, dtype, 4, xchunk, fused_shape=fs, steps=n)
+        s4, f4, p4 = _run(case, dtype, 5 if fs < 0 else 4, xchunk, fused_shape=max(fs, 0), steps=n)
         for k in FIELD_KEYS:
             assert np.array_equal(f1[k], f4[k]), (k, fs, xchunk, n)
         for q, (a, b) in enumerate(zip(p1, p4)):
