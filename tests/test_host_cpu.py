@@ -104,3 +104,42 @@ def test_coupled_components_closure():
             seen = sum(1 << q for q, n in enumerate("xyz") if np.any(f["D" + n])) | \
                 sum(8 << q for q, n in enumerate("xyz") if np.any(f["H" + n]))
             assert seen == coupled_components(shape, 1 << c), (shape, comp)
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: the header must compile as C99 (and as C++), with no torch / CUDA types, and a C
+    translation unit that calls through it must link against the built library."""
+    import shutil
+    import subprocess
+    import tempfile
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    header = os.path.join(ROOT, "include", "ceviche_b200.h")
+    subprocess.run([gcc, "-x", "c", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", header], check=True)
+    subprocess.run([shutil.which("g++") or gcc, "-x", "c++", "-std=c++17", "-fsyntax-only", header], check=True)
+    assert "#include <torch" not in open(header).read() and "#include <cuda" not in open(header).read()
+    from ceviche_b200 import build
+    lib = build.LIB_PATH
+    if not os.path.isfile(lib):
+        pytest.skip("library not built")
+    src = r"""
+#include "ceviche_b200.h"
+#include <stdio.h>
+int main(void) {
+    cev_fdtd* plan = 0;
+    /* no GPU needed: an invalid dtype is rejected before any CUDA call */
+    int rc = cev_fdtd_create(&plan, 0, 7, 1, 4, 4, 4, 5e-8, 1e-16, 0, 0);
+    printf("%d %d %s\n", cev_abi_version(), rc, cev_last_error());
+    return (rc != 0 && plan == 0) ? 0 : 1;
+}
+"""
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "t.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "t")
+        subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), c, lib, "-Wl,-rpath," + os.path.dirname(lib),
+                        "-o", exe], check=True)
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert out.stdout.split()[0] == "1" and "dtype" in out.stdout
