@@ -93,6 +93,8 @@ def grad_case(name):
         return dict(eps=eps, dL=DL, npml=[2, 2, 0], steps=steps,
                     sources=[(comp, prof, gaussian(steps, 300, 20, 1.0))],
                     probes=[(k, np.ones(shape)) for k in keys], mode=name.split("_")[1])
+    if name == "c4_small":
+        return scaled_case("c4_small")
     if name == "probe3d":
         # SURVEY appendix B check: PML on all axes, two sources, dense weights on E / H / D
         case = _small3d((10, 9, 7), (3, 2, 2), 60, 31)
@@ -101,9 +103,77 @@ def grad_case(name):
     raise KeyError(name)
 
 
-GRAD_CASES = ("ref_rev_E", "ref_rev_H", "ref_fwd_E", "ref_fwd_H", "probe3d")
+GRAD_CASES = ("ref_rev_E", "ref_rev_H", "ref_fwd_E", "ref_fwd_H", "probe3d", "c4_small")
 
 
 def objective_weights(steps, n_probes, seed=5):
     """Fixed cotangent for scalar objectives L = sum(w * series**2) on the probe series."""
     return np.random.default_rng(seed).random((steps, n_probes))
+
+
+# ---- scaled copies of the BASELINE configs (SURVEY 8d) -------------------------------------------------------------
+def _guide(shape, core=5.9536, split=True):
+    """Config-2 style geometry: a guide along x (half-widths scale with the grid) that splits into two arms."""
+    Nx, Ny, Nz = shape
+    eps = np.ones(shape)
+    cy, cz = Ny // 2, Nz // 2
+    hy, hz = max(1, Ny // 24), max(1, Nz // 32) if Nz > 1 else 1
+    off_max = Ny // 6
+    for i in range(Nx):
+        d = 0
+        if split and i >= Nx // 2:
+            d = int(round(off_max * min(1.0, (i - Nx // 2) / max(1, Nx // 2 - Nx // 8))))
+        for c in ({cy} if d == 0 else {cy - d, cy + d}):
+            eps[i, c - hy:c + hy, max(0, cz - hz):cz + hz if Nz > 1 else 1] = core
+    return eps, (cy, cz, hy, hz, off_max)
+
+
+def scaled_case(name):
+    """'c2_96': config 2 (3-D splitter, PML on all axes, Jz sheet source, arm probes) at 96^3 for 2000 steps.
+    'c4_small': config 4 (gradient of a windowed mode-overlap-like objective w.r.t. eps_r) at 32x28x20, 300 steps.
+    'c5_small': config 5 (forward-mode JVP over eps_r directions, 2-D TM) at 256x256, 1000 steps, 4 directions."""
+    from .fdtd_numpy import C_0, time_step
+    dt = time_step(DL)
+    omega = 2 * np.pi * C_0 / 2e-6
+    if name == "c2_96":
+        shape, steps = (96, 96, 96), 2000
+        eps, (cy, cz, hy, hz, off) = _guide(shape)
+        prof = np.zeros(shape); prof[14, cy - hy:cy + hy, cz - hz:cz + hz] = 1.0
+        t = np.arange(steps)
+        wave = 5 * np.exp(-(t - 300) ** 2 / (2 * 60.0 ** 2)) * np.cos(omega * dt * t)
+        probes = []
+        for c in (cy - off, cy + off):
+            m = np.zeros(shape); m[82, c - hy:c + hy, cz - hz:cz + hz] = 1.0
+            probes.append(("Ez", m))
+        m = np.zeros(shape); m[40, cy - hy:cy + hy, cz - hz:cz + hz] = 1.0
+        probes.append(("Hy", m))
+        return dict(eps=eps, dL=DL, npml=[12, 12, 12], steps=steps, sources=[("z", prof, wave)], probes=probes,
+                    snapshots=(steps,))
+    if name == "c4_small":
+        shape, steps = (32, 28, 20), 300
+        eps, (cy, cz, hy, hz, off) = _guide(shape, split=False)
+        rng = np.random.default_rng(1)
+        eps[12:20, cy - 4:cy + 4, cz - 2:cz + 2] = 1 + 4.95 * rng.random((8, 8, 4))      # the design box
+        prof = np.zeros(shape); prof[6, cy - hy:cy + hy, cz - hz:cz + hz] = 1.0
+        t = np.arange(steps)
+        wave = 3 * np.exp(-(t - 80) ** 2 / (2 * 25.0 ** 2)) * np.cos(omega * dt * t)
+        yy = np.exp(-((np.arange(shape[1]) - cy) / 2.0) ** 2)[:, None] * np.exp(-((np.arange(shape[2]) - cz) / 2.0) ** 2)[None, :]
+        m = np.zeros(shape); m[26] = yy                                              # a mode-like overlap mask
+        return dict(eps=eps, dL=DL, npml=[4, 4, 4], steps=steps, sources=[("z", prof, wave)], probes=[("Ez", m), ("Hy", m)],
+                    mode="rev")
+    if name == "c5_small":
+        shape, steps, B = (256, 256, 1), 1000, 4
+        eps = np.full(shape, 1.44 ** 2)
+        eps[:, 120:136, 0] = 3.48 ** 2                                               # slab waveguide
+        V = np.zeros((B,) + shape)
+        for b in range(B):                                                           # four grating-tooth groups
+            x0 = 70 + b * 36
+            eps[x0:x0 + 12, 136:144, 0] = 3.48 ** 2
+            V[b, x0:x0 + 12, 136:144, 0] = 1.0
+        prof = np.zeros(shape); prof[30, 120:136, 0] = 1.0
+        mask = np.zeros(shape); mask[60:220, 180, 0] = 1.0
+        t = np.arange(steps)
+        wave = np.exp(-(t - 150) ** 2 / (2 * 40.0 ** 2)) * np.cos(omega * dt * t)
+        return dict(eps=eps, dL=DL, npml=[10, 10, 0], steps=steps, sources=[("z", prof, wave)],
+                    probes=[("Ez", mask), ("Hx", mask)], directions=V)
+    raise KeyError(name)

@@ -169,9 +169,50 @@ def make_modes_golden():
     print("modes_ridge", vals)
 
 
+def make_c2_scaled_golden():
+    """Config 2 at 96^3 for 2000 steps: the first 150 steps by the REFERENCE ITSELF, all 2000 by the C restatement
+    (oracle/fdtd_c.c), asserted bit-identical on the overlap (and in tests/test_oracle_c.py in general)."""
+    from .fdtd_c import OracleFDTDC
+    case = cases.scaled_case("c2_96")
+    head = dict(case, steps=150, sources=[(c, p, w[:150]) for c, p, w in case["sources"]], snapshots=())
+    ref_series, _, F = run_reference(head)
+    O = OracleFDTDC(case["eps"], case["dL"], case["npml"])
+    series, snaps = O.run(case["steps"], case["sources"], case["probes"], case["snapshots"])
+    assert np.array_equal(series[:150], ref_series), "C restatement differs from the reference"
+    out = {"series": series, "dt": np.float64(F.dt), "stride": np.int64(6), "reference_steps": np.int64(150)}
+    for k, v in snaps[case["steps"]].items():
+        out["end_" + k] = v[::6, ::6, ::6]
+        out["end_%s_norm" % k] = np.float64(np.linalg.norm(v))
+    np.savez_compressed(os.path.join(OUT, "fields_c2_96.npz"), **out)
+    print("fields c2_96 series norm", np.linalg.norm(series, axis=0))
+
+
+def make_c5_scaled_golden():
+    """Config 5 at 256x256: d(series)/d(eps_r) along four directions by torch.func.jvp over the torch restatement, and
+    by a central finite difference through the REFERENCE's numpy code for the first direction."""
+    case = cases.scaled_case("c5_small")
+    shape = case["eps"].shape
+    fn = series_fn(shape, case["dL"], case["npml"], case["steps"], case["sources"], case["probes"])
+    eps0 = torch.as_tensor(case["eps"].copy())
+    series, ds = None, []
+    for b in range(case["directions"].shape[0]):
+        series, tan = torch.func.jvp(fn, (eps0,), (torch.as_tensor(case["directions"][b]),))
+        ds.append(tan.numpy())
+    h = 1e-4
+    up = run_reference(case, eps=case["eps"] + h * case["directions"][0])[0]
+    dn = run_reference(case, eps=case["eps"] - h * case["directions"][0])[0]
+    np.savez_compressed(os.path.join(OUT, "jvp_c5_small.npz"), series=series.numpy(), dseries=np.stack(ds),
+                        fd_central_dir0=(up - dn) / (2 * h))
+    print("jvp c5_small", np.linalg.norm(np.stack(ds), axis=(1, 2)), "fd/ad dir0",
+          np.linalg.norm((up - dn) / (2 * h) - ds[0]) / np.linalg.norm(ds[0]))
+
+
 def main(argv):
     os.makedirs(OUT, exist_ok=True)
-    which = argv[1:] or ["fields", "grads", "modes"]
+    which = argv[1:] or ["fields", "grads", "modes", "scaled"]
+    if "scaled" in which:
+        make_c2_scaled_golden()
+        make_c5_scaled_golden()
     if "modes" in which:
         make_modes_golden()
     if "fields" in which:

@@ -1,0 +1,71 @@
+"""Scaled copies of the BASELINE configs against committed golden vectors: config 2 at 96^3 for 2000 steps
+(reference itself for the first 150 steps, its bit-identical C restatement for the rest), config 4 at 32x28x20
+(gradient by torch.autograd over the torch restatement + finite differences through the reference), config 5 at
+256x256 (four tangent directions by torch.func.jvp + a finite difference through the reference)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cases
+from oracle.fdtd_numpy import FIELD_KEYS, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def test_config2_scaled_2000_steps(golden_dir):
+    import ceviche_b200
+    case = cases.scaled_case("c2_96")
+    gold = np.load(os.path.join(golden_dir, "fields_c2_96.npz"))
+    F = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"])
+    assert F.dt == float(gold["dt"])
+    series = F.run(case["steps"], case["sources"], case["probes"]).cpu().numpy()
+    s = int(gold["stride"])
+    for p in range(series.shape[1]):
+        assert np.abs(gold["series"][:, p]).max() > 0
+        assert rel_l2(series[:, p], gold["series"][:, p]) <= 1e-10, p
+    for k in FIELD_KEYS:
+        f = F.fields[k].cpu().numpy()
+        assert rel_l2(f[::s, ::s, ::s], gold["end_" + k]) <= 1e-10, k
+        assert abs(float(np.linalg.norm(f)) - float(gold["end_%s_norm" % k])) <= 1e-10 * float(gold["end_%s_norm" % k]), k
+    # fp32 storage: the 1e-5 bar holds on <= 1000-step runs; checked on the first 1000 steps
+    F32 = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"], dtype=torch.float32)
+    s32 = F32.run(1000, [(c, p, w[:1000]) for c, p, w in case["sources"]], case["probes"]).cpu().numpy()
+    for p in range(series.shape[1]):
+        assert rel_l2(s32[:, p], gold["series"][:1000, p]) <= 1e-5, p
+
+
+def test_config4_scaled_gradient(golden_dir):
+    import ceviche_b200
+    case = cases.grad_case("c4_small")
+    gold = np.load(os.path.join(golden_dir, "grad_c4_small.npz"))
+    w = torch.as_tensor(cases.objective_weights(case["steps"], len(case["probes"]))).cuda()
+    for every in (None, 7):
+        eps = torch.as_tensor(case["eps"]).cuda().requires_grad_(True)
+        F = ceviche_b200.fdtd(eps, case["dL"], case["npml"])
+        series = F.run(case["steps"], case["sources"], case["probes"], checkpoint_every=every)
+        L = (series ** 2 * w).sum()
+        (g,) = torch.autograd.grad(L, eps)
+        assert abs(float(L.detach()) - float(gold["value"])) <= 1e-10 * abs(float(gold["value"]))
+        assert rel_l2(g.cpu().numpy(), gold["grad_ad"]) <= 1e-10
+        cells = gold["fd_cells"]
+        got = np.array([g[tuple(c)].item() for c in cells])
+        assert rel_l2(got, gold["fd_central"]) <= 1e-5        # FD through the REFERENCE's numpy code
+        assert rel_l2(got, gold["fd_one_sided"]) <= 1e-4      # the reference's own criterion
+
+
+def test_config5_scaled_batched_jvp(golden_dir):
+    import ceviche_b200
+    case = cases.scaled_case("c5_small")
+    gold = np.load(os.path.join(golden_dir, "jvp_c5_small.npz"))
+    F = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"])
+    series, dseries = F.jvp_run(case["steps"], torch.as_tensor(case["directions"]), case["sources"], case["probes"])
+    assert F._active == 0b011100                                   # TM: the masked marching kernels served it
+    series, dseries = series.cpu().numpy(), dseries.cpu().numpy()
+    for p in range(series.shape[1]):
+        assert rel_l2(series[:, p], gold["series"][:, p]) <= 1e-10
+    for b in range(dseries.shape[0]):
+        assert np.abs(gold["dseries"][b]).max() > 0
+        assert rel_l2(dseries[b], gold["dseries"][b]) <= 1e-10, b
+    assert rel_l2(dseries[0], gold["fd_central_dir0"]) <= 1e-5   # FD through the REFERENCE's numpy code

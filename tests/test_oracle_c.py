@@ -36,3 +36,15 @@ def test_c_oracle_against_reference_golden(golden_dir):
     for t in case["snapshots"]:
         for k in FIELD_KEYS:
             assert np.array_equal(snaps[t][k][::s, ::s, :], gold["t%d_%s" % (t, k)]), (t, k)
+
+
+def test_c_oracle_reproduces_scaled_config2_prefix(golden_dir):
+    """The 96^3 / 2000-step fixture of config 2 (its first 150 steps come from the reference itself): the first 200
+    steps recomputed here, bit for bit."""
+    case = cases.scaled_case("c2_96")
+    gold = np.load(os.path.join(golden_dir, "fields_c2_96.npz"))
+    n = 200
+    O = OracleFDTDC(case["eps"], case["dL"], case["npml"])
+    series, _ = O.run(n, [(c, p, w[:n]) for c, p, w in case["sources"]], case["probes"])
+    assert np.array_equal(series, gold["series"][:n])
+    assert int(gold["reference_steps"]) == 150
