@@ -55,7 +55,8 @@ def _rendezvous(tmp_path):
 
 @pytest.mark.parametrize("dtype_name", ["float64", "float32"])
 @pytest.mark.parametrize("shape,npml", [((24, 20, 72), (4, 3, 6)), ((14, 9, 40), (0, 2, 3)),
-                                        ((40, 64, 1), (5, 6, 0))])       # the last one: a 2-D grid (relabelled x, z, y)
+                                        ((40, 64, 1), (5, 6, 0)),        # a 2-D grid (relabelled x, z, y)
+                                        ((256, 128, 64), (20, 20, 20))]) # the parity grid of BASELINE config 3
 def test_slabs_bit_identical_to_single_gpu(shape, npml, dtype_name, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -72,3 +73,12 @@ def test_slabs_bit_identical_to_single_gpu(shape, npml, dtype_name, tmp_path):
     for k in F.fields:
         assert np.array_equal(got[k], F.fields[k].cpu().numpy()), k
     np.testing.assert_allclose(got["series"], series, rtol=1e-11, atol=1e-12 * np.abs(series).max())
+    if shape == (256, 128, 64) and dtype_name == "float64":     # ... and that grid against the CPU oracle
+        from oracle.fdtd_c import OracleFDTDC
+        from oracle.fdtd_numpy import rel_l2
+        O = OracleFDTDC(case["eps"], case["dL"], case["npml"])
+        o_series, _ = O.run(steps, case["sources"], case["probes"])
+        for k in F.fields:
+            assert rel_l2(got[k], O.fields()[k]) <= 1e-10, k
+        for p in range(series.shape[1]):
+            assert rel_l2(got["series"][:, p], o_series[:, p]) <= 1e-10, p
