@@ -133,7 +133,7 @@ struct cev_fdtd {
     std::vector<cudaStream_t> side;        // forward mode: one side stream (+ event) per tangent state
     std::vector<cudaEvent_t> side_ev;
     cudaEvent_t main_ev = nullptr;
-    int jvp_streams = -1;        // -1 auto (grids <= 2^23 cells), 0 never, 1 always
+    int jvp_streams = -1;        // -1 auto (2-D grids <= 2^23 cells, any grid <= 2^20 cells), 0 never, 1 always
     uint64_t epoch = 1;          // bumped whenever sources, probes or options change
     int use_graph = -1;          // -1 auto (small grids), 0 never, 1 whenever possible
     void drop_graphs() {
@@ -782,7 +782,9 @@ int jvp_loop(cev_fdtd* p, const cev_state* st, int B, const cev_state* tst, cons
     // half-step reads the primal D of the previous step (so it waits for the primal D launch, and the next primal D
     // launch waits for it); a tangent D half-step only touches its own state.
     const int64_t cells = (int64_t)p->N[0] * p->N[1] * p->N[2];
-    const bool fork = B >= 2 && (p->jvp_streams == 1 || (p->jvp_streams < 0 && cells <= ((int64_t)1 << 23)));
+    // auto: where it was measured to pay (scripts/tune2d.py) -- 2-D grids up to 2^23 cells, and small grids of any shape
+    const bool small = cells <= ((int64_t)1 << 20) || (p->N[1] == 1 && cells <= ((int64_t)1 << 23));
+    const bool fork = B >= 2 && (p->jvp_streams == 1 || (p->jvp_streams < 0 && small));
     if (fork) {
         while ((int)p->side.size() < B) {
             cudaStream_t q;
