@@ -180,3 +180,34 @@ def test_inverse_design_loop_improves_mode_overlap():
     assert abs(float(fd) - float(g0 @ d)) <= 1e-6 * abs(float(fd))
     rho, hist = adam_optimize(objective, rho0, True, step_size=0.1, Nsteps=4, bounds=(0.0, 1.0), direction="max", verbose=False)
     assert hist[-1] > hist[0] > 0 and float(rho.min()) >= 0.0 and float(rho.max()) <= 1.0
+
+
+def test_hips_autograd_registration_callables():
+    """ceviche_b200.hips registers the FDTD run in the reference's operator-extension style (primitives.py:28-54).
+    HIPS autograd is not installed: a stand-in `extend` records the registrations, and the registered VJP / JVP are
+    checked against torch.autograd / jvp_run directly."""
+    import types
+    import ceviche_b200
+    from ceviche_b200 import hips
+    reg = {}
+    ext = types.SimpleNamespace(primitive=lambda f: f,
+                                defvjp=lambda f, *makers: reg.setdefault("vjp", (f, makers)),
+                                defjvp=lambda f, *jvps: reg.setdefault("jvp", (f, jvps)))
+    prim = hips.register(ext)
+    assert reg["vjp"][0] is prim and reg["jvp"][0] is prim
+    assert all(m is None for m in reg["vjp"][1][1:]) and all(m is None for m in reg["jvp"][1][1:])
+    case = cases.grad_case("probe3d")
+    F = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"])
+    series = prim(case["eps"], F, case["steps"], case["sources"], case["probes"])
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal(series.shape)
+    g_hips = reg["vjp"][1][0](series, case["eps"], F, case["steps"], case["sources"], case["probes"])(v)
+    eps = torch.as_tensor(case["eps"]).cuda().requires_grad_(True)
+    F2 = ceviche_b200.fdtd(eps, case["dL"], case["npml"])
+    s2 = F2.run(case["steps"], case["sources"], case["probes"])
+    (g_ref,) = torch.autograd.grad(s2, eps, grad_outputs=torch.as_tensor(v).cuda())
+    assert np.array_equal(series, s2.detach().cpu().numpy())
+    assert rel_l2(g_hips, g_ref.cpu().numpy()) <= 1e-12
+    d = rng.standard_normal(case["eps"].shape)
+    t_hips = reg["jvp"][1][0](d, series, case["eps"], F, case["steps"], case["sources"], case["probes"])
+    assert abs(float((t_hips * v).sum()) - float((g_hips * d).sum())) <= 1e-9 * abs(float((g_hips * d).sum()))   # <v, J d> = <J^T v, d>

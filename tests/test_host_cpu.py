@@ -143,3 +143,19 @@ int main(void) {
         out = subprocess.run([exe], capture_output=True, text=True)
         assert out.returncode == 0, out.stdout + out.stderr
         assert out.stdout.split()[0] == "1" and "dtype" in out.stdout
+
+
+def test_hips_binding_is_a_soft_dependency():
+    """Without HIPS autograd the module imports and exposes no primitive; with an `extend` module the registration uses
+    exactly the reference's protocol (one maker for eps_r, None for the other arguments)."""
+    import types
+    from ceviche_b200 import hips
+    import importlib.util
+    if importlib.util.find_spec("autograd") is None:
+        assert hips.fdtd_series is None
+    calls = []
+    ext = types.SimpleNamespace(primitive=lambda f: f, defvjp=lambda f, *m: calls.append(("vjp", len(m), m[1:])),
+                                defjvp=lambda f, *m: calls.append(("jvp", len(m), m[1:])))
+    prim = hips.register(ext)
+    assert callable(prim) and [c[0] for c in calls] == ["vjp", "jvp"]
+    assert all(c[1] == 5 and all(x is None for x in c[2]) for c in calls)
