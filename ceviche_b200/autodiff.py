@@ -241,6 +241,13 @@ def jvp_run(sim, steps, waveforms, eps_tangents):
     """Primal + B tangents.  eps_tangents: [B, Nx, Ny, Nz] directions in eps_r.
     Returns (series [steps, P], dseries [B, steps, P])."""
     plan = sim._ensure_plan()
+    if sim.t_index != 0 or any(bool(t.requires_grad) for t in sim._H + sim._D):
+        # the tangent states start at zero: a primal state that already depends on eps_r (earlier run() / forward()
+        # calls with this permittivity) would drop d(state)/d(eps) of that history -- same rule as the reverse-mode run()
+        raise RuntimeError("jvp_run() must start from initialize_fields(): tangents do not chain across run() calls "
+                           "(use the per-step forward() API under torch.autograd.forward_ad for that)")
+    if sim._n_mon_pts > 0:
+        raise RuntimeError("jvp_run() does not accumulate running-DFT monitors: clear them with set_monitors([], [])")
     v = eps_tangents.to(device=sim.device, dtype=torch.float64)
     if v.dim() == 3:
         v = v.unsqueeze(0)

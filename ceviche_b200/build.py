@@ -12,7 +12,7 @@ HEADER = os.path.join(ROOT, "include", "ceviche_b200.h")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17",
+    "-O3", "-lineinfo", "-std=c++17", "--threads", "0",
     "-Xcompiler", "-fPIC", "-shared",
     "--expt-relaxed-constexpr",
 ]

@@ -19,6 +19,7 @@
 #include "step_v2.cuh"
 #include "step_v3.cuh"
 #include "step_v4.cuh"
+#include "step_v5.h"
 #include "adjoint.cuh"
 
 namespace {
@@ -50,6 +51,10 @@ constexpr int PROBE_CHUNK = 8192;   // points per probe slot (one CTA each)
 struct DeviceBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    DeviceBuf() = default;
+    DeviceBuf(const DeviceBuf&) = delete;
+    DeviceBuf& operator=(const DeviceBuf&) = delete;
+    ~DeviceBuf() { release(); }          // (owners are destroyed with their device current: cev_fdtd_destroy / create)
     int alloc(size_t n) {
         release();
         if (n == 0) return 0;
@@ -80,7 +85,11 @@ struct cev_fdtd {
     double dL = 0, dt = 0, cdt = 0;
     int nH[3] = {0, 0, 0}, nD[3] = {0, 0, 0};   // internal compact counts
     int variant = 0;             // 0 auto, 1 baseline kernels, 2 marching kernels, 3 TMA-staged marching kernels,
-                                 // 4 fused full-step kernel wherever it applies (cev_fdtd_run_fused)
+                                 // 4 fused full-step kernel wherever it applies (cev_fdtd_run_fused), 5 hybrid,
+                                 // 6 tensor-map TMA kernels (step_v5.cuh) wherever they apply
+    int tma_rows = 4, tma_stages_H = 3, tma_stages_D = 4;   // tile rows / ring depths of the tensor-map kernels
+    int auto_v5 = 0;                    // kernel_variant 0 (auto) picks them on large 3-D grids
+    cev::V5MapCache* v5 = nullptr;      // CUtensorMap descriptors of this plan's arrays
     int fused_shape = 0;         // tile shape of the fused kernel: 0 auto, else LZ*100 + BY
     int xchunk = 0;              // 0 auto
     int pf_dist = 1;             // L2 prefetch distance of the marching kernels (planes)
@@ -104,7 +113,7 @@ struct cev_fdtd {
     std::vector<int64_t> h_src_cell;
     std::vector<double> h_src_w;
     struct SrcTiling {                              // source points sorted by owning CTA of one launch geometry
-        int x0, x1, xchunk, lz, vec, part, rows;
+        int x0, x1, xchunk, lz, vec, part, rows, xorder;
         DeviceBuf begin, comp, id, cell, w;
     };
     std::vector<std::unique_ptr<SrcTiling>> src_tilings;
@@ -364,7 +373,7 @@ int attach_sources_v2(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row, i
     const int rows = rows_override ? rows_override : V2_BY * (32 / LZ);
     for (auto& t : p->src_tilings)
         if (t->x0 == a.x0 && t->x1 == a.x1 && t->xchunk == a.xchunk && t->lz == LZ && t->vec == V && t->part == part &&
-            t->rows == rows)
+            t->rows == rows && t->xorder == a.xorder)
             hit = t.get();
     if (!hit) {
         const int zcells = (LZ < 0 ? -LZ : LZ) * V;
@@ -377,7 +386,9 @@ int attach_sources_v2(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row, i
             for (int b = 0; b < a.n_boxes; ++b) {
                 const Box& B = a.box[b];
                 if (i < B.x0 || i >= B.x1 || j < B.y0 || j >= B.y1 || k < B.z0 || k >= B.z1) continue;
-                owner.push_back(B.cta0 + (((i - B.x0) / a.xchunk) * B.nty + (j - B.y0) / rows) * B.ntz + (k - B.z0) / zcells);
+                int xc = (i - B.x0) / a.xchunk;
+                if (a.xorder) xc = v5_rank_of_chunk(xc, (B.x1 - B.x0 + a.xchunk - 1) / a.xchunk);
+                owner.push_back(B.cta0 + (xc * B.nty + (j - B.y0) / rows) * B.ntz + (k - B.z0) / zcells);
                 pick.push_back(q);
                 break;
             }
@@ -400,6 +411,7 @@ int attach_sources_v2(cev_fdtd* p, StepArgs<T, AT>& a, const double* wave_row, i
         for (int b = 0; b < a.n_tiles; ++b) begin[b + 1] += begin[b];
         std::unique_ptr<cev_fdtd::SrcTiling> t(new cev_fdtd::SrcTiling());
         t->x0 = a.x0; t->x1 = a.x1; t->xchunk = a.xchunk; t->lz = LZ; t->vec = V; t->part = part; t->rows = rows;
+        t->xorder = a.xorder;
         const size_t mm = (size_t)(m > 0 ? m : 1);
         if (t->begin.alloc(begin.size() * 4) || t->comp.alloc(mm * 4) || t->id.alloc(mm * 4) || t->cell.alloc(mm * 4) ||
             t->w.alloc(mm * 8))
@@ -432,6 +444,17 @@ int attach_probes(const cev_fdtd* p, StepArgs<T, AT>& a, int which, int64_t t, d
     a.t_probe = t;
     a.partials = partials;
     return which == 0 ? p->n_slots_ED : p->n_slots - p->n_slots_ED;
+}
+
+// The tensor-map TMA kernels (step_v5.cuh) serve whole y-z planes of 3-D grids with all six components live.
+template <typename T, typename AT>
+bool want_v5(cev_fdtd* p, const StepArgs<T, AT>& a, int64_t x0, int64_t x1) {
+    if (p->variant != 6 && p->variant != 0) return false;
+    if (p->variant == 0 && !p->auto_v5) return false;
+    if (x1 <= x0 || !v5_eligible<T, AT>(a, p->tma_rows)) return false;
+    if (p->variant == 0 && (int64_t)a.Ny * a.Nz < (1 << 14)) return false;     // small planes: too few CTAs per chunk
+    if (!p->v5) p->v5 = v5_cache_create();
+    return true;
 }
 
 template <typename T, typename AT>
@@ -467,6 +490,12 @@ int launch_H(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, void* con
         else if (a.wz && a.on == (unsigned)MASK_TE) k_step_H_v2<T, AT, V, 32, false, MASK_TE, true><<<g, blk, 0, s>>>(a);
         else k_step_H_v2<T, AT, V, 32, false, -1, true><<<g, blk, 0, s>>>(a);
         CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
+    if (want_v5(p, a, x0, x1)) {                // tensor-map TMA kernel: box copies described by CUtensorMaps
+        v5_set_tiles(a, x0, x1, p->tma_rows, p->xchunk);
+        const int aux = attach_probes(p, a, 0, probe_t, partials);
+        if (v5_launch_H<T, AT>(p->v5, a, p->tma_rows, p->tma_stages_H, aux, s)) return fail("%s", v5_last_error());
         return 0;
     }
     if (p->variant == 3 && a.on == 63u) {       // TMA-staged kernel: one launch, rows of 32 vectors
@@ -556,6 +585,13 @@ int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const
     const dim3 blk(32, V2_BY);
     const bool extras = a.J[0] || a.J[1] || a.J[2] || a.Eout[0] || a.Eout[1] || a.Eout[2];
     if (extras) a.on = 63u;
+    if (!extras && want_v5(p, a, x0, x1)) {     // tensor-map TMA kernel
+        v5_set_tiles(a, x0, x1, p->tma_rows, p->xchunk);
+        if (inject && attach_sources_v2(p, a, wave_row, 0, 32, p->tma_rows)) return -1;
+        const int aux = attach_probes(p, a, 1, probe_t, partials);
+        if (v5_launch_D<T, AT>(p->v5, a, p->tma_rows, p->tma_stages_D, aux, s)) return fail("%s", v5_last_error());
+        return 0;
+    }
     // auto: the TMA-staged D kernel wins in fp64 (measured, scripts/tune.py); fp32 and the H half-step stay on the
     // register-marching kernels
     if ((p->variant == 3 || ((p->variant == 0 || p->variant >= 4) && sizeof(T) == 8 && x1 - x0 >= 4 && a.Ny >= V3_BY)) && !extras && a.on == 63u) {
@@ -1283,6 +1319,7 @@ int cev_fdtd_destroy(cev_fdtd* p) {
     for (auto q : p->side) cudaStreamDestroy(q);
     for (auto e : p->side_ev) cudaEventDestroy(e);
     if (p->main_ev) cudaEventDestroy(p->main_ev);
+    if (p->v5) v5_cache_destroy(p->v5);
     p->tables.release();
     p->src_comp.release(); p->src_id.release(); p->src_cell.release(); p->src_weight.release();
     for (auto& t : p->src_tilings) {
@@ -1305,8 +1342,19 @@ int cev_fdtd_set_option(cev_fdtd* p, const char* name, int64_t value) {
         if (value < -1 || value > 1) return fail("use_graph must be -1 (auto: small grids), 0 or 1");
         p->use_graph = (int)value;
     } else if (!strcmp(name, "kernel_variant")) {
-        if (value < 0 || value > 5) return fail("kernel_variant must be 0 (auto), 1 (baseline), 2 (marching), 3 (TMA-staged), 4 (fused) or 5 (hybrid)");
+        if (value < 0 || value > 6)
+            return fail("kernel_variant must be 0 (auto), 1 (baseline), 2 (marching), 3 (TMA-staged), 4 (fused), 5 (hybrid) or 6 (tensor-map TMA)");
         p->variant = (int)value;
+    } else if (!strcmp(name, "tma_rows")) {
+        if (!v5_supported_shape((int)value, 3)) return fail("tma_rows must be 4 or 8");
+        p->tma_rows = (int)value;
+    } else if (!strcmp(name, "tma_stages") || !strcmp(name, "tma_stages_H") || !strcmp(name, "tma_stages_D")) {
+        if (!v5_supported_shape(p->tma_rows, (int)value)) return fail("%s must be 3 or 4", name);
+        if (name[10] != 'D') p->tma_stages_H = (int)value;      // "tma_stages" sets both
+        if (name[10] != 'H') p->tma_stages_D = (int)value;
+    } else if (!strcmp(name, "auto_tensor_map")) {
+        if (value != 0 && value != 1) return fail("auto_tensor_map must be 0 or 1");
+        p->auto_v5 = (int)value;
     } else if (!strcmp(name, "fused_shape")) {
         if (value != 0 && value != 804 && value != 1604 && value != 1608 && value != 3204 && value != 3208)
             return fail("fused_shape must be 0 (auto) or one of 804, 1604, 1608, 3204, 3208 (lanes_z*100 + warps)");
@@ -1441,11 +1489,11 @@ int cev_fdtd_set_sources(cev_fdtd* p, int nsrc, const cev_points* src) {
         if (src[s].n > ncell) return fail("source %d: more points than cells", s);
         total += src[s].n;
     }
-    p->epoch++;
-    p->nsrc = nsrc;
-    p->n_src_pts = total;
-    if (p->src_comp.alloc(total * 4) || p->src_id.alloc(total * 4) || p->src_cell.alloc(total * 8) || p->src_weight.alloc(total * 8)) return -1;
+    // everything is fetched and validated on the host BEFORE the plan is touched: a failing call leaves the
+    // previous sources (and their tilings) in place
     std::vector<int32_t> comp(total), id(total);
+    std::vector<int64_t> cell(total);
+    std::vector<double> w(total);
     int64_t off = 0;
     for (int s = 0; s < nsrc; ++s) {
         for (int64_t q = 0; q < src[s].n; ++q) {
@@ -1453,29 +1501,34 @@ int cev_fdtd_set_sources(cev_fdtd* p, int nsrc, const cev_points* src) {
             id[off + q] = s;
         }
         if (src[s].n) {
-            CUDA_TRY(cudaMemcpy((int64_t*)p->src_cell.p + off, src[s].idx, src[s].n * 8, cudaMemcpyDeviceToDevice));
-            CUDA_TRY(cudaMemcpy((double*)p->src_weight.p + off, src[s].weight, src[s].n * 8, cudaMemcpyDeviceToDevice));
+            CUDA_TRY(cudaMemcpy(cell.data() + off, src[s].idx, src[s].n * 8, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(w.data() + off, src[s].weight, src[s].n * 8, cudaMemcpyDeviceToHost));
         }
         off += src[s].n;
     }
+    for (int64_t q = 0; q < total; ++q)
+        if (cell[q] < 0 || cell[q] >= ncell) return fail("source point outside the grid");
+    DeviceBuf d_comp, d_id, d_cell, d_w;
+    if (d_comp.alloc(total * 4) || d_id.alloc(total * 4) || d_cell.alloc(total * 8) || d_w.alloc(total * 8)) return -1;
     if (total) {
-        CUDA_TRY(cudaMemcpy(p->src_comp.p, comp.data(), total * 4, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(p->src_id.p, id.data(), total * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d_comp.p, comp.data(), total * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d_id.p, id.data(), total * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d_cell.p, cell.data(), total * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d_w.p, w.data(), total * 8, cudaMemcpyHostToDevice));
     }
-    p->h_src_comp = comp;
-    p->h_src_id = id;
-    p->h_src_cell.resize(total);
-    p->h_src_w.resize(total);
-    if (total) {
-        CUDA_TRY(cudaMemcpy(p->h_src_cell.data(), p->src_cell.p, total * 8, cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemcpy(p->h_src_w.data(), p->src_weight.p, total * 8, cudaMemcpyDeviceToHost));
-        for (int64_t q = 0; q < total; ++q)
-            if (p->h_src_cell[q] < 0 || p->h_src_cell[q] >= ncell) return fail("source point outside the grid");
-    }
-    for (auto& t : p->src_tilings) {
-        t->begin.release(); t->comp.release(); t->id.release(); t->cell.release(); t->w.release();
-    }
-    p->src_tilings.clear();
+    // commit
+    p->epoch++;
+    p->nsrc = nsrc;
+    p->n_src_pts = total;
+    std::swap(p->src_comp.p, d_comp.p); std::swap(p->src_comp.bytes, d_comp.bytes);
+    std::swap(p->src_id.p, d_id.p); std::swap(p->src_id.bytes, d_id.bytes);
+    std::swap(p->src_cell.p, d_cell.p); std::swap(p->src_cell.bytes, d_cell.bytes);
+    std::swap(p->src_weight.p, d_w.p); std::swap(p->src_weight.bytes, d_w.bytes);
+    p->h_src_comp.swap(comp);
+    p->h_src_id.swap(id);
+    p->h_src_cell.swap(cell);
+    p->h_src_w.swap(w);
+    p->src_tilings.clear();          // (DeviceBuf destructors free the device copies)
     return 0;
 }
 
@@ -1492,6 +1545,12 @@ int cev_fdtd_set_probes(cev_fdtd* p, int nprobe, const cev_points* probe, int64_
         if (P.field < 0 || P.field > 8) return fail("probe %d: field code must be 0..8", q);
         if (P.n < 0 || (P.n > 0 && !P.weight)) return fail("probe %d: needs a weight array", q);
         if (!P.idx && (P.cell0 < 0 || P.cell0 + P.n > ncell)) return fail("probe %d: dense range outside the grid", q);
+        if (P.idx && P.n > 0) {      // sparse point sets are read and scattered to (adjoint seeds) unchecked by the kernels
+            std::vector<int64_t> cells(P.n);
+            CUDA_TRY(cudaMemcpy(cells.data(), P.idx, P.n * 8, cudaMemcpyDeviceToHost));
+            for (int64_t r = 0; r < P.n; ++r)
+                if (cells[r] < 0 || cells[r] >= ncell) return fail("probe %d: point outside the grid", q);
+        }
         woff[q] = wtotal;
         ioff[q] = P.idx ? itotal : -1;
         wtotal += P.n;

@@ -51,6 +51,15 @@ struct Box {
 };
 constexpr int MAX_BOXES = 6;
 
+// Outside-in order of the x-chunks of a launch (tensor-map kernels): rank 0, 1, 2, 3 ... -> chunk first, last, second,
+// last but one ...; the chunks in the x-PML (the slowest CTAs) start first, cheap interior chunks fill the tail.
+__host__ __device__ __forceinline__ int v5_chunk_of_rank(int r, int nchunks) {
+    return (r & 1) ? nchunks - 1 - (r >> 1) : (r >> 1);
+}
+__host__ __device__ __forceinline__ int v5_rank_of_chunk(int c, int nchunks) {
+    return (2 * c <= nchunks - 1) ? 2 * c : 2 * (nchunks - 1 - c) + 1;
+}
+
 // Everything a half-step kernel needs.  Axes/components are in the plan's INTERNAL order
 // (a cyclic relabelling of x,y,z chosen so that the last internal axis is the contiguous
 // one with extent > 1; see cev_fdtd.cu).  T = storage type, AT = arithmetic type.
@@ -106,6 +115,7 @@ struct StepArgs {
     unsigned on;
     int n_tiles, ntz, nty, xchunk;
     int wz;                   // marching kernels: 1 = the warps of a CTA tile z (grids with a single row per plane)
+    int xorder;               // tensor-map kernels: 1 = x-chunks dealt outside-in (v5_chunk_of_rank)
     int n_boxes;
     Box box[MAX_BOXES];
     int pf_dist;              // L2 prefetch distance in x-planes (0 = off)

@@ -91,6 +91,9 @@ class _Plan:
         self.lib = _lib.load()
         self.handle = C.c_void_p()
         self._keep = [np.ascontiguousarray(a, dtype=np.float64) for a in list(sH) + list(sD)]
+        for q, a in enumerate(self._keep):      # the C side reads shape[axis] entries of each profile
+            if a.shape != (shape[q % 3],):
+                raise ValueError("sigma profile {} has shape {}, expected ({},)".format(q, a.shape, shape[q % 3]))
         dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
         cH = _lib.c_dptr3(*[dp(a) for a in self._keep[:3]])
         cD = _lib.c_dptr3(*[dp(a) for a in self._keep[3:]])
@@ -181,7 +184,10 @@ class fdtd:
         """New permittivity => new Yee averages and 1/eps, and a FIELD RESET (fdtd.py:63-72)."""
         new_eps = self._as_eps(new_eps, pad=False)
         if tuple(new_eps.shape) != tuple(self.grid_shape):
-            self._plan = None
+            # the reference fails here too: its sigma arrays keep the old shape and _compute_update_parameters
+            # (fdtd.py:265-311) raises numpy's broadcast ValueError
+            raise ValueError("eps_r of shape {} assigned to an FDTD object of grid shape {}: operands could not be "
+                             "broadcast together (make a new fdtd object)".format(tuple(new_eps.shape), tuple(self.grid_shape)))
         self.__eps_r = new_eps
         e64 = new_eps.to(torch.float64)
         # ceviche/utils.py:153-176 (grid_center_to_xyz): mean with the previous cell, periodic
@@ -221,10 +227,15 @@ class fdtd:
         self._mE64 = [1 / e for e in (self.eps_xx, self.eps_yy, self.eps_zz)]
         self._mE = [m.to(self.dtype).contiguous() for m in self._mE64]
         self.mEx1, self.mEy1, self.mEz1 = self._mE
+        # the reference's m*1..4 arrays freeze dt at THIS call (a later `F.dL = ...` changes dt and the curls,
+        # fdtd.py:41-45, 80, but not the coefficients until eps_r is assigned again)
+        if self.__dict__.get("_coef_dt") != self.dt:
+            self._plan = None
+        self._coef_dt = self.dt
 
     def _ensure_plan(self):
         if self._plan is None:
-            self._plan = _Plan(self.device, self.dtype, self.arith_f64, self.grid_shape, self.dL, self.dt,
+            self._plan = _Plan(self.device, self.dtype, self.arith_f64, self.grid_shape, self.dL, self._coef_dt,
                                self.sigH, self.sigD)
             self._alloc_pml()
             for name, value in self._options.items():
@@ -317,6 +328,12 @@ class fdtd:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _sync_for_upload(self):
+        """The point-set uploads of the C ABI (cev_fdtd_set_sources / _probes / _monitors) are blocking copies on the
+        legacy default stream, which does not wait for torch's non-blocking side streams: finish the work that
+        produced the index / weight tensors first."""
+        torch.cuda.current_stream(self.device).synchronize()
+
     def _as_J(self, J):
         if J is None:
             return None
@@ -395,6 +412,7 @@ class fdtd:
         for s, (comp, profile) in enumerate(sources):
             pts[s] = self._point_set(3 + _COMP[comp], profile, keep, dense_ok=False)
         with torch.cuda.device(self.device):
+            self._sync_for_upload()
             _lib.check(plan.lib.cev_fdtd_set_sources(plan.handle, len(sources), pts))
         self._n_sources = len(sources)
         self._source_mask = sum({1 << _COMP[comp] for comp, _ in sources})
@@ -408,6 +426,7 @@ class fdtd:
             pts[p] = self._point_set(_FIELD_CODE[key], mask, keep, dense_ok=True)
         n_slots = C.c_int64()
         with torch.cuda.device(self.device):
+            self._sync_for_upload()
             _lib.check(plan.lib.cev_fdtd_set_probes(plan.handle, len(probes), pts, C.byref(n_slots)))
         owner = (C.c_int32 * max(1, n_slots.value))()
         _lib.check(plan.lib.cev_fdtd_probe_slots(plan.handle, owner))
@@ -440,6 +459,7 @@ class fdtd:
             self._mon_counts.append(int(nz.numel()))
         n_pts = C.c_int64()
         with torch.cuda.device(self.device):
+            self._sync_for_upload()
             _lib.check(plan.lib.cev_fdtd_set_monitors(plan.handle, len(monitors), pts, len(freqs), C.byref(n_pts)))
         self._n_mon_pts = n_pts.value
         self._mon_freqs = freqs

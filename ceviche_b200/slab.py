@@ -119,6 +119,7 @@ class CudaSlabBackend:
             pp[q] = mk(field, idx, w)
         n_slots = C.c_int64()
         with torch.cuda.device(self.device):
+            torch.cuda.current_stream(self.device).synchronize()     # blocking legacy-stream copies follow
             _lib.check(self.plan.lib.cev_fdtd_set_sources(self.plan.handle, len(sources), sp))
             _lib.check(self.plan.lib.cev_fdtd_set_probes(self.plan.handle, len(probes), pp, C.byref(n_slots)))
         owner = (C.c_int32 * max(1, n_slots.value))()

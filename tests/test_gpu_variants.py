@@ -21,7 +21,8 @@ def _case(shape, npml, steps, seed):
     return dict(eps=eps, dL=cases.DL, npml=list(npml), steps=steps, sources=src, probes=probes)
 
 
-def _run(case, dtype, variant, xchunk=0, per_step=False, lanes_z=8, prefetch=1, split=0, fused_shape=0, steps=None):
+def _run(case, dtype, variant, xchunk=0, per_step=False, lanes_z=8, prefetch=1, split=0, fused_shape=0, steps=None,
+         tma_rows=4, tma_stages=4):
     import ceviche_b200
     if steps is not None:
         case = dict(case, steps=steps, sources=[(c, p, w[:steps]) for c, p, w in case["sources"]])
@@ -32,6 +33,8 @@ def _run(case, dtype, variant, xchunk=0, per_step=False, lanes_z=8, prefetch=1, 
     F.set_option("lanes_z", lanes_z)
     F.set_option("prefetch_planes", prefetch)
     F.set_option("split_launch", split)
+    F.set_option("tma_rows", tma_rows)
+    F.set_option("tma_stages", tma_stages)
     if per_step:
         profs = [(c, torch.as_tensor(p).cuda()) for c, p, _ in case["sources"]]
         for t in range(case["steps"]):
@@ -72,6 +75,30 @@ def test_marching_equals_baseline_bitwise(shape, npml, dtype):
         for a, b in zip(p1, p3):
             assert np.array_equal(a, b), ("v3", xchunk)
         assert np.array_equal(s1, s3)
+
+
+# grids the tensor-map TMA kernels serve (Ny a multiple of the tile rows, Nz >= one tile row of 32 vectors), incl. a
+# partial last z-tile, wide / absent PML on single axes and no PML at all; the last two are not eligible (fallback)
+TMA_SHAPES = [((20, 16, 136), (4, 3, 6)), ((6, 8, 260), (2, 3, 20)), ((9, 24, 128), (2, 0, 5)), ((40, 48, 192), (5, 7, 0)),
+              ((18, 16, 128), (0, 0, 0)), ((3, 8, 256), (0, 2, 9)), ((35, 32, 384), (6, 5, 8)),
+              ((12, 10, 136), (2, 3, 4)), ((12, 16, 40), (2, 3, 4))]
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
+@pytest.mark.parametrize("shape,npml", TMA_SHAPES)
+def test_tensor_map_kernels_equal_baseline_bitwise(shape, npml, dtype):
+    """step_v5.cuh (cp.async.bulk.tensor box copies, lean PML update) against the one-thread-per-cell kernels:
+    fields, the twelve PML integral arrays and the probe series, for both tile heights, both ring depths and
+    several x-chunkings (chunk ends exercise the x+1 / x-1 neighbour-only stages and the periodic wrap planes)."""
+    case = _case(shape, npml, 40, 7)
+    s1, f1, p1 = _run(case, dtype, 1)
+    for rows, stages, xchunk in ((4, 4, 0), (4, 3, 1), (8, 4, 3), (8, 3, 5), (4, 4, 2), (4, 3, 1000), (8, 4, 7)):
+        s6, f6, p6 = _run(case, dtype, 6, xchunk, tma_rows=rows, tma_stages=stages)
+        for k in FIELD_KEYS:
+            assert np.array_equal(f1[k], f6[k]), (k, rows, stages, xchunk)
+        for q, (a, b) in enumerate(zip(p1, p6)):
+            assert np.array_equal(a, b), (q, rows, stages, xchunk)
+        assert np.array_equal(s1, s6), (rows, stages, xchunk)
 
 
 FUSED_SHAPES = SHAPES + [((5, 3, 8), (1, 1, 2)), ((1, 6, 16), (0, 2, 3)), ((17, 1, 36), (3, 0, 4)), ((36, 31, 124), (5, 4, 6)),
