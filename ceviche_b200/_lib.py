@@ -34,6 +34,14 @@ class cev_adjoint(C.Structure):
     _fields_ = [(n, c_void_p3) for n in ("lH", "lD", "lICE", "lIH", "lICH", "lID", "gC", "gC2", "G_mE")]
 
 
+class cev_halo_layout(C.Structure):
+    _fields_ = [("bytes", C.c_size_t), ("plane_bytes", C.c_size_t), ("D_hi", C.c_size_t * 2), ("inv_eps_hi", C.c_size_t * 2),
+                ("H_lo", C.c_size_t * 2), ("flag_D", C.c_size_t), ("flag_H", C.c_size_t), ("err", C.c_size_t)]
+
+
+IPC_HANDLE_BYTES = 64
+
+
 class CevicheB200Error(RuntimeError):
     pass
 
@@ -68,6 +76,15 @@ def _declare(lib):
         "cev_fdtd_bind_monitors": [C.c_void_p, C.c_void_p, C.c_void_p],
         "cev_fdtd_run": [C.c_void_p, P(cev_state), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
         "cev_fdtd_run_fused": [C.c_void_p, P(cev_state), P(cev_state), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
+        "cev_fdtd_halo_layout": [C.c_void_p, P(cev_halo_layout)],
+        "cev_halo_alloc": [C.c_int, C.c_size_t, P(C.c_void_p), C.c_char_p],
+        "cev_halo_open": [C.c_int, C.c_char_p, P(C.c_void_p)],
+        "cev_halo_close": [C.c_int, C.c_void_p],
+        "cev_halo_free": [C.c_int, C.c_void_p],
+        "cev_fdtd_halo_attach": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+        "cev_fdtd_halo_push_static": [C.c_void_p, P(cev_state), C.c_void_p],
+        "cev_fdtd_halo_reset": [C.c_void_p, C.c_void_p],
+        "cev_fdtd_halo_error": [C.c_void_p, P(C.c_int)],
     }
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
@@ -80,7 +97,9 @@ EXPORTS = ("cev_last_error", "cev_abi_version", "cev_fdtd_create", "cev_fdtd_des
            "cev_fdtd_set_option",
            "cev_fdtd_step_H", "cev_fdtd_step_D", "cev_fdtd_compute_E", "cev_fdtd_set_sources",
            "cev_fdtd_set_probes", "cev_fdtd_probe_slots", "cev_fdtd_set_monitors", "cev_fdtd_bind_monitors", "cev_fdtd_run", "cev_fdtd_run_fused", "cev_fdtd_step_H_ex", "cev_fdtd_step_D_ex",
-           "cev_fdtd_sample_probes", "cev_fdtd_jvp_run", "cev_fdtd_adjoint_step", "cev_fdtd_adjoint_seed")
+           "cev_fdtd_sample_probes", "cev_fdtd_jvp_run", "cev_fdtd_adjoint_step", "cev_fdtd_adjoint_seed",
+           "cev_fdtd_halo_layout", "cev_halo_alloc", "cev_halo_open", "cev_halo_close", "cev_halo_free",
+           "cev_fdtd_halo_attach", "cev_fdtd_halo_push_static", "cev_fdtd_halo_reset", "cev_fdtd_halo_error")
 
 
 def load():

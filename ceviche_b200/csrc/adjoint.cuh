@@ -6,15 +6,23 @@
 // backward difference), so the adjoint sweeps reuse the two stencils with their roles swapped.
 // For step n, given the cotangents (lH, lD, lICE, lIH, lICH, lID) of the state after step n:
 //
-//   adj_D (cell-local)   gD = lD ; gICH = lICH + m3D gD ; gID = lID + m4D gD
+//   (D, cell-local)      gD = lD ; gICH = lICH + m3D gD ; gID = lID + m4D gD
 //                        gC = m2D gD + gICH ; lD <- m1D gD + gID ; lICH <- gICH ; lID <- gID
-//   adj_H (stencil)      gH = lH + curl_E(gC) ; gICE = lICE + m3H gH ; gIH = lIH + m4H gH
+//   (H, stencil)         gH = lH + curl_E(gC) ; gICE = lICE + m3H gH ; gIH = lIH + m4H gH
 //                        gC2 = m2H gH + gICE ; lH <- m1H gH + gIH ; lICE <- gICE ; lIH <- gIH
-//   adj_E (stencil)      lE = curl_H(gC2) ; lD += mE lE ; G_mE += lE * D_{n-1}
+//   (E, stencil)         lE = curl_H(gC2) ; lD += mE lE ; G_mE += lE * D_{n-1}
 //
 // after which (lH, lD, ...) are the cotangents of the state after step n-1 and G_mE has gained
 // step n's contribution to dL/d(1/eps).  eps_r enters the step only through mE = 1/eps_yee
 // (fdtd.py:67, 314-316), so G_mE is the whole gradient; the chain to eps_r is done by the host.
+//
+// Two kernels per step, one scratch vector field (round 1: three kernels, two scratch fields, 42 words per cell):
+//   k_adj_H   evaluates gC ON THE FLY at the cell and its +1 neighbours from the OLD lD / lICH (off the PML it is
+//             just C0 dt lD), applies the H part, writes lH and gC2: lD, lH in; lH, gC2 out = 12 words per cell;
+//   k_adj_ED  takes lE from gC2, applies the DEFERRED cell-local D part (lD, lICH, lID) and adds mE lE:
+//             gC2, lD, mE in; lD out = 12 words, plus D_{n-1} in and the fp64 G_mE read-modify-write INSIDE the
+//             design box only (g_box): gradients are rarely wanted outside the region being optimised.
+// 24 words per cell outside the box, 33 inside (fp64; SURVEY 8(d) counts 27 with G everywhere and no scratch).
 #pragma once
 #include "common.cuh"
 
@@ -29,9 +37,9 @@ struct AdjArgs {
     T* lIH[3];
     T* lICH[3];
     T* lID[3];
-    T* gC[3];        // scratch: cotangent of curl_H(H_n)
     T* gC2[3];       // scratch: cotangent of curl_E(E_{n-1})
     double* G[3];    // dL/d(mE), accumulated in fp64 whatever the storage type
+    int gb[6];       // design box (internal axes: x0, x1, y0, y1, z0, z1): G is only accumulated inside
     const T* mE[3];
     const T* Dprev[3];   // forward D after step n-1
     const int* mapH[3];
@@ -47,7 +55,7 @@ struct AdjArgs {
 // transposed component update, cell-local.  Returns gC; updates l, lIcurl, lIself in place.
 template <typename T, typename AT>
 __device__ __forceinline__ AT adj_component(AT g, AT ua, AT ra, AT ub, AT rb, AT uc, AT scdt, T* l, int64_t o,
-                                            T* lIcurl, int64_t icurl, T* lIself, int64_t iself) {
+                                            T* lIcurl, int64_t icurl, T* lIself, int64_t iself, AT extra = AT(0)) {
     AT m1, m2;
     coef12<AT>(ua, ra, ub, rb, scdt, m1, m2);
     AT gIc = AT(0), gIs = AT(0);
@@ -61,7 +69,7 @@ __device__ __forceinline__ AT adj_component(AT g, AT ua, AT ra, AT ub, AT rb, AT
         gIs = (AT)lIself[iself] + m4 * g;
         lIself[iself] = (T)gIs;
     }
-    l[o] = (T)(m1 * g + gIs);
+    l[o] = (T)(m1 * g + gIs + extra);
     return m2 * g + gIc;
 }
 
@@ -73,32 +81,33 @@ __device__ __forceinline__ AT adj_component(AT g, AT ua, AT ra, AT ub, AT rb, AT
     const int64_t plane = (int64_t)a.Ny * a.Nz;                      \
     const int64_t o = i * plane + (int64_t)j * a.Nz + k;
 
+// gC of component c at cell (i, j, k) = flat offset o, from the OLD cotangents (nothing is written): off the D-side
+// PML it is C0 dt lD exactly (m2 = s r_a r_b with r = 1, no integral).  mx / my / mz: the cell's compact indices.
 template <typename T, typename AT>
-__global__ void k_adj_D(const AdjArgs<T, AT> a) {
-    CEV_CELL_INDEX();
-    const AT ux = a.uD[0][i], uy = a.uD[1][j], uz = a.uD[2][k];
-    const AT rx = a.rD[0][i], ry = a.rD[1][j], rz = a.rD[2][k];
-    const int mx = a.mapD[0][i], my = a.mapD[1][j], mz = a.mapD[2][k];
+__device__ __forceinline__ AT adj_gC(const AdjArgs<T, AT>& a, int c, int i, int j, int k, int mx, int my, int mz, int64_t o) {
     const AT s = a.cdt;
-    {
-        const int64_t ic = (mx >= 0) ? ((int64_t)mx * a.Ny + j) * a.Nz + k : -1;
-        const int64_t is = (my >= 0 && mz >= 0) ? ((int64_t)i * a.nD[1] + my) * a.nD[2] + mz : -1;
-        a.gC[0][o] = (T)adj_component<T, AT>((AT)a.lD[0][o], uy, ry, uz, rz, ux, s, a.lD[0], o, a.lICH[0], ic, a.lID[0], is);
+    const AT g = (AT)a.lD[c][o];
+    if ((mx & my & mz) < 0) return s * g;                // all three are -1: not in the PML of any axis
+    AT ra, rb, uc;
+    int64_t ic;
+    if (c == 0) {
+        ra = a.rD[1][j]; rb = a.rD[2][k]; uc = a.uD[0][i];
+        ic = (mx >= 0) ? ((int64_t)mx * a.Ny + j) * a.Nz + k : -1;
+    } else if (c == 1) {
+        ra = a.rD[0][i]; rb = a.rD[2][k]; uc = a.uD[1][j];
+        ic = (my >= 0) ? ((int64_t)i * a.nD[1] + my) * a.Nz + k : -1;
+    } else {
+        ra = a.rD[0][i]; rb = a.rD[1][j]; uc = a.uD[2][k];
+        ic = (mz >= 0) ? ((int64_t)i * a.Ny + j) * a.nD[2] + mz : -1;
     }
-    {
-        const int64_t ic = (my >= 0) ? ((int64_t)i * a.nD[1] + my) * a.Nz + k : -1;
-        const int64_t is = (mx >= 0 && mz >= 0) ? ((int64_t)mx * a.Ny + j) * a.nD[2] + mz : -1;
-        a.gC[1][o] = (T)adj_component<T, AT>((AT)a.lD[1][o], ux, rx, uz, rz, uy, s, a.lD[1], o, a.lICH[1], ic, a.lID[1], is);
-    }
-    {
-        const int64_t ic = (mz >= 0) ? ((int64_t)i * a.Ny + j) * a.nD[2] + mz : -1;
-        const int64_t is = (mx >= 0 && my >= 0) ? ((int64_t)mx * a.nD[1] + my) * a.Nz + k : -1;
-        a.gC[2][o] = (T)adj_component<T, AT>((AT)a.lD[2][o], ux, rx, uy, ry, uz, s, a.lD[2], o, a.lICH[2], ic, a.lID[2], is);
-    }
+    const AT rr = mul_rn(ra, rb);
+    AT v = mul_rn(s, rr) * g;
+    if (ic >= 0) v += (AT)a.lICH[c][ic] + mul_rn(mul_rn(s, uc + uc), rr) * g;
+    return v;
 }
 
 template <typename T, typename AT>
-__global__ void k_adj_H(const AdjArgs<T, AT> a) {
+__global__ void __launch_bounds__(256) k_adj_H(const AdjArgs<T, AT> a) {
     CEV_CELL_INDEX();
     const int ip = (i + 1 == a.Nx) ? 0 : i + 1;
     const int jp = (j + 1 == a.Ny) ? 0 : j + 1;
@@ -107,10 +116,18 @@ __global__ void k_adj_H(const AdjArgs<T, AT> a) {
     const int64_t o_jp = i * plane + (int64_t)jp * a.Nz + k;
     const int64_t o_kp = i * plane + (int64_t)j * a.Nz + kp;
     const AT inv = a.inv_dL;
+    const int dx = a.mapD[0][i], dy = a.mapD[1][j], dz = a.mapD[2][k];
+    const int dxp = a.mapD[0][ip], dyp = a.mapD[1][jp], dzp = a.mapD[2][kp];
     // curl_E (forward differences, derivatives.py:16-22) of gC
-    const AT cx = ((AT)a.gC[2][o_jp] - (AT)a.gC[2][o]) * inv - ((AT)a.gC[1][o_kp] - (AT)a.gC[1][o]) * inv;
-    const AT cy = ((AT)a.gC[0][o_kp] - (AT)a.gC[0][o]) * inv - ((AT)a.gC[2][o_ip] - (AT)a.gC[2][o]) * inv;
-    const AT cz = ((AT)a.gC[1][o_ip] - (AT)a.gC[1][o]) * inv - ((AT)a.gC[0][o_jp] - (AT)a.gC[0][o]) * inv;
+    const AT gx = adj_gC<T, AT>(a, 0, i, j, k, dx, dy, dz, o);
+    const AT gy = adj_gC<T, AT>(a, 1, i, j, k, dx, dy, dz, o);
+    const AT gz = adj_gC<T, AT>(a, 2, i, j, k, dx, dy, dz, o);
+    const AT gz_jp = adj_gC<T, AT>(a, 2, i, jp, k, dx, dyp, dz, o_jp), gx_jp = adj_gC<T, AT>(a, 0, i, jp, k, dx, dyp, dz, o_jp);
+    const AT gy_kp = adj_gC<T, AT>(a, 1, i, j, kp, dx, dy, dzp, o_kp), gx_kp = adj_gC<T, AT>(a, 0, i, j, kp, dx, dy, dzp, o_kp);
+    const AT gz_ip = adj_gC<T, AT>(a, 2, ip, j, k, dxp, dy, dz, o_ip), gy_ip = adj_gC<T, AT>(a, 1, ip, j, k, dxp, dy, dz, o_ip);
+    const AT cx = (gz_jp - gz) * inv - (gy_kp - gy) * inv;
+    const AT cy = (gx_kp - gx) * inv - (gz_ip - gz) * inv;
+    const AT cz = (gy_ip - gy) * inv - (gx_jp - gx) * inv;
     const AT ux = a.uH[0][i], uy = a.uH[1][j], uz = a.uH[2][k];
     const AT rx = a.rH[0][i], ry = a.rH[1][j], rz = a.rH[2][k];
     const int mx = a.mapH[0][i], my = a.mapH[1][j], mz = a.mapH[2][k];
@@ -133,7 +150,7 @@ __global__ void k_adj_H(const AdjArgs<T, AT> a) {
 }
 
 template <typename T, typename AT>
-__global__ void k_adj_E(const AdjArgs<T, AT> a) {
+__global__ void __launch_bounds__(256) k_adj_ED(const AdjArgs<T, AT> a) {
     CEV_CELL_INDEX();
     const int im = (i == 0) ? a.Nx - 1 : i - 1;
     const int jm = (j == 0) ? a.Ny - 1 : j - 1;
@@ -143,15 +160,44 @@ __global__ void k_adj_E(const AdjArgs<T, AT> a) {
     const int64_t o_km = i * plane + (int64_t)j * a.Nz + km;
     const AT inv = a.inv_dL;
     // curl_H (backward differences, derivatives.py:24-30) of gC2
+    const AT c0 = (AT)a.gC2[0][o], c1 = (AT)a.gC2[1][o], c2 = (AT)a.gC2[2][o];
     AT lE[3];
-    lE[0] = ((AT)a.gC2[2][o] - (AT)a.gC2[2][o_jm]) * inv - ((AT)a.gC2[1][o] - (AT)a.gC2[1][o_km]) * inv;
-    lE[1] = ((AT)a.gC2[0][o] - (AT)a.gC2[0][o_km]) * inv - ((AT)a.gC2[2][o] - (AT)a.gC2[2][o_im]) * inv;
-    lE[2] = ((AT)a.gC2[1][o] - (AT)a.gC2[1][o_im]) * inv - ((AT)a.gC2[0][o] - (AT)a.gC2[0][o_jm]) * inv;
+    lE[0] = (c2 - (AT)a.gC2[2][o_jm]) * inv - (c1 - (AT)a.gC2[1][o_km]) * inv;
+    lE[1] = (c0 - (AT)a.gC2[0][o_km]) * inv - (c2 - (AT)a.gC2[2][o_im]) * inv;
+    lE[2] = (c1 - (AT)a.gC2[1][o_im]) * inv - (c0 - (AT)a.gC2[0][o_jm]) * inv;
+    // the deferred cell-local D part, then lD += mE lE
+    const int mx = a.mapD[0][i], my = a.mapD[1][j], mz = a.mapD[2][k];
+    const bool in_box = i >= a.gb[0] && i < a.gb[1] && j >= a.gb[2] && j < a.gb[3] && k >= a.gb[4] && k < a.gb[5];
+    if ((mx & my & mz) < 0) {                                // off the PML: m1 = 1, no integrals
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        a.lD[c][o] = (T)((AT)a.lD[c][o] + (AT)a.mE[c][o] * lE[c]);
-        if (a.G[c]) a.G[c][o] += (double)lE[c] * (double)a.Dprev[c][o];
+        for (int c = 0; c < 3; ++c) {
+            a.lD[c][o] = (T)((AT)a.lD[c][o] + (AT)a.mE[c][o] * lE[c]);
+            if (in_box && a.G[c]) a.G[c][o] += (double)lE[c] * (double)a.Dprev[c][o];
+        }
+        return;
     }
+    const AT ux = a.uD[0][i], uy = a.uD[1][j], uz = a.uD[2][k];
+    const AT rx = a.rD[0][i], ry = a.rD[1][j], rz = a.rD[2][k];
+    const AT s = a.cdt;
+    {
+        const int64_t ic = (mx >= 0) ? ((int64_t)mx * a.Ny + j) * a.Nz + k : -1;
+        const int64_t is = (my >= 0 && mz >= 0) ? ((int64_t)i * a.nD[1] + my) * a.nD[2] + mz : -1;
+        adj_component<T, AT>((AT)a.lD[0][o], uy, ry, uz, rz, ux, s, a.lD[0], o, a.lICH[0], ic, a.lID[0], is, (AT)a.mE[0][o] * lE[0]);
+    }
+    {
+        const int64_t ic = (my >= 0) ? ((int64_t)i * a.nD[1] + my) * a.Nz + k : -1;
+        const int64_t is = (mx >= 0 && mz >= 0) ? ((int64_t)mx * a.Ny + j) * a.nD[2] + mz : -1;
+        adj_component<T, AT>((AT)a.lD[1][o], ux, rx, uz, rz, uy, s, a.lD[1], o, a.lICH[1], ic, a.lID[1], is, (AT)a.mE[1][o] * lE[1]);
+    }
+    {
+        const int64_t ic = (mz >= 0) ? ((int64_t)i * a.Ny + j) * a.nD[2] + mz : -1;
+        const int64_t is = (mx >= 0 && my >= 0) ? ((int64_t)mx * a.nD[1] + my) * a.Nz + k : -1;
+        adj_component<T, AT>((AT)a.lD[2][o], ux, rx, uy, ry, uz, s, a.lD[2], o, a.lICH[2], ic, a.lID[2], is, (AT)a.mE[2][o] * lE[2]);
+    }
+    if (in_box)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            if (a.G[c]) a.G[c][o] += (double)lE[c] * (double)a.Dprev[c][o];
 }
 
 // Seeds of a probe-series objective: for step n and probe p with cotangent g = gbar[n, p],

@@ -88,7 +88,17 @@ struct cev_fdtd {
                                  // 4 fused full-step kernel wherever it applies (cev_fdtd_run_fused), 5 hybrid,
                                  // 6 tensor-map TMA kernels (step_v5.cuh) wherever they apply
     int tma_rows = 4, tma_stages_H = 3, tma_stages_D = 4;   // tile rows / ring depths of the tensor-map kernels
-    int auto_v5 = 0;                    // kernel_variant 0 (auto) picks them on large 3-D grids
+    int auto_v5 = 1;                    // kernel_variant 0 (auto) picks them on large 3-D grids
+    // x-slab halo exchange through peer-mapped memory (cev_fdtd_halo_attach): this slab's exchange block and the
+    // neighbours' (device pointers valid on this device), and how many H / D half-steps have used them
+    struct Halo {
+        unsigned char* own = nullptr;
+        unsigned char* left = nullptr;
+        unsigned char* right = nullptr;
+        uint64_t nH = 0, nD = 0;
+        bool paused = false;        // option "halo_pause": launches ignore the blocks (periodic wrap inside the slab)
+        bool on() const { return own && !paused; }
+    } halo;
     cev::V5MapCache* v5 = nullptr;      // CUtensorMap descriptors of this plan's arrays
     int fused_shape = 0;         // tile shape of the fused kernel: 0 auto, else LZ*100 + BY
     int xchunk = 0;              // 0 auto
@@ -160,6 +170,21 @@ namespace {
 
 using namespace cev;
 
+void halo_layout(const cev_fdtd* p, cev_halo_layout* lay) {
+    const size_t es = p->dtype == CEV_F64 ? 8 : 4;
+    const size_t pb = ((size_t)p->Nl[1] * p->Nl[2] * es + 255) / 256 * 256;
+    for (int c = 0; c < 2; ++c) {
+        lay->D_hi[c] = (0 + c) * pb;
+        lay->inv_eps_hi[c] = (2 + c) * pb;
+        lay->H_lo[c] = (4 + c) * pb;
+    }
+    lay->flag_D = 6 * pb;
+    lay->flag_H = 6 * pb + 128;
+    lay->err = 6 * pb + 256;
+    lay->plane_bytes = pb;
+    lay->bytes = 6 * pb + 512;
+}
+
 void fill_probe_table(const cev_fdtd* p, ProbeTable& pr) {
     pr.n_slots = p->n_slots;
     pr.slot_field = (const int32_t*)p->pr_field.p;
@@ -209,6 +234,16 @@ int fill_args(const cev_fdtd* p, const cev_state* st, StepArgs<T, AT>& a, const 
             if (!a.dmE[A] || !a.Dp[A]) return fail("cev_tangent: d_inv_eps and D_primal must be non-NULL");
             a.dmEhi[A] = a.dmE[A];     // tangents run on whole (periodic) grids only
             a.Dphi[A] = a.Dp[A];
+        }
+    }
+    if (p->halo.on()) {      // attached exchange block: the halo planes this slab reads live there
+        if (tan) return fail("tangent steps do not support x-slab halos");
+        cev_halo_layout lay;
+        halo_layout(p, &lay);
+        for (int c = 1; c < 3; ++c) {
+            a.Dhi[c] = (const T*)(p->halo.own + lay.D_hi[c - 1]);
+            a.mEhi[c] = (const T*)(p->halo.own + lay.inv_eps_hi[c - 1]);
+            a.Hlo[c] = (const T*)(p->halo.own + lay.H_lo[c - 1]);
         }
     }
     if (tan && (st->D_xhi[1] || st->D_xhi[2])) return fail("tangent steps do not support x-halo planes");
@@ -448,11 +483,14 @@ int attach_probes(const cev_fdtd* p, StepArgs<T, AT>& a, int which, int64_t t, d
 
 // The tensor-map TMA kernels (step_v5.cuh) serve whole y-z planes of 3-D grids with all six components live.
 template <typename T, typename AT>
-bool want_v5(cev_fdtd* p, const StepArgs<T, AT>& a, int64_t x0, int64_t x1) {
-    if (p->variant != 6 && p->variant != 0) return false;
-    if (p->variant == 0 && !p->auto_v5) return false;
+bool want_v5(cev_fdtd* p, const StepArgs<T, AT>& a, int64_t x0, int64_t x1, bool isH) {
+    const bool forced = p->variant == 6 || p->halo.on();
+    if (!forced && (p->variant != 0 || !p->auto_v5)) return false;
     if (x1 <= x0 || !v5_eligible<T, AT>(a, p->tma_rows)) return false;
-    if (p->variant == 0 && (int64_t)a.Ny * a.Nz < (1 << 14)) return false;     // small planes: too few CTAs per chunk
+    if (!forced && (int64_t)a.Ny * a.Nz < (1 << 14)) return false;     // small planes: too few CTAs per chunk
+    // measured on B200 (profiles/r2_tune_tensor_map.log): the fp32 H half-step of very large grids is the one case
+    // where the register-marching kernel is still ahead (6.29 vs 5.94 TB/s at 512^3)
+    if (!forced && isH && sizeof(T) == 4 && (int64_t)a.Nx * a.Ny * a.Nz >= ((int64_t)1 << 26)) return false;
     if (!p->v5) p->v5 = v5_cache_create();
     return true;
 }
@@ -492,8 +530,22 @@ int launch_H(cev_fdtd* p, const cev_state* st, const cev_tangent* tan, void* con
         CUDA_TRY(cudaGetLastError());
         return 0;
     }
-    if (want_v5(p, a, x0, x1)) {                // tensor-map TMA kernel: box copies described by CUtensorMaps
+    if (p->halo.on() && (!want_v5(p, a, x0, x1, true) || H_out || x0 != 0 || x1 != a.Nx))
+        return fail("x-slab halos over peer memory need in-place whole-slab launches of the tensor-map kernels "
+                    "(3-D grid, Ny a multiple of %d, Nz a multiple of the 16-byte vector and >= 32 vectors)", p->tma_rows);
+    if (want_v5(p, a, x0, x1, true)) {          // tensor-map TMA kernel: box copies described by CUtensorMaps
         v5_set_tiles(a, x0, x1, p->tma_rows, p->xchunk);
+        if (p->halo.on()) {      // this launch reads the right neighbour's D plane 0 and feeds its H plane -1
+            cev_halo_layout lay;
+            halo_layout(p, &lay);
+            a.peer_out[0] = (T*)(p->halo.right + lay.H_lo[0]);
+            a.peer_out[1] = (T*)(p->halo.right + lay.H_lo[1]);
+            a.peer_flag = (unsigned long long*)(p->halo.right + lay.flag_H);
+            a.own_flag = (const unsigned long long*)(p->halo.own + lay.flag_D);
+            a.own_target = p->halo.nH * (uint64_t)(a.ntz * a.nty);     // the neighbour's D half-steps so far, all CTAs of its plane 0
+            a.halo_err = (int*)(p->halo.own + lay.err);
+            p->halo.nH++;
+        }
         const int aux = attach_probes(p, a, 0, probe_t, partials);
         if (v5_launch_H<T, AT>(p->v5, a, p->tma_rows, p->tma_stages_H, aux, s)) return fail("%s", v5_last_error());
         return 0;
@@ -585,8 +637,22 @@ int launch_D(cev_fdtd* p, const cev_state* st, void* const D_out[3], void* const
     const dim3 blk(32, V2_BY);
     const bool extras = a.J[0] || a.J[1] || a.J[2] || a.Eout[0] || a.Eout[1] || a.Eout[2];
     if (extras) a.on = 63u;
-    if (!extras && want_v5(p, a, x0, x1)) {     // tensor-map TMA kernel
+    if (p->halo.on() && (extras || !want_v5(p, a, x0, x1, false) || D_out || x0 != 0 || x1 != a.Nx))
+        return fail("x-slab halos over peer memory need in-place whole-slab launches of the tensor-map kernels "
+                    "(3-D grid, Ny a multiple of %d, Nz a multiple of the 16-byte vector and >= 32 vectors, no dense J)", p->tma_rows);
+    if (!extras && want_v5(p, a, x0, x1, false)) {     // tensor-map TMA kernel
         v5_set_tiles(a, x0, x1, p->tma_rows, p->xchunk);
+        if (p->halo.on()) {      // this launch reads the left neighbour's last H plane and feeds its D plane nx
+            cev_halo_layout lay;
+            halo_layout(p, &lay);
+            a.peer_out[0] = (T*)(p->halo.left + lay.D_hi[0]);
+            a.peer_out[1] = (T*)(p->halo.left + lay.D_hi[1]);
+            a.peer_flag = (unsigned long long*)(p->halo.left + lay.flag_D);
+            a.own_flag = (const unsigned long long*)(p->halo.own + lay.flag_H);
+            a.own_target = (p->halo.nD + 1) * (uint64_t)(a.ntz * a.nty);   // the neighbour's H half-step of THIS time step
+            a.halo_err = (int*)(p->halo.own + lay.err);
+            p->halo.nD++;
+        }
         if (inject && attach_sources_v2(p, a, wave_row, 0, 32, p->tma_rows)) return -1;
         const int aux = attach_probes(p, a, 1, probe_t, partials);
         if (v5_launch_D<T, AT>(p->v5, a, p->tma_rows, p->tma_stages_D, aux, s)) return fail("%s", v5_last_error());
@@ -771,7 +837,8 @@ int run_loop(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* wav
     int64_t n0 = 0;
     const int64_t cells = (int64_t)p->N[0] * p->N[1] * p->N[2];
     const bool monitors = p->n_mon_pts > 0 && p->mon_acc;     // (their phasor row changes every step: no graph replay)
-    const bool graphs = !monitors && (p->use_graph == 1 || (p->use_graph < 0 && cells <= GRAPH_MAX_CELLS));
+    const bool graphs = !monitors && !p->halo.on() &&      // (the halo targets change with every step: no static graph)
+                        (p->use_graph == 1 || (p->use_graph < 0 && cells <= GRAPH_MAX_CELLS));
     if (graphs && nsteps >= 2 * GRAPH_K + 1) {
         // step 0 the ordinary way (it also builds the source tilings and sets kernel attributes), then whole blocks
         if (launch_H<T, AT>(p, st, nullptr, nullptr, 0, Nx, -1, partials, s)) return -1;
@@ -1210,6 +1277,7 @@ int cev_fdtd_create(cev_fdtd** out, int device, int dtype, int arith_f64, int64_
     p->device = device;
     p->dtype = dtype;
     p->arith64 = (dtype == CEV_F64) ? 1 : (arith_f64 ? 1 : 0);
+    p->tma_stages_D = dtype == CEV_F64 ? 4 : 3;      // tuned on B200 (3 CTAs x 4 stages vs 4 CTAs x 3 stages per SM)
     p->Nl[0] = nx;
     p->Nl[1] = Ny;
     p->Nl[2] = Nz;
@@ -1350,8 +1418,12 @@ int cev_fdtd_set_option(cev_fdtd* p, const char* name, int64_t value) {
         p->tma_rows = (int)value;
     } else if (!strcmp(name, "tma_stages") || !strcmp(name, "tma_stages_H") || !strcmp(name, "tma_stages_D")) {
         if (!v5_supported_shape(p->tma_rows, (int)value)) return fail("%s must be 3 or 4", name);
-        if (name[10] != 'D') p->tma_stages_H = (int)value;      // "tma_stages" sets both
-        if (name[10] != 'H') p->tma_stages_D = (int)value;
+        const char which = name[10] ? name[11] : 0;             // "tma_stages" sets both
+        if (which != 'D') p->tma_stages_H = (int)value;
+        if (which != 'H') p->tma_stages_D = (int)value;
+    } else if (!strcmp(name, "halo_pause")) {
+        if (value != 0 && value != 1) return fail("halo_pause must be 0 or 1");
+        p->halo.paused = value != 0;
     } else if (!strcmp(name, "auto_tensor_map")) {
         if (value != 0 && value != 1) return fail("auto_tensor_map must be 0 or 1");
         p->auto_v5 = (int)value;
@@ -1508,6 +1580,20 @@ int cev_fdtd_set_sources(cev_fdtd* p, int nsrc, const cev_points* src) {
     }
     for (int64_t q = 0; q < total; ++q)
         if (cell[q] < 0 || cell[q] >= ncell) return fail("source point outside the grid");
+    {   // sorted by (component, cell), source order kept inside equal keys: what inject_points (common.cuh) expects
+        std::vector<int64_t> order(total);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) {
+            return comp[x] != comp[y] ? comp[x] < comp[y] : cell[x] < cell[y];
+        });
+        std::vector<int32_t> comp2(total), id2(total);
+        std::vector<int64_t> cell2(total);
+        std::vector<double> w2(total);
+        for (int64_t r = 0; r < total; ++r) {
+            comp2[r] = comp[order[r]]; id2[r] = id[order[r]]; cell2[r] = cell[order[r]]; w2[r] = w[order[r]];
+        }
+        comp.swap(comp2); id.swap(id2); cell.swap(cell2); w.swap(w2);
+    }
     DeviceBuf d_comp, d_id, d_cell, d_w;
     if (d_comp.alloc(total * 4) || d_id.alloc(total * 4) || d_cell.alloc(total * 8) || d_w.alloc(total * 8)) return -1;
     if (total) {
@@ -1657,7 +1743,9 @@ int cev_fdtd_run(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double*
     if (nsteps == 0) return 0;
     if (p->n_src_pts > 0 && !waveform) return fail("plan has sources but waveform is NULL");
     if (p->n_slots > 0 && !partials) return fail("plan has probes but partials is NULL");
-    if (st->D_xhi[1] || st->D_xhi[2] || st->H_xlo[1] || st->H_xlo[2]) return fail("cev_fdtd_run steps a whole (periodic) grid; slabs are driven per half-step");
+    if (st->D_xhi[1] || st->D_xhi[2] || st->H_xlo[1] || st->H_xlo[2])
+        return fail("cev_fdtd_run steps a whole (periodic) grid, or an x-slab whose halos are attached with cev_fdtd_halo_attach; "
+                    "slabs with caller-owned halo planes are driven per half-step");
     DeviceGuard guard(p->device);
     return DISPATCH(p, run_loop, p, st, nsteps, p->n_src_pts > 0 ? waveform : nullptr, partials, (cudaStream_t)stream);
 }
@@ -1673,6 +1761,112 @@ int cev_fdtd_run_fused(cev_fdtd* p, const cev_state* st, const cev_state* shadow
     DeviceGuard guard(p->device);
     return DISPATCH(p, run_loop_fused, p, st, shadow, nsteps, p->n_src_pts > 0 ? waveform : nullptr, partials,
                     (cudaStream_t)stream);
+}
+
+// ---- x-slab halo exchange through peer-mapped memory ------------------------------------------------------
+int cev_fdtd_halo_layout(const cev_fdtd* p, cev_halo_layout* lay) {
+    if (!p || !lay) return fail("NULL argument");
+    halo_layout(p, lay);
+    return 0;
+}
+
+int cev_halo_alloc(int device, size_t bytes, void** block, unsigned char ipc_handle[CEV_IPC_HANDLE_BYTES]) {
+    if (!block || bytes == 0) return fail("bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == CEV_IPC_HANDLE_BYTES, "IPC handle size");
+    DeviceGuard guard(device);
+    void* q = nullptr;
+    CUDA_TRY(cudaMalloc(&q, bytes));
+    if (cudaMemset(q, 0, bytes) != cudaSuccess) {
+        cudaFree(q);
+        return fail("cudaMemset of the halo block failed");
+    }
+    if (ipc_handle) {
+        cudaIpcMemHandle_t h;
+        const cudaError_t e = cudaIpcGetMemHandle(&h, q);
+        if (e != cudaSuccess) {
+            cudaFree(q);
+            return fail("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+        }
+        memcpy(ipc_handle, &h, sizeof h);
+    }
+    *block = q;
+    return 0;
+}
+
+int cev_halo_open(int device, const unsigned char ipc_handle[CEV_IPC_HANDLE_BYTES], void** block) {
+    if (!ipc_handle || !block) return fail("NULL argument");
+    DeviceGuard guard(device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof h);
+    CUDA_TRY(cudaIpcOpenMemHandle(block, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int cev_halo_close(int device, void* block) {
+    if (!block) return 0;
+    DeviceGuard guard(device);
+    CUDA_TRY(cudaIpcCloseMemHandle(block));
+    return 0;
+}
+
+int cev_halo_free(int device, void* block) {
+    if (!block) return 0;
+    DeviceGuard guard(device);
+    CUDA_TRY(cudaFree(block));
+    return 0;
+}
+
+int cev_fdtd_halo_attach(cev_fdtd* p, void* own, void* left, void* right) {
+    if (!p) return fail("NULL argument");
+    if (!own && !left && !right) {
+        p->halo = cev_fdtd::Halo();
+        return 0;
+    }
+    if (!own || !left || !right) return fail("own, left and right exchange blocks must all be given (or all NULL to detach)");
+    if (!p->x_is_x() || p->Nl[1] == 1 || p->Nl[2] == 1) return fail("x-slab halos need a 3-D grid");
+    p->halo.own = (unsigned char*)own;
+    p->halo.left = (unsigned char*)left;
+    p->halo.right = (unsigned char*)right;
+    p->halo.nH = p->halo.nD = 0;
+    return 0;
+}
+
+int cev_fdtd_halo_push_static(cev_fdtd* p, const cev_state* st, void* stream) {
+    if (!p || !st) return fail("NULL argument");
+    if (!p->halo.own) return fail("no exchange block attached");
+    DeviceGuard guard(p->device);
+    cev_halo_layout lay;
+    halo_layout(p, &lay);
+    const size_t es = p->dtype == CEV_F64 ? 8 : 4;
+    const size_t nb = (size_t)p->Nl[1] * p->Nl[2] * es;
+    for (int c = 1; c < 3; ++c) {       // my plane 0 of 1/eps_y, 1/eps_z is the LEFT neighbour's plane nx
+        if (!st->inv_eps[c]) return fail("cev_state: inv_eps missing");
+        CUDA_TRY(cudaMemcpyAsync(p->halo.left + lay.inv_eps_hi[c - 1], st->inv_eps[c], nb, cudaMemcpyDefault, (cudaStream_t)stream));
+    }
+    return 0;
+}
+
+int cev_fdtd_halo_reset(cev_fdtd* p, void* stream) {
+    if (!p) return fail("NULL argument");
+    if (!p->halo.own) return fail("no exchange block attached");
+    DeviceGuard guard(p->device);
+    cev_halo_layout lay;
+    halo_layout(p, &lay);
+    for (int c = 0; c < 2; ++c) {
+        CUDA_TRY(cudaMemsetAsync(p->halo.own + lay.D_hi[c], 0, lay.plane_bytes, (cudaStream_t)stream));
+        CUDA_TRY(cudaMemsetAsync(p->halo.own + lay.H_lo[c], 0, lay.plane_bytes, (cudaStream_t)stream));
+    }
+    return 0;
+}
+
+int cev_fdtd_halo_error(cev_fdtd* p, int* err) {
+    if (!p || !err) return fail("NULL argument");
+    if (!p->halo.own) return fail("no exchange block attached");
+    DeviceGuard guard(p->device);
+    cev_halo_layout lay;
+    halo_layout(p, &lay);
+    CUDA_TRY(cudaMemcpy(err, p->halo.own + lay.err, sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 }  // extern "C"

@@ -116,6 +116,15 @@ struct StepArgs {
     int n_tiles, ntz, nty, xchunk;
     int wz;                   // marching kernels: 1 = the warps of a CTA tile z (grids with a single row per plane)
     int xorder;               // tensor-map kernels: 1 = x-chunks dealt outside-in (v5_chunk_of_rank)
+    // x-slab halo exchange through peer-mapped memory (tensor-map kernels; all NULL / 0 on a periodic grid):
+    // the CTAs that produce the slab's boundary plane also store its y, z components into the neighbour's halo
+    // buffer and bump the neighbour's arrival counter; the CTAs that read this slab's own halo plane first wait
+    // until its counter has reached own_target (see step_v5.cuh)
+    T* peer_out[2];
+    unsigned long long* peer_flag;
+    const unsigned long long* own_flag;
+    unsigned long long own_target;
+    int* halo_err;
     int n_boxes;
     Box box[MAX_BOXES];
     int pf_dist;              // L2 prefetch distance in x-planes (0 = off)
@@ -164,6 +173,27 @@ __device__ void probe_block(const StepArgs<T, AT>& a, int slot) {
         asm volatile("bar.sync 1, %0;" ::"n"(PROBE_THREADS));
     }
     if (tid == 0) a.partials[a.t_probe * a.pr.n_slots + slot] = red[0];
+}
+
+// Sparse J injection, D += J with J = sum_s profile_s * waveform[t, s] (fdtd.py:125-127 for the callers'
+// J = profile * scalar(t), utils.py:328).  The points q0 <= q < q1 are sorted by (component, cell) with the source
+// order kept inside a run of equal keys (the host sorts once, stably): the thread that meets the first point of a run
+// sums the run's terms in that order and adds the sum to the cell ONCE -- the reference's own order (the J arrays
+// are summed, then D += J), no atomics: overlapping sources give the same bits whatever the launch geometry.
+template <typename T, typename AT, typename CELL>
+__device__ __forceinline__ void inject_points(int64_t q0, int64_t q1, int tid, int nthreads, const int32_t* comp,
+                                              const int32_t* id, const CELL* cell, const double* w, const double* wave,
+                                              T* D0, T* D1, T* D2, int64_t cell_lo = 0, int64_t cell_hi = INT64_MAX) {
+    for (int64_t q = q0 + tid; q < q1; q += nthreads) {
+        const int c = comp[q];
+        const CELL o = cell[q];
+        if (q > q0 && comp[q - 1] == c && cell[q - 1] == o) continue;       // not the first point of its run
+        if ((int64_t)o < cell_lo || (int64_t)o >= cell_hi) continue;        // (baseline path: only the planes this launch updated)
+        double j = __dmul_rn(w[q], wave[id[q]]);
+        for (int64_t r = q + 1; r < q1 && comp[r] == c && cell[r] == o; ++r) j = __dadd_rn(j, __dmul_rn(w[r], wave[id[r]]));
+        T* D = c == 0 ? D0 : (c == 1 ? D1 : D2);
+        D[o] = (T)add_rn((AT)D[o], (AT)j);
+    }
 }
 
 // (a1-a0)/dL - (b1-b0)/dL, both quotients rounded before the subtraction (derivatives.py:16-30)

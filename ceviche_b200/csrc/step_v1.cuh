@@ -207,12 +207,9 @@ struct SourceTable {
 template <typename T, typename AT>
 __global__ void k_inject(SourceTable s, T* D0, T* D1, T* D2, const double* __restrict__ wave_row, int64_t cell_lo,
                          int64_t cell_hi) {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= s.n) return;
-    if (s.cell[q] < cell_lo || s.cell[q] >= cell_hi) return;   // only the x-planes this launch updated
-    T* D = s.comp[q] == 0 ? D0 : (s.comp[q] == 1 ? D1 : D2);
-    const T add = (T)(s.weight[q] * wave_row[s.src[q]]);
-    atomicAdd(&D[s.cell[q]], add);
+    // (the plan keeps its points sorted by (component, cell): see inject_points)
+    inject_points<T, AT, int64_t>(0, s.n, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, s.comp, s.src, s.cell,
+                                  s.weight, wave_row, D0, D1, D2, cell_lo, cell_hi);
 }
 
 // Stand-alone probe sampling (after the last step of a run).

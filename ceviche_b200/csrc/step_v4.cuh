@@ -415,13 +415,8 @@ __global__ void __launch_bounds__(32 * BY, (BY >= 8 ? 1 : ((NOPML || V4_PML_NOIN
     // ---- in-kernel source injection: D += J after the update (fdtd.py:125-127)
     if (a.src_wave) {
         __syncthreads();
-        const int tid = threadIdx.y * 32 + threadIdx.x;
-        const int qe = a.src_begin[bid + 1];
-        for (int q = a.src_begin[bid] + tid; q < qe; q += 32 * BY) {
-            const int c = a.src_comp[q];
-            T* Dc = c == 0 ? a.Dout[0] : (c == 1 ? a.Dout[1] : a.Dout[2]);
-            atomicAdd(Dc + a.src_cell[q], (T)(a.src_w[q] * a.src_wave[a.src_id[q]]));
-        }
+        inject_points<T, AT, int32_t>(a.src_begin[bid], a.src_begin[bid + 1], threadIdx.y * 32 + threadIdx.x, 32 * BY, a.src_comp,
+                                      a.src_id, a.src_cell, a.src_w, a.src_wave, a.Dout[0], a.Dout[1], a.Dout[2]);
     }
 }
 

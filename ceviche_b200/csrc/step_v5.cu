@@ -162,9 +162,14 @@ void v5_set_tiles(StepArgs<T, AT>& a, int64_t x0, int64_t x1, int rows, int xchu
     a.x1 = (int)x1;
     a.wz = 0;
     a.xorder = 1;
-    a.xchunk = xchunk > 0 ? xchunk : 16;
     a.ntz = (a.Nz + 32 * V - 1) / (32 * V);
     a.nty = a.Ny / rows;
+    if (xchunk > 0) {
+        a.xchunk = xchunk < V5_MAXCH ? xchunk : V5_MAXCH;
+    } else {       // 16 planes amortise the pipeline fill; shorter chunks where that leaves fewer than ~9 waves of CTAs
+        a.xchunk = 16;
+        while (a.xchunk > 4 && (int64_t)a.ntz * a.nty * ((x1 - x0 + a.xchunk - 1) / a.xchunk) < 4096) a.xchunk /= 2;
+    }
     const int nchunks = (int)((x1 - x0 + a.xchunk - 1) / a.xchunk);
     a.n_tiles = a.ntz * a.nty * nchunks;
     a.n_boxes = 1;

@@ -64,6 +64,45 @@ __device__ __forceinline__ void tma_box_3d(void* dst, const CUtensorMap* map, in
         : "memory");
 }
 
+// ---- x-slab halos over peer-mapped memory -----------------------------------------------------------------
+// The neighbour GPU writes this slab's halo plane straight into its memory (NVLink stores from inside the
+// neighbour's half-step kernel) and then bumps an arrival counter there with a system-scope release.  A CTA about
+// to fetch the halo plane spins on the counter (acquire) and then orders the TMA unit's reads after it.  The wait
+// is bounded: a neighbour that never arrives sets *err instead of hanging the GPU.
+__device__ __forceinline__ void halo_wait(const unsigned long long* flag, unsigned long long target, int* err) {
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        if (v >= target) break;
+        if (clock64() - t0 > (1LL << 33)) {          // ~4 s at 1.9 GHz
+            *err = 1;
+            break;
+        }
+        __nanosleep(100);
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+// after every thread of the CTA has stored its part of the boundary plane to the neighbour (and met at a barrier)
+__device__ __forceinline__ void halo_signal(unsigned long long* peer_flag) {
+    __threadfence_system();
+    atomicAdd_system(peer_flag, 1ULL);
+}
+
+template <typename T, int V>
+__device__ __forceinline__ Vec<T, V> ldv_cg(const T* p) {        // 16-byte load that bypasses L1
+    const int4 raw = __ldcg(reinterpret_cast<const int4*>(p));
+    Vec<T, V> out;
+    static_assert(sizeof(out) == sizeof(raw), "Vec is one 16-byte vector");
+    memcpy(&out, &raw, sizeof(raw));
+    return out;
+}
+
+// bit 1: some lane of the warp is in the y-PML, bit 2: some lane has a cell in the z-PML (loop-invariant votes)
+__device__ __forceinline__ int v5_warp_flags(bool fy, bool fz) {
+    return (__any_sync(0xffffffffu, fy) ? 2 : 0) | (__any_sync(0xffffffffu, fz) ? 4 : 0);
+}
+
 // one lane of a converged warp (SASS ELECT): the TMA instructions take uniform operands, and a branch the
 // compiler knows to be taken by a single lane lets it issue them without a per-lane fallback loop
 __device__ __forceinline__ bool elect_one() {
@@ -84,6 +123,7 @@ struct PmlLean {
     bool fy, fz[V], yz;
     AT uy, ry, su2y;
     AT uz[V], rz[V], su2z[V], rrx[V], m4x[V];
+    AT m1y, m2y, m1zc[V], m2zc[V];             // (2 r - 1, s r) of the single-axis paths below
     int o_ic1, o_ic2, o_is0, o_is1, o_is2;     // plane-independent parts of the compact offsets
     int n1, n2, Ny, Nz, orow;
     // old integrals of the current plane (loaded before the thread blocks on the TMA barrier)
@@ -103,6 +143,8 @@ struct PmlLean {
         fy = my >= 0;
         yz = fy;
         su2y = mul_rn(s, uy + uy);
+        m1y = add_rn(ry + ry, AT(-1));
+        m2y = mul_rn(s, ry);
         const AT n4uy = mul_rn(AT(-4), uy);
         int mz0 = 0;
 #pragma unroll
@@ -115,6 +157,8 @@ struct PmlLean {
             su2z[e] = mul_rn(s, uz[e] + uz[e]);
             rrx[e] = mul_rn(ry, rz[e]);
             m4x[e] = mul_rn(mul_rn(n4uy, uz[e]), rrx[e]);
+            m1zc[e] = add_rn(rz[e] + rz[e], AT(-1));
+            m2zc[e] = mul_rn(s, rz[e]);
             if (e == 0) mz0 = mz[0];
         }
         (void)mz0;
@@ -143,12 +187,11 @@ struct PmlLean {
     }
 
     // old[c].v[e], curl[c][e] -> out[c].v[e]; the new integrals go back to global memory
-    __device__ __forceinline__ void apply(const StepArgs<T, AT>& a, int i, int mx, AT s, const Vec<T, V>* old,
+    __device__ __forceinline__ void apply(const StepArgs<T, AT>& a, int i, int mx, AT ux, AT rx, AT s, const Vec<T, V>* old,
                                           const AT (*curl)[V], Vec<T, V>* out) {
         T* const* Ic = IS_H ? a.ICE : a.ICH;
         T* const* Is = IS_H ? a.IH : a.ID;
         const bool fx = mx >= 0;
-        const AT ux = CEV_TAB(a, u, 0)[i], rx = CEV_TAB(a, r, 0)[i];
         const AT su2x = mul_rn(s, ux + ux);
         const AT n4ux = mul_rn(AT(-4), ux);
         // z component: (a, b) = (x, y): the same coefficients for the V cells
@@ -213,15 +256,103 @@ struct PmlLean {
         if (fx && fy) stv<T, V>(Is[2] + mx * (n1 * Nz) + o_is2, s2v);
     }
 
-    // pull the y- and z-slab curl integrals of a later plane of this thread into L2
-    __device__ __forceinline__ void prefetch(const StepArgs<T, AT>& a, int ip, bool line_lane) const {
+    __device__ __forceinline__ bool fz_any() const {
+        bool f = false;
+#pragma unroll
+        for (int e = 0; e < V; ++e) f |= fz[e];
+        return f;
+    }
+
+    // ---- single-axis paths.  Most PML cells lie in the PML of ONE axis (the faces of the shell), where the other two
+    // axes have u = 0, r = 1 exactly and the general update above collapses: products with 1 and sums with 0 are
+    // exact, so the expressions below are the general ones with those factors dropped -- bit for bit the same
+    // values, a third of the instructions.  The caller picks a path per WARP (votes over the lanes' flags); lanes
+    // of the warp that are off the PML take it with u = 0, r = 1 and get the vacuum update.
+    // x only: every lane has the same coefficients (fx holds for the whole plane)
+    __device__ __forceinline__ void apply_x(const StepArgs<T, AT>& a, int mx, AT ux, AT rx, AT s, const Vec<T, V>* old,
+                                            const AT (*curl)[V], Vec<T, V>* out) {
         T* const* Ic = IS_H ? a.ICE : a.ICH;
+        const AT su2x = mul_rn(s, ux + ux);
+        const AT m1 = add_rn(rx + rx, AT(-1)), m2 = mul_rn(s, rx);
+        Vec<T, V> n0;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const AT I = (AT)I0.v[e] + curl[0][e];
+            n0.v[e] = (T)I;
+            out[0].v[e] = (T)muladd(su2x, I, muladd(s, curl[0][e], (AT)old[0].v[e]));
+            out[1].v[e] = (T)muladd(m1, (AT)old[1].v[e], mul_rn(m2, curl[1][e]));
+            out[2].v[e] = (T)muladd(m1, (AT)old[2].v[e], mul_rn(m2, curl[2][e]));
+        }
+        stv<T, V>(Ic[0] + mx * (Ny * Nz) + orow, n0);
+    }
+    // y only (this thread's row may or may not be in the y-PML: fy)
+    __device__ __forceinline__ void apply_y(const StepArgs<T, AT>& a, int i, AT s, const Vec<T, V>* old, const AT (*curl)[V],
+                                            Vec<T, V>* out) {
+        T* const* Ic = IS_H ? a.ICE : a.ICH;
+        Vec<T, V> n1v;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            out[0].v[e] = (T)muladd(m1y, (AT)old[0].v[e], mul_rn(m2y, curl[0][e]));
+            AT v = muladd(s, curl[1][e], (AT)old[1].v[e]);
+            if (fy) {
+                const AT I = (AT)I1.v[e] + curl[1][e];
+                n1v.v[e] = (T)I;
+                v = muladd(su2y, I, v);
+            }
+            out[1].v[e] = (T)v;
+            out[2].v[e] = (T)muladd(m1y, (AT)old[2].v[e], mul_rn(m2y, curl[2][e]));
+        }
+        if (fy) stv<T, V>(Ic[1] + i * (n1 * Nz) + o_ic1, n1v);
+    }
+    // z only (each of this thread's cells may or may not be in the z-PML: fz[e])
+    __device__ __forceinline__ void apply_z(const StepArgs<T, AT>& a, int i, AT s, const Vec<T, V>* old, const AT (*curl)[V],
+                                            Vec<T, V>* out) {
+        T* const* Ic = IS_H ? a.ICE : a.ICH;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            out[0].v[e] = (T)muladd(m1zc[e], (AT)old[0].v[e], mul_rn(m2zc[e], curl[0][e]));
+            out[1].v[e] = (T)muladd(m1zc[e], (AT)old[1].v[e], mul_rn(m2zc[e], curl[1][e]));
+            AT v = muladd(s, curl[2][e], (AT)old[2].v[e]);
+            if (fz[e]) {
+                const AT I = (AT)I2[e] + curl[2][e];
+                Ic[2][i * (Ny * n2) + o_ic2 + mz[e]] = (T)I;
+                v = muladd(su2z[e], I, v);
+            }
+            out[2].v[e] = (T)v;
+        }
+    }
+
+    // pull the curl integrals of a later plane of this thread into L2 (mxp: that plane's compact x index)
+    __device__ __forceinline__ void prefetch(const StepArgs<T, AT>& a, int ip, int mxp, bool line_lane) const {
+        T* const* Ic = IS_H ? a.ICE : a.ICH;
+        if (mxp >= 0 && line_lane) prefetch_l2(Ic[0] + mxp * (Ny * Nz) + orow);
         if (fy && line_lane) prefetch_l2(Ic[1] + ip * (n1 * Nz) + o_ic1);
         if (fz[0]) prefetch_l2(Ic[2] + ip * (Ny * n2) + o_ic2 + mz[0]);
         else if (fz[V - 1]) prefetch_l2(Ic[2] + ip * (Ny * n2) + o_ic2 + mz[V - 1]);
     }
 #undef CEV_TAB
 };
+
+// Per-plane PML table entries of a CTA's x-chunk (compact index, u, r of the x axis) staged in shared memory by
+// the prologue: the marching loop then reads them with LDS latency instead of one dependent global load per plane.
+constexpr int V5_MAXCH = 64;      // longest x-chunk (the host clamps)
+constexpr int V5_PF = 3;          // L2 prefetch distance of the PML integrals, in planes
+template <typename AT>
+struct V5XTab {
+    int mx[V5_MAXCH + V5_PF + 1];
+    AT u[V5_MAXCH], r[V5_MAXCH];
+};
+template <typename AT>
+__device__ __forceinline__ void v5_fill_xtab(V5XTab<AT>& t, const int* map, const AT* u, const AT* r, int xs, int xe, int x1,
+                                             int tid, int nthreads) {
+    for (int q = tid; q < xe - xs + V5_PF + 1; q += nthreads) {
+        t.mx[q] = xs + q < x1 ? map[xs + q] : -1;
+        if (xs + q < xe) {
+            t.u[q] = u[xs + q];
+            t.r[q] = r[xs + q];
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Which tile / x-chunk a CTA serves and which cells of it a thread owns.  A warp covers 8 vectors along z times
@@ -273,6 +404,8 @@ __global__ void __launch_bounds__(32 * BY) k_step_H_v5(const StepArgs<T, AT> a, 
     const int k0 = active ? z0 + t.vec * V : z0;
     const int plane = a.Ny * a.Nz;
 
+    __shared__ V5XTab<AT> xt;
+    v5_fill_xtab<AT>(xt, a.mapH[0], a.uH[0], a.rH[0], xs, xe, a.x1, w * 32 + lane, 32 * BY);
     if (lane == 0 && w == 0) {
 #pragma unroll
         for (int s = 0; s < NS; ++s) mbar_init(&full[s], BY);
@@ -299,6 +432,7 @@ __global__ void __launch_bounds__(32 * BY) k_step_H_v5(const StepArgs<T, AT> a, 
     };
     auto box_nxt = [&](int q, T* st, int p, uint64_t* bar) {
         const bool hi = p >= a.Nx;
+        if (hi && a.own_flag) halo_wait(a.own_flag, a.own_target, a.halo_err);    // x-slab: the right neighbour's plane 0
         const int px = hi ? maps.x_hi : p;
         const int c = 1 + q % 2;                           // q = 0..3: D_y, D_z, mE_y, mE_z
         if (q < 2) tma_box_3d(st + c * BLK, hi ? &maps.Dhi[c - 1] : &maps.D[c], z0, y0, px, bar);
@@ -348,6 +482,7 @@ __global__ void __launch_bounds__(32 * BY) k_step_H_v5(const StepArgs<T, AT> a, 
     const AT inv = a.inv_dL;
     PmlLean<T, AT, V, true> pml;
     pml.init(a, j, k0, s);
+    const int warp_yz = v5_warp_flags(pml.fy, pml.fz_any());
     const int orow = j * a.Nz + k0;
     const bool zedge = k0 + V >= a.Nz;               // the +1 z-neighbour of this lane's last cell is k = 0
     const int col = t.vec * V;
@@ -357,20 +492,39 @@ __global__ void __launch_bounds__(32 * BY) k_step_H_v5(const StepArgs<T, AT> a, 
     int sc = 0;                                      // stage of the current plane, parity of its barrier
     uint32_t ph = 0;
     int sp = NS - 1;                                 // stage to refill at this iteration (plane i + NS - 1)
+    T gn0 = T(0), gn1 = T(0), gn2 = T(0), gn3 = T(0);
+    if (zedge) {
+        const int okp = xs * plane + j * a.Nz;
+        gn0 = a.mE[0][okp]; gn1 = a.Din[0][okp]; gn2 = a.mE[1][okp]; gn3 = a.Din[1][okp];
+    }
     for (int i = xs; i < xe; ++i) {
         if (i + NS - 1 <= xe) issue(i + NS - 1, sp);
         sp = (sp + 1 == NS) ? 0 : sp + 1;
         const int sn = (sc + 1 == NS) ? 0 : sc + 1;
         const uint32_t phn = (sn == 0) ? ph ^ 1u : ph;
-        const int mx = a.mapH[0][i];
+        const int q = i - xs;
+        const int mx = xt.mx[q];
         const bool in_pml = pml.yz || mx >= 0;
+        // the old PML integrals go through the LSU: issued (with the L2 prefetch of a later plane's) before the thread
+        // blocks on the TMA barriers, so that their latency overlaps the wait and the shared-memory loads
         if (in_pml && active) pml.load(a, i, mx);
-        if (active && pml.yz && i + 2 < a.x1) pml.prefetch(a, i + 2, (lane & 7) == 0);
+        {
+            const int mxp = xt.mx[q + V5_PF];
+            if (active && (pml.yz || mxp >= 0) && i + V5_PF < a.x1) pml.prefetch(a, i + V5_PF, mxp, (lane & 7) == 0);
+        }
+        const int pbase = i * plane;
+        // periodic wrap along z: the box is zero-filled beyond the row, so the edge lane takes the cell k = 0 of its row
+        // straight from global memory -- fetched ONE PLANE AHEAD (these loads miss every cache level: issued at the
+        // point of use they put a DRAM round trip on the warp's critical path, 10 % of the kernel when measured)
+        const T gx0 = gn0, gx1 = gn1, gx2 = gn2, gx3 = gn3;
+        if (zedge && i + 1 < xe) {
+            const int okp = pbase + plane + j * a.Nz;
+            gn0 = a.mE[0][okp]; gn1 = a.Din[0][okp]; gn2 = a.mE[1][okp]; gn3 = a.Din[1][okp];
+        }
         mbar_wait(&full[sc], ph);
         mbar_wait(&full[sn], phn);
         const T* cur = stage0 + (size_t)sc * L::H_STAGE;
         const T* nxt = stage0 + (size_t)sn * L::H_STAGE;
-        const int pbase = i * plane;
 
         AT E[3][V], CE[3][V];
         Vec<T, V> h[3];
@@ -387,10 +541,9 @@ __global__ void __launch_bounds__(32 * BY) k_step_H_v5(const StepArgs<T, AT> a, 
         const Vec<T, V> dyn = ldv<T, V>(nxt + 1 * BLK + r0), myn = ldv<T, V>(nxt + 4 * BLK + r0);
         const Vec<T, V> dzn = ldv<T, V>(nxt + 2 * BLK + r0), mzn = ldv<T, V>(nxt + 5 * BLK + r0);
         AT ex_kp, ey_kp;
-        if (zedge) {                                 // periodic wrap along z: the box was zero-filled there
-            const int okp = pbase + j * a.Nz;
-            ex_kp = mul_rn((AT)a.mE[0][okp], (AT)a.Din[0][okp]);
-            ey_kp = mul_rn((AT)a.mE[1][okp], (AT)a.Din[1][okp]);
+        if (zedge) {
+            ex_kp = mul_rn((AT)gx0, (AT)gx1);
+            ey_kp = mul_rn((AT)gx2, (AT)gx3);
         } else {
             ex_kp = mul_rn((AT)cur[3 * BLK + r0 + V], (AT)cur[0 * BLK + r0 + V]);
             ey_kp = mul_rn((AT)cur[4 * BLK + r0 + V], (AT)cur[1 * BLK + r0 + V]);
@@ -410,21 +563,34 @@ __global__ void __launch_bounds__(32 * BY) k_step_H_v5(const StepArgs<T, AT> a, 
         }
         if (active) {
             Vec<T, V> out[3];
-            if (!in_pml) {
+            // path of the WARP: none / one axis / general (see PmlLean)
+            const int path = (mx >= 0 ? 1 : 0) | warp_yz;
+            if (path == 0) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
 #pragma unroll
                     for (int e = 0; e < V; ++e) out[c].v[e] = (T)muladd(s, CE[c][e], (AT)h[c].v[e]);
+            } else if (path == 1) {
+                pml.apply_x(a, mx, xt.u[q], xt.r[q], s, h, CE, out);
+            } else if (path == 2) {
+                pml.apply_y(a, i, s, h, CE, out);
+            } else if (path == 4) {
+                pml.apply_z(a, i, s, h, CE, out);
             } else {
-                pml.apply(a, i, mx, s, h, CE, out);
+                pml.apply(a, i, mx, xt.u[q], xt.r[q], s, h, CE, out);
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) stv<T, V>(a.Hout[c] + pbase + orow, out[c]);
+            if (a.peer_out[0] && i + 1 == a.Nx) {    // x-slab: H_y, H_z of the last plane are the right neighbour's i = -1
+                stv<T, V>(a.peer_out[0] + orow, out[1]);
+                stv<T, V>(a.peer_out[1] + orow, out[2]);
+            }
         }
         __syncthreads();                             // every warp is done with the oldest stage: it may be refilled
         sc = sn;
         ph = phn;
     }
+    if (a.peer_out[0] && xe == a.Nx && lane == 0 && w == 0) halo_signal(a.peer_flag);   // (after the loop's last barrier)
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -451,6 +617,8 @@ __global__ void __launch_bounds__(32 * BY) k_step_D_v5(const StepArgs<T, AT> a, 
     const int k0 = active ? z0 + t.vec * V : z0;
     const int plane = a.Ny * a.Nz;
 
+    __shared__ V5XTab<AT> xt;
+    v5_fill_xtab<AT>(xt, a.mapD[0], a.uD[0], a.rD[0], xs, xe, a.x1, w * 32 + lane, 32 * BY);
     if (lane == 0 && w == 0) {
 #pragma unroll
         for (int s = 0; s < NS; ++s) mbar_init(&full[s], BY);
@@ -505,6 +673,7 @@ __global__ void __launch_bounds__(32 * BY) k_step_D_v5(const StepArgs<T, AT> a, 
             mbar_arrive_tx(bar, w < 2 ? BM : 0u);
             if (w < 2) {
                 const bool lo = p < 0;
+                if (lo && a.own_flag) halo_wait(a.own_flag, a.own_target, a.halo_err);    // x-slab: the left neighbour's last plane
                 const int px = lo ? maps.x_lo : p;
                 tma_box_3d(st + (1 + w) * BLK, lo ? &maps.Hlo[w] : &maps.H[1 + w], z0 - V, y0, px, bar);
             }
@@ -518,6 +687,7 @@ __global__ void __launch_bounds__(32 * BY) k_step_D_v5(const StepArgs<T, AT> a, 
     const AT inv = a.inv_dL;
     PmlLean<T, AT, V, false> pml;
     pml.init(a, j, k0, s);
+    const int warp_yz = v5_warp_flags(pml.fy, pml.fz_any());
     const int orow = j * a.Nz + k0;
     const bool zedge = k0 == 0;                      // the -1 z-neighbour of this lane's first cell is k = Nz-1
     const int col = V + t.vec * V;
@@ -527,20 +697,35 @@ __global__ void __launch_bounds__(32 * BY) k_step_D_v5(const StepArgs<T, AT> a, 
     int sc = 0;                                      // stage of plane i-1
     uint32_t ph = 0;
     int sp = NS - 1;                                 // stage to refill at this iteration (plane i + NS - 2)
+    T gn0 = T(0), gn1 = T(0);
+    if (zedge) {
+        const int okm = xs * plane + j * a.Nz + a.Nz - 1;
+        gn0 = a.Hin[0][okm]; gn1 = a.Hin[1][okm];
+    }
     for (int i = xs; i < xe; ++i) {
         if (i + NS - 2 < xe) issue(i + NS - 2, sp);
         sp = (sp + 1 == NS) ? 0 : sp + 1;
         const int sn = (sc + 1 == NS) ? 0 : sc + 1;
         const uint32_t phn = (sn == 0) ? ph ^ 1u : ph;
-        const int mx = a.mapD[0][i];
+        const int q = i - xs;
+        const int mx = xt.mx[q];
         const bool in_pml = pml.yz || mx >= 0;
         if (in_pml && active) pml.load(a, i, mx);
-        if (active && pml.yz && i + 2 < a.x1) pml.prefetch(a, i + 2, (lane & 7) == 0);
+        {
+            const int mxp = xt.mx[q + V5_PF];
+            if (active && (pml.yz || mxp >= 0) && i + V5_PF < a.x1) pml.prefetch(a, i + V5_PF, mxp, (lane & 7) == 0);
+        }
+        const int pbase = i * plane;
+        // periodic wrap along z: the cell k = Nz-1 of the row, straight from global memory, one plane ahead (see k_step_H_v5)
+        const T gx0 = gn0, gx1 = gn1;
+        if (zedge && i + 1 < xe) {
+            const int okm = pbase + plane + j * a.Nz + a.Nz - 1;
+            gn0 = a.Hin[0][okm]; gn1 = a.Hin[1][okm];
+        }
         mbar_wait(&full[sc], ph);
         mbar_wait(&full[sn], phn);
         const T* prv = stage0 + (size_t)sc * L::D_STAGE;
         const T* cur = stage0 + (size_t)sn * L::D_STAGE;
-        const int pbase = i * plane;
 
         Vec<T, V> h[3], d[3];
 #pragma unroll
@@ -551,10 +736,9 @@ __global__ void __launch_bounds__(32 * BY) k_step_D_v5(const StepArgs<T, AT> a, 
         const Vec<T, V> hxj = ldv<T, V>(cur + 0 * BLK + rm), hzj = ldv<T, V>(cur + 2 * BLK + rm);
         const Vec<T, V> hyp = ldv<T, V>(prv + 1 * BLK + r0), hzp = ldv<T, V>(prv + 2 * BLK + r0);
         AT hx_km, hy_km;
-        if (zedge) {                                 // periodic wrap along z: the box was zero-filled there
-            const int okm = pbase + j * a.Nz + a.Nz - 1;
-            hx_km = (AT)a.Hin[0][okm];
-            hy_km = (AT)a.Hin[1][okm];
+        if (zedge) {
+            hx_km = (AT)gx0;
+            hy_km = (AT)gx1;
         } else {
             hx_km = (AT)cur[0 * BLK + r0 - 1];
             hy_km = (AT)cur[1 * BLK + r0 - 1];
@@ -571,13 +755,20 @@ __global__ void __launch_bounds__(32 * BY) k_step_D_v5(const StepArgs<T, AT> a, 
         }
         if (active) {
             Vec<T, V> out[3];
-            if (!in_pml) {
+            const int path = (mx >= 0 ? 1 : 0) | warp_yz;
+            if (path == 0) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
 #pragma unroll
                     for (int e = 0; e < V; ++e) out[c].v[e] = (T)muladd(s, CH[c][e], (AT)d[c].v[e]);
+            } else if (path == 1) {
+                pml.apply_x(a, mx, xt.u[q], xt.r[q], s, d, CH, out);
+            } else if (path == 2) {
+                pml.apply_y(a, i, s, d, CH, out);
+            } else if (path == 4) {
+                pml.apply_z(a, i, s, d, CH, out);
             } else {
-                pml.apply(a, i, mx, s, d, CH, out);
+                pml.apply(a, i, mx, xt.u[q], xt.r[q], s, d, CH, out);
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) stv<T, V>(a.Dout[c] + pbase + orow, out[c]);
@@ -589,13 +780,20 @@ __global__ void __launch_bounds__(32 * BY) k_step_D_v5(const StepArgs<T, AT> a, 
 
     // ---- in-kernel source injection: D += J after the update (fdtd.py:125-127)
     if (a.src_wave) {
-        const int tid = threadIdx.y * 32 + threadIdx.x;
-        const int qe = a.src_begin[bid + 1];
-        for (int q = a.src_begin[bid] + tid; q < qe; q += 32 * BY) {
-            const int c = a.src_comp[q];
-            T* Dc = c == 0 ? a.Dout[0] : (c == 1 ? a.Dout[1] : a.Dout[2]);
-            atomicAdd(Dc + a.src_cell[q], (T)(a.src_w[q] * a.src_wave[a.src_id[q]]));
+        inject_points<T, AT, int32_t>(a.src_begin[bid], a.src_begin[bid + 1], threadIdx.y * 32 + threadIdx.x, 32 * BY, a.src_comp,
+                                      a.src_id, a.src_cell, a.src_w, a.src_wave, a.Dout[0], a.Dout[1], a.Dout[2]);
+    }
+    // ---- x-slab: D_y, D_z of plane 0 (sources included) are the left neighbour's i = nx plane
+    if (a.peer_out[0] && xs == 0) {
+        __syncthreads();                             // the injections above have been issued
+        if (active) {
+            const Vec<T, V> dy = ldv_cg<T, V>(a.Dout[1] + orow);     // (L2, where the injections landed)
+            const Vec<T, V> dz = ldv_cg<T, V>(a.Dout[2] + orow);
+            stv<T, V>(a.peer_out[0] + orow, dy);
+            stv<T, V>(a.peer_out[1] + orow, dz);
         }
+        __syncthreads();
+        if (lane == 0 && w == 0) halo_signal(a.peer_flag);
     }
 }
 

@@ -114,7 +114,15 @@ class _Plan:
 
 class fdtd:
 
-    def __init__(self, eps_r, dL, npml, *, dtype=torch.float64, device=None, arith=None):
+    def __new__(cls, eps_r=None, dL=None, npml=None, *, devices=None, global_shape=None, **kw):
+        """`devices=[...]` (more than one): the grid is cut into x-slabs over the GPUs of one box, one process per GPU
+        (ceviche_b200/slab.py); the object returned has the same caller-loop surface."""
+        if devices is not None and len(devices) > 1:
+            from .slab import make_slab_fdtd
+            return make_slab_fdtd(eps_r, dL, npml, devices=devices, global_shape=global_shape, **kw)
+        return super().__new__(cls)
+
+    def __init__(self, eps_r, dL, npml, *, dtype=torch.float64, device=None, arith=None, devices=None, global_shape=None):
         """ Makes an FDTD object (signature of ceviche/fdtd.py:12)
                 eps_r: relative permittivity, 1-/2-/3-D numpy array or torch tensor
                 dL: the grid size (scalar, as the reference: fdtd.py:219)
@@ -124,6 +132,10 @@ class fdtd:
         """
         if dtype not in _DTYPES:
             raise ValueError("dtype must be torch.float64 or torch.float32")
+        if devices is not None and len(devices) == 1 and device is None:
+            device = devices[0] if not isinstance(devices[0], int) else torch.device("cuda", devices[0])
+        if global_shape is not None:
+            raise ValueError("global_shape is only meaningful with several `devices` (x-slabs)")
         if not torch.cuda.is_available():
             raise _lib.CevicheB200Error("ceviche_b200 needs a CUDA device: there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)

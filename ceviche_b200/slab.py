@@ -9,11 +9,21 @@ each halo plane are contiguous blocks: no packing).  The stencil reach is one pl
 * the D half-step (curl_H, derivatives.py:24-30: backward differences) needs H_y, H_z at local i = -1
   -> plane nx-1 of the LEFT neighbour.
 
-np.roll wraps, so the ranks form a ring (rank 0 <-> rank P-1).  Schedule per half-step: interior planes
-first (they need no halo), then wait for the halo posted at the end of the previous half-step, then the
-one boundary plane, then post this half-step's send/recv (NCCL send/recv over NVLink, on a side stream):
-every message has a whole interior half-step to arrive.  Probe partial sums are reduced once at the end.
-Results are bit-identical to the single-GPU run (no arithmetic is reordered).
+np.roll wraps, so the ranks form a ring (rank 0 <-> rank P-1).  Two halo transports:
+
+* "peer" (default wherever the tensor-map kernels serve the slab: 3-D, Ny a multiple of 4, Nz a multiple of the
+  16-byte vector and >= 32 vectors): every rank owns an exchange block in device memory, shared with its two
+  neighbours by CUDA IPC; the CTAs that produce a slab's boundary plane store it straight into the neighbour's
+  block (NVLink peer stores) and bump an arrival counter there, the CTAs that read a halo plane wait for its
+  counter (include/ceviche_b200.h, "x-slab decomposition").  One H and one D launch per time step per rank, the
+  time loop runs in C (cev_fdtd_run): no collective, no extra launch, no Python per step.
+* "nccl" (any grid the path serves, incl. 2-D): per half-step the interior planes first (they need no halo),
+  then wait for the halo posted at the end of the previous half-step, then the one boundary plane, then post
+  this half-step's ncclSend/ncclRecv on a side stream.
+
+Probe partial sums are reduced once per run().  Results are bit-identical to the single-GPU run (no arithmetic
+is reordered).  `ceviche_b200.fdtd(eps_r, dL, npml, devices=[...])` returns a SlabFDTD: the same object surface
+(run / prepare / forward / initialize_fields / fields / t_index / dt / grid_shape), one process per GPU.
 
 The per-slab compute goes through a small backend interface (`CudaSlabBackend` = the C ABI); tests inject
 a numpy backend to exercise the partitioning / exchange / reduction logic on CPU with gloo.
@@ -157,6 +167,13 @@ class CudaSlabBackend:
         _lib.check(self.plan.lib.cev_fdtd_sample_probes(self.plan.handle, C.byref(st), None, which, t,
                                                         self.partials.data_ptr(), self._s()))
 
+    def run_c(self, steps, wf):
+        """The whole time loop in C (cev_fdtd_run): the plan's attached exchange blocks carry the halos."""
+        st = self._st or self._state()
+        _lib.check(self.plan.lib.cev_fdtd_run(self.plan.handle, C.byref(st), steps,
+                                              wf.data_ptr() if self.n_sources and steps else None,
+                                              self.partials.data_ptr() if self.n_slots and steps else None, self._s()))
+
     def series(self):
         return self.partials @ self.fold
 
@@ -167,16 +184,53 @@ class CudaSlabBackend:
         return (self.D if key[0] == "D" else self.H)[c]
 
 
+class _LazyFields:
+    """`fields` of a slab simulator: fields[key] gathers the full (Nx, Ny, Nz) array on every rank (a collective:
+    all ranks must ask for the same keys in the same order).  `local_fields[key]` is this rank's slab."""
+
+    def __init__(self, sim):
+        self._sim = sim
+
+    def __getitem__(self, key):
+        return self._sim.gather(key)
+
+    def keys(self):
+        return ("Ex", "Ey", "Ez", "Dx", "Dy", "Dz", "Hx", "Hy", "Hz")
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+
+class _LocalFields(_LazyFields):
+    def __getitem__(self, key):
+        loc = self._sim.be.field(key)
+        return loc if torch.is_tensor(loc) else torch.as_tensor(loc)
+
+
 class SlabFDTD:
-    """FDTD on an x-slab per rank.  `eps_local` is this rank's slab of eps_r WITH one extra leading
-    plane (global plane lo-1, periodic) as needed by the Yee averaging along x (utils.py:167)."""
+    """FDTD on an x-slab per rank (one process per GPU): what `ceviche_b200.fdtd(eps_r, dL, npml, devices=[...])`
+    returns.  Same surface as the single-GPU object for the caller loop: prepare / run / forward /
+    initialize_fields / set_option / fields / t_index / dt / grid_shape / Nx, Ny, Nz.
+
+    eps_r: the GLOBAL permittivity (every rank passes the same array; the slab and the extra plane the Yee
+    averaging along x needs, utils.py:167, are cut here), or -- with `global_shape` given -- this rank's slab WITH
+    one extra leading plane (global plane lo-1, periodic), shape (nx+1, Ny, Nz), for grids too large to
+    materialise on every rank."""
 
     def __init__(self, global_shape, eps_local, dL, npml, *, dtype=torch.float64, device=None, group=None,
-                 backend_factory=None):
+                 backend_factory=None, path=None, arith=None, _ring=None):
         self.group = group
-        self.P = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.Nx, self.Ny, self.Nz = self.global_shape = tuple(global_shape)
+        if _ring is not None:                     # several slabs in one process (tests): (rank, world)
+            self.rank, self.P = _ring
+        else:
+            self.P = dist.get_world_size(group) if dist.is_initialized() else 1
+            self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._in_process = _ring is not None
+        self.Nx, self.Ny, self.Nz = self.global_shape = self.grid_shape = tuple(int(v) for v in global_shape)
+        self.N = self.Nx * self.Ny * self.Nz
         if self.Ny <= 1 and self.Nz <= 1:
             raise ValueError("slab decomposition needs a 2-D or 3-D grid (Ny > 1 or Nz > 1)")
         self.lo, self.hi = partition(self.Nx, self.P)[self.rank]
@@ -198,20 +252,108 @@ class SlabFDTD:
         local_shape = (self.nx, self.Ny, self.Nz)
         if backend_factory is None:
             dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-            self.be = CudaSlabBackend(dev, dtype, local_shape, dL, self.dt, sH, sD, inv_eps)
+            self.be = CudaSlabBackend(dev, dtype, local_shape, dL, self.dt, sH, sD, inv_eps,
+                                      arith_f64=arith in ("f64", torch.float64))
         else:
             self.be = backend_factory(local_shape, dL, self.dt, sH, sD, [m.cpu().numpy() for m in inv_eps])
         self.right = (self.rank + 1) % self.P
         self.left = (self.rank - 1) % self.P
-        self.be.halo = self.P > 1
         self._pending = []
         self.t_index = 0
-        if self.P > 1:
+        self.n_probes = 0
+        self.fields = _LazyFields(self)
+        self.local_fields = _LocalFields(self)
+        self._blocks = None
+        # ---- which halo transport
+        if path not in (None, "peer", "nccl"):
+            raise ValueError("path must be 'peer', 'nccl' or None (auto)")
+        can_peer = self.be.is_cuda and self.P > 1 and self._peer_supported()
+        if path == "peer" and not can_peer:
+            raise ValueError("the peer-memory halo path needs CUDA slabs of a 3-D grid with Ny a multiple of 4 and Nz a "
+                             "multiple of the 16-byte vector and >= 32 vectors")
+        self.path = "none" if self.P == 1 else ("peer" if (can_peer and path != "nccl") else "nccl")
+        self.be.halo = self.path == "nccl"
+        if self.path == "nccl":
             # static halo: 1/eps_y, 1/eps_z at local i = nx  <- plane 0 of the right neighbour
             self._exchange([self.be.mE[1][0], self.be.mE[2][0]], self.left, [self.be.mE_hi[1], self.be.mE_hi[2]], self.right)
             self._wait()
+        elif self.path == "peer" and not self._in_process:
+            self._peer_setup_ipc()
 
-    # ---- halo plumbing ------------------------------------------------------------------------
+    def __repr__(self):
+        return "FDTD(eps_r.shape={}, dL={}, NPML={}, x-slab {} of {})".format(self.grid_shape, self.dL, self.npml,
+                                                                               self.rank, self.P)
+
+    def slab_path(self):
+        return {"peer": "direct stores into the neighbour's peer-mapped halo block from inside the half-step kernels "
+                        "(CUDA IPC over NVLink), arrival counters, time loop in C",
+                "nccl": "ncclSend/ncclRecv of the halo planes per half-step on a side stream, boundary plane launched after the interior",
+                "none": "single slab (periodic wrap inside the array)"}[self.path]
+
+    def set_option(self, name, value):
+        _lib.check(self.be.plan.lib.cev_fdtd_set_option(self.be.plan.handle, name.encode(), int(value)))
+
+    # ---- peer-memory halo plumbing ----------------------------------------------------------------
+    def _peer_supported(self):
+        v = 2 if self.dtype == torch.float64 else 4
+        return (self.Ny > 1 and self.Nz > 1 and self.Ny % 4 == 0 and self.Nz % v == 0 and self.Nz >= 32 * v)
+
+    def _layout(self):
+        lay = _lib.cev_halo_layout()
+        _lib.check(self.be.plan.lib.cev_fdtd_halo_layout(self.be.plan.handle, C.byref(lay)))
+        return lay
+
+    def _peer_alloc(self, want_handle=True):
+        lib = self.be.plan.lib
+        block, handle = C.c_void_p(), C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        _lib.check(lib.cev_halo_alloc(self.be.device.index, self._layout().bytes, C.byref(block), handle if want_handle else None))
+        return block, handle.raw
+
+    def _peer_attach(self, own, left, right):
+        """own / left / right: device pointers of the three exchange blocks (left may equal right)."""
+        be, lib = self.be, self.be.plan.lib
+        self._blocks = (own, left, right)
+        _lib.check(lib.cev_fdtd_halo_attach(be.plan.handle, own, left, right))
+        with torch.cuda.device(be.device):
+            st = be._state()
+            _lib.check(lib.cev_fdtd_halo_push_static(be.plan.handle, C.byref(st), be._s()))
+            torch.cuda.current_stream(be.device).synchronize()
+
+    def _peer_setup_ipc(self):
+        """One process per GPU: allocate this rank's block, trade IPC handles, map the neighbours' blocks."""
+        lib, dev = self.be.plan.lib, self.be.device.index
+        own, handle = self._peer_alloc()
+        handles = [None] * self.P
+        dist.all_gather_object(handles, handle, group=self.group)
+        opened = {}
+        for r in {self.left, self.right}:
+            q = C.c_void_p()
+            _lib.check(lib.cev_halo_open(dev, handles[r], C.byref(q)))
+            opened[r] = q
+        self._opened, self._own_block = opened, own
+        self._peer_attach(own, opened[self.left], opened[self.right])
+        dist.barrier(group=self.group)            # every neighbour's 1/eps halo has landed before the first step
+
+    def _peer_check(self):
+        err = C.c_int(0)
+        _lib.check(self.be.plan.lib.cev_fdtd_halo_error(self.be.plan.handle, C.byref(err)))
+        if err.value:
+            raise _lib.CevicheB200Error("x-slab halo wait timed out: a neighbouring rank never delivered its boundary plane "
+                                        "(all ranks must run the same sequence of steps)")
+
+    def __del__(self):
+        try:
+            if self._blocks is not None and not self._in_process:
+                lib, dev = self.be.plan.lib, self.be.device.index
+                lib.cev_fdtd_halo_attach(self.be.plan.handle, None, None, None)
+                for q in self._opened.values():
+                    lib.cev_halo_close(dev, q)
+                lib.cev_halo_free(dev, self._own_block)
+                self._blocks = None
+        except Exception:
+            pass
+
+    # ---- NCCL halo plumbing -------------------------------------------------------------------------
     def _exchange(self, send_planes, send_to, recv_planes, recv_from):
         """Post send/recv of contiguous planes; on CUDA the NCCL calls are enqueued on the side stream after
         everything already queued on the compute stream, so the interior kernels launched next overlap."""
@@ -232,53 +374,141 @@ class SlabFDTD:
         self._pending = []
 
     # ---- caller loop ----------------------------------------------------------------------------
+    def initialize_fields(self):
+        """fdtd.py:147-211 on every slab: zero state (and halo planes), t_index = 0.  A collective."""
+        be = self.be
+        for t in be.H + be.D:
+            t.zero_()
+        if be.is_cuda:
+            for fam in _PML_FAMILIES:
+                for t in be.pml[fam]:
+                    t.zero_()
+        else:
+            for arrs in be.I.values():
+                for arr in arrs:
+                    arr[...] = 0.0
+        for t in [x for x in (be.D_hi + be.H_lo) if x is not None]:
+            t.zero_()
+        if self.path == "peer":
+            if not self._in_process:
+                torch.cuda.current_stream(be.device).synchronize()
+                dist.barrier(group=self.group)        # no neighbour is still writing into this rank's block
+            _lib.check(be.plan.lib.cev_fdtd_halo_reset(be.plan.handle, be._s()))
+            if not self._in_process:
+                torch.cuda.current_stream(be.device).synchronize()
+                dist.barrier(group=self.group)
+        self.t_index = 0
+
     def prepare(self, sources=(), probes=()):
-        """sources [(comp, global profile)], probes [(field key, global mask)] -> local point sets."""
+        """sources [(comp, global profile)], probes [(field key, global mask)] -> local point sets.  Profiles / masks
+        are dense (Nx, Ny, Nz) arrays, or point lists {"ijk", "w", "Ny", "Nz"} on grids too large for dense masks."""
         plane = self.Ny * self.Nz
-        src = [(_COMP[c],) + localize_points(p, self.lo, self.hi, plane) for c, p in sources]
+        src = [(_COMP[s[0]],) + localize_points(s[1], self.lo, self.hi, plane) for s in sources]
         prb = [(_FIELD_CODE[k],) + localize_points(m, self.lo, self.hi, plane) for k, m in probes]
         self.be.set_points(src, prb)
         self.n_probes = len(probes)
+        self.n_sources = len(sources)
 
-    def run(self, steps, waveforms):
-        """`steps` leap-frog steps; waveforms [steps, n_sources].  Returns the probe series
-        [steps, n_probes] summed over ranks (identical on every rank)."""
+    def run(self, steps, sources=None, probes=None, waveforms=None):
+        """`steps` leap-frog steps (the loop of ceviche/utils.py:325-331 on every slab).  Same arguments as the
+        single-GPU `fdtd.run`: sources [(component, profile[, waveform])] / probes [(field key, mask)] (None = keep
+        the prepared ones), waveforms [steps, n_sources].  Returns the probe series [steps, n_probes] summed over
+        ranks (identical on every rank).  A collective: every rank calls it with the same arguments."""
+        if sources is not None and not isinstance(sources, (list, tuple)):      # run(steps, waveforms): the older call
+            sources, waveforms = None, sources
+        steps = int(steps)
+        if sources is not None or probes is not None:
+            if sources is None or probes is None:
+                raise ValueError("run(): give sources and probes together (or prepare() them once)")
+            self.prepare(sources, probes)
+            if waveforms is None:
+                waveforms = (np.stack([np.asarray(s_[2], dtype=np.float64)[:steps] for s_ in sources], axis=1)
+                             if len(sources) else np.zeros((steps, 0)))
         be, nx, P = self.be, self.nx, self.P
+        if waveforms is None:
+            if getattr(self, "n_sources", 0):
+                raise ValueError("run(): prepared sources need `waveforms` [steps, n_sources]")
+            waveforms = np.zeros((steps, 0))
         wf = torch.as_tensor(np.ascontiguousarray(waveforms, dtype=np.float64)) if not torch.is_tensor(waveforms) else waveforms.double().contiguous()
         if be.is_cuda:
             wf = wf.to(be.device)
+        if tuple(wf.shape) != (steps, getattr(self, "n_sources", wf.shape[1] if wf.dim() == 2 else 0)):
+            raise ValueError("waveforms must have shape (steps, n_sources)")
         be.new_partials(steps)
-        for n in range(steps):
-            # ---- H half-step (fdtd.py:80-97): interior, then the plane that needs the right neighbour's D
-            if P > 1:
-                be.step_H(0, nx - 1, n - 1)
-                self._wait()
-                be.step_H(nx - 1, nx, -1)
-                self._exchange([be.H[1][nx - 1], be.H[2][nx - 1]], self.right, [be.H_lo[1], be.H_lo[2]], self.left)
-                # ---- D half-step (fdtd.py:105-127): interior, then the plane that needs the left neighbour's H
-                be.step_D(1, nx, n, wf[n])
-                self._wait()
-                be.step_D(0, 1, -1, wf[n])
-                self._exchange([be.D[1][0], be.D[2][0]], self.left, [be.D_hi[1], be.D_hi[2]], self.right)
-            else:
-                be.step_H(0, nx, n - 1)
-                be.step_D(0, nx, n, wf[n])
-        if steps > 0:
-            be.sample(0, steps - 1)
+        if self.path in ("peer", "none") and be.is_cuda:
+            be.run_c(steps, wf)                   # the time loop in C; peer path: halos travel inside the kernels
+        else:
+            for n in range(steps):
+                # ---- H half-step (fdtd.py:80-97): interior, then the plane that needs the right neighbour's D
+                if P > 1:
+                    be.step_H(0, nx - 1, n - 1)
+                    self._wait()
+                    be.step_H(nx - 1, nx, -1)
+                    self._exchange([be.H[1][nx - 1], be.H[2][nx - 1]], self.right, [be.H_lo[1], be.H_lo[2]], self.left)
+                    # ---- D half-step (fdtd.py:105-127): interior, then the plane that needs the left neighbour's H
+                    be.step_D(1, nx, n, wf[n])
+                    self._wait()
+                    be.step_D(0, 1, -1, wf[n])
+                    self._exchange([be.D[1][0], be.D[2][0]], self.left, [be.D_hi[1], be.D_hi[2]], self.right)
+                else:
+                    be.step_H(0, nx, n - 1)
+                    be.step_D(0, nx, n, wf[n])
+            if steps > 0:
+                be.sample(0, steps - 1)
         self.t_index += steps
         series = be.series()
-        if P > 1:
-            self._wait()     # leave no message in flight; the D halo is in place for a following run()
-            self._pending_none = True
+        if P > 1 and not self._in_process:
+            if self.path == "nccl":
+                self._wait()     # leave no message in flight; the D halo is in place for a following run()
             if self.n_probes:
                 dist.all_reduce(series, group=self.group)
+            if self.path == "peer":
+                self._peer_check()
         return series
+
+    def forward(self, Jx=None, Jy=None, Jz=None):
+        """One time step with dense GLOBAL J arrays (the reference's per-step call, fdtd.py:74-144), for API
+        compatibility on small grids: J is re-uploaded as a sparse source set on every call (use run() for time
+        loops).  Returns `fields` (gathers lazily)."""
+        srcs = []
+        for comp, J in zip("xyz", (Jx, Jy, Jz)):
+            if J is None:
+                continue
+            J = J.detach().cpu().numpy() if torch.is_tensor(J) else np.asarray(J, dtype=np.float64)
+            J = np.broadcast_to(J.reshape(J.shape + (1,) * (3 - J.ndim)) if J.ndim else J, self.global_shape)
+            srcs.append((comp, J, np.ones(1)))
+        keep = getattr(self, "_probe_spec", None)
+        self.prepare([(c, p) for c, p, _ in srcs], [])
+        self.run(1, waveforms=np.ones((1, len(srcs))))
+        self._sources_stale = True
+        del keep
+        return self.fields
+
+    def time_local_step_H(self, reps=20):
+        """CUDA-event time (ms) of the H half-step over this rank's whole slab, halos paused (periodic wrap inside
+        the slab: the same work, no neighbour involved)."""
+        be = self.be
+        if self.path == "peer":
+            self.set_option("halo_pause", 1)
+        be.new_partials(1)
+        for _ in range(3):
+            be.step_H(0, be.nx, -1)
+        torch.cuda.synchronize(be.device)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            be.step_H(0, be.nx, -1)
+        b.record()
+        torch.cuda.synchronize(be.device)
+        if self.path == "peer":
+            self.set_option("halo_pause", 0)
+        return a.elapsed_time(b) / reps
 
     def gather(self, key):
         """Full field on every rank (tests / small grids only)."""
         loc = self.be.field(key)
         loc = loc if torch.is_tensor(loc) else torch.as_tensor(loc)
-        if self.P == 1:
+        if self.P == 1 or self._in_process:
             return loc
         sizes = [hi - lo for lo, hi in partition(self.Nx, self.P)]
         outs = [torch.empty((s, self.Ny, self.Nz), dtype=loc.dtype, device=loc.device) for s in sizes]
@@ -290,3 +520,24 @@ class SlabFDTD:
             if r == self.rank:
                 buf.copy_(loc)
             dist.broadcast(buf, src=r, group=self.group)
+
+
+def make_slab_fdtd(eps_r, dL, npml, *, devices, global_shape=None, dtype=torch.float64, device=None, arith=None,
+                   group=None, path=None):
+    """What `ceviche_b200.fdtd(eps_r, dL, npml, devices=[...])` builds: one SlabFDTD per process.  `devices` lists the
+    CUDA device of every slab in rank order (one process per GPU, torch.distributed initialised with that many ranks)."""
+    P = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if len(devices) != P:
+        raise ValueError("devices lists {} slabs but the process group has {} ranks (one process per GPU)".format(len(devices), P))
+    if device is None:
+        d = devices[rank]
+        device = torch.device("cuda", d) if isinstance(d, int) else torch.device(d)
+    if global_shape is None:
+        e = torch.as_tensor(np.asarray(eps_r, dtype=np.float64)) if not torch.is_tensor(eps_r) else eps_r
+        e = reshape_to_ND(e, 3)
+        global_shape = tuple(e.shape)
+        lo, hi = partition(global_shape[0], P)[rank]
+        idx = torch.arange(lo - 1, hi) % global_shape[0]
+        eps_r = e[idx.to(e.device)]
+    return SlabFDTD(global_shape, eps_r, dL, npml, dtype=dtype, device=device, group=group, path=path, arith=arith)

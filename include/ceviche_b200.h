@@ -109,7 +109,8 @@ int cev_fdtd_destroy(cev_fdtd* plan);
 
 /* Tuning / test knobs: "kernel_variant" 0 auto | 1 baseline (one thread per cell) | 2 marching | 3 TMA-staged |
  * 4 fused full-step kernel in cev_fdtd_run_fused | 5 hybrid there (lean fused kernel on the PML-free interior, the
- * half-step kernels on the PML shell); "fused_shape" 0 auto | lanes_z*100 + warps; "use_graph" / "jvp_streams" -1 auto | 0 | 1;
+ * half-step kernels on the PML shell); 6 tensor-map TMA kernels (cp.async.bulk.tensor box copies; "tma_rows" 4|8 tile rows, "tma_stages[_H|_D]" 3|4 ring
+ * depth, "auto_tensor_map" 0|1: let variant 0 pick them on large 3-D grids); "fused_shape" 0 auto | lanes_z*100 + warps; "use_graph" / "jvp_streams" -1 auto | 0 | 1;
  * "xchunk" x-planes per CTA of the marching kernels (0 = auto); "lanes_z" 8|16|32 lanes of a warp along z;
  * "prefetch_planes" L2 prefetch distance; "split_launch" 0|1 separate launches for the PML-free interior and
  * the PML shell.  Results do not depend on them (bit-identical).
@@ -189,6 +190,45 @@ int cev_fdtd_jvp_run(cev_fdtd* plan, const cev_state* st, int B, const cev_state
 int cev_fdtd_adjoint_step(cev_fdtd* plan, const cev_state* fwd, const cev_adjoint* adj, void* stream);
 int cev_fdtd_adjoint_seed(cev_fdtd* plan, const cev_state* fwd, const cev_adjoint* adj, const double* gbar_row,
                           void* stream);
+
+/* ---- x-slab decomposition over the GPUs of one box: halo planes through peer-mapped memory ----
+ * The reference has no parallel path (single-thread numpy); this is the multi-GPU boundary SURVEY 8(b) sketched as
+ * cev_fdtd_halo_ptrs.  The grid is cut into contiguous x-slabs, one plan per slab (nx = local planes).  A slab reads
+ * two halo planes per half-step: D_y, D_z (and the static 1/eps_y, 1/eps_z) of its RIGHT neighbour's first plane in
+ * the H half-step (curl_E, derivatives.py:16-22: forward differences) and H_y, H_z of its LEFT neighbour's last
+ * plane in the D half-step (curl_H, derivatives.py:24-30: backward differences); np.roll wraps, so the slabs form
+ * a ring.  Each slab owns an EXCHANGE BLOCK (cev_halo_layout) holding the planes it reads and two arrival counters;
+ * the neighbours store into it directly from inside their half-step kernels (NVLink peer stores by the CTAs that
+ * produce the boundary plane, followed by a system-scope release increment of the counter), and the CTAs that read
+ * a halo plane first wait for its counter: no extra launch, no collective.  The boundary x-chunks run first in each
+ * launch, so a halo has a whole half-step to arrive.  One process per GPU: the block is shared by CUDA IPC.
+ *   cev_halo_alloc / cev_halo_free     this slab's block (zeroed) + its 64-byte IPC handle
+ *   cev_halo_open / cev_halo_close     map a neighbour's block into this process (peer access is enabled lazily)
+ *   cev_fdtd_halo_attach(plan, own, left, right)   from now on cev_fdtd_run / the in-place whole-slab half-steps of
+ *        this plan use the blocks (cev_state's *_xhi / *_xlo members are ignored); (NULL, NULL, NULL) detaches.
+ *        Every slab must issue the same sequence of half-steps.  A 2-slab ring passes the same block as left and right.
+ *   cev_fdtd_halo_push_static   copy this slab's first plane of 1/eps_y, 1/eps_z to the left neighbour (once per eps_r)
+ *   cev_fdtd_halo_reset         zero the field halo planes of this slab's own block (with initialize_fields)
+ *   cev_fdtd_halo_error         1 if a halo wait timed out (a neighbour never arrived) since the block was allocated */
+#define CEV_IPC_HANDLE_BYTES 64
+typedef struct cev_halo_layout {
+    size_t bytes;               /* size of an exchange block */
+    size_t plane_bytes;
+    size_t D_hi[2];             /* byte offsets: D_y, D_z of the plane at local i = nx */
+    size_t inv_eps_hi[2];
+    size_t H_lo[2];             /* H_y, H_z of the plane at local i = -1 */
+    size_t flag_D, flag_H;      /* uint64 arrival counters of the D / H halo planes */
+    size_t err;                 /* int32 */
+} cev_halo_layout;
+int cev_fdtd_halo_layout(const cev_fdtd* plan, cev_halo_layout* layout);
+int cev_halo_alloc(int device, size_t bytes, void** block, unsigned char ipc_handle[CEV_IPC_HANDLE_BYTES]);
+int cev_halo_open(int device, const unsigned char ipc_handle[CEV_IPC_HANDLE_BYTES], void** block);
+int cev_halo_close(int device, void* block);
+int cev_halo_free(int device, void* block);
+int cev_fdtd_halo_attach(cev_fdtd* plan, void* own_block, void* left_block, void* right_block);
+int cev_fdtd_halo_push_static(cev_fdtd* plan, const cev_state* st, void* stream);
+int cev_fdtd_halo_reset(cev_fdtd* plan, void* stream);
+int cev_fdtd_halo_error(cev_fdtd* plan, int* err);
 
 #ifdef __cplusplus
 }

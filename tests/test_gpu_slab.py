@@ -22,7 +22,7 @@ def _case(shape, npml, steps, seed):
     return dict(eps=eps, dL=cases.DL, npml=list(npml), steps=steps, sources=src, probes=probes)
 
 
-def _worker(rank, world, port, shape, npml, steps, seed, dtype_name, out):
+def _worker(rank, world, port, shape, npml, steps, seed, dtype_name, out, path):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"       # (NCCL bootstrap); the store is a file: no port to collide on
@@ -30,17 +30,23 @@ def _worker(rank, world, port, shape, npml, steps, seed, dtype_name, out):
     dist.init_process_group("nccl", init_method="file://" + port, rank=rank, world_size=world,
                             device_id=torch.device("cuda", rank))
     try:
-        from ceviche_b200.slab import SlabFDTD, partition
+        import ceviche_b200
         case = _case(shape, npml, steps, seed)
-        lo, hi = partition(shape[0], world)[rank]
-        eps = case["eps"]
-        eps_local = np.concatenate([eps[(lo - 1) % shape[0]][None], eps[lo:hi]], 0)
-        sim = SlabFDTD(shape, eps_local, case["dL"], case["npml"], dtype=getattr(torch, dtype_name), device="cuda:%d" % rank)
-        sim.prepare([(c, p) for c, p, _ in case["sources"]], case["probes"])
+        # the reference's constructor with the one extra keyword: every rank passes the GLOBAL permittivity
+        sim = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"], dtype=getattr(torch, dtype_name),
+                                devices=list(range(world)), path=path)
+        assert sim.path == (path or sim.path) and sim.grid_shape == tuple(shape) and sim.t_index == 0
         wf = np.stack([w for _, _, w in case["sources"]], 1)
         half = steps // 2
-        series = torch.cat([sim.run(half, wf[:half]), sim.run(steps - half, wf[half:])]).cpu().numpy()
-        fields = {k: sim.gather(k).cpu().numpy() for k in ("Ex", "Ey", "Ez", "Dx", "Dy", "Dz", "Hx", "Hy", "Hz")}
+        s1 = sim.run(half, [(c, p) for c, p, _ in case["sources"]], case["probes"], waveforms=wf[:half])
+        s2 = sim.run(steps - half, waveforms=wf[half:])          # prepared sources / probes are kept
+        series = torch.cat([s1, s2]).cpu().numpy()
+        assert sim.t_index == steps
+        fields = {k: sim.fields[k].cpu().numpy() for k in ("Ex", "Ey", "Ez", "Dx", "Dy", "Dz", "Hx", "Hy", "Hz")}
+        # a reset and the same run again on the same object
+        sim.initialize_fields()
+        s3 = sim.run(steps, waveforms=wf).cpu().numpy()
+        assert np.array_equal(s3, series), "second run after initialize_fields() differs"
         if rank == 0:
             np.savez(out, series=series, **fields)
     finally:
@@ -54,18 +60,22 @@ def _rendezvous(tmp_path):
 
 
 @pytest.mark.parametrize("dtype_name", ["float64", "float32"])
-@pytest.mark.parametrize("shape,npml", [((24, 20, 72), (4, 3, 6)), ((14, 9, 40), (0, 2, 3)),
-                                        ((40, 64, 1), (5, 6, 0)),        # a 2-D grid (relabelled x, z, y)
-                                        ((256, 128, 64), (20, 20, 20))]) # the parity grid of BASELINE config 3
-def test_slabs_bit_identical_to_single_gpu(shape, npml, dtype_name, tmp_path):
+@pytest.mark.parametrize("shape,npml,path", [((24, 20, 72), (4, 3, 6), "nccl"), ((14, 9, 40), (0, 2, 3), "nccl"),
+                                             ((40, 64, 1), (5, 6, 0), "nccl"),        # a 2-D grid (relabelled x, z, y)
+                                             ((256, 128, 64), (20, 20, 20), "nccl"),  # the parity grid of BASELINE config 3
+                                             ((256, 128, 64), (20, 20, 20), None),    # ... on the default path (peer memory in fp64)
+                                             ((64, 32, 136), (6, 5, 7), "peer"), ((256, 128, 128), (20, 20, 20), "peer")])
+def test_slabs_bit_identical_to_single_gpu(shape, npml, path, dtype_name, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     import torch.multiprocessing as mp
     import ceviche_b200
-    world = min(torch.cuda.device_count(), 4)
+    world = torch.cuda.device_count()            # every GPU of the box: 2, 4 or 8 slabs
+    while shape[0] // world < 2:
+        world //= 2
     steps, seed = 30, 11
     out = str(tmp_path / "slab.npz")
-    mp.spawn(_worker, args=(world, _rendezvous(tmp_path), shape, npml, steps, seed, dtype_name, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _rendezvous(tmp_path), shape, npml, steps, seed, dtype_name, out, path), nprocs=world, join=True)
     got = np.load(out)
     case = _case(shape, npml, steps, seed)
     F = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"], dtype=getattr(torch, dtype_name))
