@@ -31,7 +31,7 @@ class cev_tangent(C.Structure):
 
 
 class cev_adjoint(C.Structure):
-    _fields_ = [(n, c_void_p3) for n in ("lH", "lD", "lICE", "lIH", "lICH", "lID", "gC", "gC2", "G_mE")]
+    _fields_ = [(n, c_void_p3) for n in ("lH", "lD", "lICE", "lIH", "lICH", "lID", "gC2", "G_mE")] + [("g_box", C.c_int64 * 6)]
 
 
 class cev_halo_layout(C.Structure):
@@ -69,6 +69,7 @@ def _declare(lib):
                              C.c_void_p, C.c_void_p, C.c_void_p],
         "cev_fdtd_adjoint_step": [C.c_void_p, P(cev_state), P(cev_adjoint), C.c_void_p],
         "cev_fdtd_adjoint_seed": [C.c_void_p, P(cev_state), P(cev_adjoint), C.c_void_p, C.c_void_p],
+        "cev_fdtd_adjoint_run": [C.c_void_p, P(cev_state), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, P(cev_adjoint), C.c_void_p],
         "cev_fdtd_set_sources": [C.c_void_p, C.c_int, P(cev_points)],
         "cev_fdtd_set_probes": [C.c_void_p, C.c_int, P(cev_points), P(C.c_int64)],
         "cev_fdtd_probe_slots": [C.c_void_p, P(C.c_int32)],
@@ -97,7 +98,7 @@ EXPORTS = ("cev_last_error", "cev_abi_version", "cev_fdtd_create", "cev_fdtd_des
            "cev_fdtd_set_option",
            "cev_fdtd_step_H", "cev_fdtd_step_D", "cev_fdtd_compute_E", "cev_fdtd_set_sources",
            "cev_fdtd_set_probes", "cev_fdtd_probe_slots", "cev_fdtd_set_monitors", "cev_fdtd_bind_monitors", "cev_fdtd_run", "cev_fdtd_run_fused", "cev_fdtd_step_H_ex", "cev_fdtd_step_D_ex",
-           "cev_fdtd_sample_probes", "cev_fdtd_jvp_run", "cev_fdtd_adjoint_step", "cev_fdtd_adjoint_seed",
+           "cev_fdtd_sample_probes", "cev_fdtd_jvp_run", "cev_fdtd_adjoint_step", "cev_fdtd_adjoint_seed", "cev_fdtd_adjoint_run",
            "cev_fdtd_halo_layout", "cev_halo_alloc", "cev_halo_open", "cev_halo_close", "cev_halo_free",
            "cev_fdtd_halo_attach", "cev_fdtd_halo_push_static", "cev_fdtd_halo_reset", "cev_fdtd_halo_error")
 

@@ -52,12 +52,32 @@ def _state(H, D, mE, pml):
     return st
 
 
-def _adjoint(lH, lD, lpml, gC, gC2, G):
+def _adjoint(lH, lD, lpml, gC2, G, box=None):
     adj = _lib.cev_adjoint()
-    adj.lH, adj.lD, adj.gC, adj.gC2, adj.G_mE = _p3(lH), _p3(lD), _p3(gC), _p3(gC2), _p3(G)
+    adj.lH, adj.lD, adj.gC2, adj.G_mE = _p3(lH), _p3(lD), _p3(gC2), _p3(G)
     for f, fam in enumerate(_FAMS):
         setattr(adj, "l" + fam, _p3(lpml[3 * f:3 * f + 3]))
+    if box is not None:
+        adj.g_box = (C.c_int64 * 6)(*[int(v) for pair in box for v in pair])
     return adj
+
+
+def _grad_box(sim):
+    """The box of 1/eps_yee cells whose G_mE the design region needs: eps_r[i,j,k] enters eps_xx at (i,j,k) and
+    (i+1,j,k) etc. (utils.py:167-174), so one more cell on the high side of every axis; None = the whole grid (also
+    when the +1 would wrap)."""
+    region = getattr(sim, "design_region", None)
+    if region is None:
+        return None
+    box = []
+    for (lo, hi), n in zip(region, sim.grid_shape):
+        lo, hi = int(lo), int(hi)
+        if not (0 <= lo < hi <= n):
+            raise ValueError("design_region {} outside the grid {}".format(region, sim.grid_shape))
+        if hi + 1 > n:
+            return None
+        box.append((lo, hi + 1))
+    return box
 
 
 def _flat_pml(sim):
@@ -143,10 +163,9 @@ class _StepFn(torch.autograd.Function):
                     gD[c] += mE[c] * gE[c]
                     G[c] += gE[c].double() * D_out[c].double()
             gJ = [gD[c].clone() if ctx.has_J[c] else None for c in range(3)]   # D' = ... + J
-            gC = [z(D_in[c]) for c in range(3)]
-            gC2 = [z(D_in[c]) for c in range(3)]
+            gC2 = [torch.empty_like(D_in[c]) for c in range(3)]
             fwd = _state(D_in, D_in, mE, [None] * 12)      # only inv_eps and D (= D before the step) are read
-            adj = _adjoint(gH, gD, gp, gC, gC2, G)
+            adj = _adjoint(gH, gD, gp, gC2, G)
             _lib.check(plan.lib.cev_fdtd_adjoint_step(plan.handle, C.byref(fwd), C.byref(adj), sim._stream()))
         grads_J = [g if g is not None else None for g in gJ]
         return (None, *G, *gH, *gD, *grads_J, *gp)
@@ -193,34 +212,28 @@ class _RunFn(torch.autograd.Function):
         with torch.cuda.device(sim.device):
             gbar = gbar.detach().to(torch.float64).contiguous()
             zf = lambda: [torch.zeros(sim.grid_shape, dtype=sim.dtype, device=sim.device) for _ in range(3)]
-            lH, lD, gC, gC2 = zf(), zf(), zf(), zf()
+            lH, lD = zf(), zf()
+            gC2 = [torch.empty(sim.grid_shape, dtype=sim.dtype, device=sim.device) for _ in range(3)]
             lp = [torch.zeros(shapes[q], dtype=sim.dtype, device=sim.device) for q in range(12)]
             G = [torch.zeros(sim.grid_shape, dtype=torch.float64, device=sim.device) for _ in range(3)]
-            adj = _adjoint(lH, lD, lp, gC, gC2, G)
+            adj = _adjoint(lH, lD, lp, gC2, G, _grad_box(sim))
+            # D after every step of a segment (the only forward quantity the transposed step needs: the step is linear
+            # in the state): one ring of slots for the whole sweep, written straight by the out-of-place D half-steps
+            longest = max(t1 - t0 for t0, t1, *_ in ctx.checkpoints)
+            hist = torch.empty((longest + 1, 3) + tuple(sim.grid_shape), dtype=sim.dtype, device=sim.device)
+            slots = (_lib.c_void_p3 * (longest + 1))(*[_p3(list(hist[k])) for k in range(longest + 1)])
             for t0, t1, H0, D0, P0 in reversed(ctx.checkpoints):
-                # recompute the segment, keeping D after every step (the only forward quantity the
-                # transposed step needs: the step is linear in the state)
-                H = [t.clone() for t in H0]
-                P = [t.clone() for t in P0]
-                # D after every step of the segment: the D half-step writes each new D straight into its history slot
-                # (out of place), so no per-step copies are made
-                hist = [[t.clone() for t in D0]]
-                for t in range(t0, t1):
-                    st = _state(H, hist[-1], ctx.mE, P)
-                    Dn = [torch.empty_like(x) for x in D0]
-                    _lib.check(lib.cev_fdtd_step_H_ex(h, C.byref(st), None, None, 0, sim.Nx, -1, None, s))
-                    _lib.check(lib.cev_fdtd_step_D_ex(h, C.byref(st), _p3(Dn), None, None, None,
-                                                      _ptr(ctx.waveforms[t:t + 1]) if sim._n_sources else None,
-                                                      0, sim.Nx, -1, None, s))
-                    hist.append(Dn)
-                for t in range(t1, t0, -1):          # step number t (1-based in the segment's frame)
-                    k = t - t0
-                    if ctx.n_probes:
-                        fwd = _state(hist[k], hist[k], ctx.mE, [None] * 12)
-                        _lib.check(lib.cev_fdtd_adjoint_seed(h, C.byref(fwd), C.byref(adj), _ptr(gbar[t - 1]), s))
-                    fwd = _state(hist[k - 1], hist[k - 1], ctx.mE, [None] * 12)
-                    _lib.check(lib.cev_fdtd_adjoint_step(h, C.byref(fwd), C.byref(adj), s))
-                del hist
+                # one C call per checkpoint segment: recompute + transposed steps (cev_fdtd_adjoint_run); the recomputation
+                # advances H and the PML integrals it is given in place
+                for c in range(3):
+                    hist[0, c].copy_(D0[c])
+                # (H and the integrals are cloned: a second backward() finds the checkpoints intact)
+                Hs, Ps = [t.clone() for t in H0], [t.clone() for t in P0]
+                st = _state(Hs, D0, ctx.mE, Ps)
+                _lib.check(lib.cev_fdtd_adjoint_run(h, C.byref(st), t1 - t0,
+                                                    _ptr(ctx.waveforms[t0:t1]) if sim._n_sources else None,
+                                                    _ptr(gbar[t0:t1]) if ctx.n_probes else None, slots, C.byref(adj), s))
+            del hist
         sim._apply_active(sim._active)
         return (None, None, None, None, *G)
 

@@ -218,7 +218,12 @@ __global__ void k_adj_seed(const AdjArgs<T, AT> a, ProbeTable pr, const int32_t*
         const double gw = g * pr.weight[wb + q];
         if (field < 3) {
             atomicAdd(&a.lD[c][cell], (T)((double)a.mE[c][cell] * gw));
-            if (a.G[c]) atomicAdd(&a.G[c][cell], gw * (double)Dn[cell]);
+            if (a.G[c]) {
+                const int64_t pl = (int64_t)a.Ny * a.Nz;
+                const int ci = (int)(cell / pl), cj = (int)((cell % pl) / a.Nz), ck = (int)(cell % a.Nz);
+                if (ci >= a.gb[0] && ci < a.gb[1] && cj >= a.gb[2] && cj < a.gb[3] && ck >= a.gb[4] && ck < a.gb[5])
+                    atomicAdd(&a.G[c][cell], gw * (double)Dn[cell]);
+            }
         } else if (field < 6) {
             atomicAdd(&a.lD[c][cell], (T)gw);
         } else {

@@ -1175,13 +1175,12 @@ int fill_adj(const cev_fdtd* p, const cev_state* fwd, const cev_adjoint* adj, Ad
         a.lIH[A] = (T*)adj->lIH[L];
         a.lICH[A] = (T*)adj->lICH[L];
         a.lID[A] = (T*)adj->lID[L];
-        a.gC[A] = (T*)adj->gC[L];
         a.gC2[A] = (T*)adj->gC2[L];
         a.G[A] = adj->G_mE[L];
         a.mE[A] = (const T*)fwd->inv_eps[L];
         a.Dprev[A] = (const T*)fwd->D[L];
-        if (!a.lH[A] || !a.lD[A] || !a.gC[A] || !a.gC2[A] || !a.mE[A] || !a.Dprev[A])
-            return fail("cev_adjoint: lH, lD, gC, gC2 and the forward inv_eps / D must be non-NULL");
+        if (!a.lH[A] || !a.lD[A] || !a.gC2[A] || !a.mE[A] || !a.Dprev[A])
+            return fail("cev_adjoint: lH, lD, gC2 and the forward inv_eps / D must be non-NULL");
         const int Bx = (A + 1) % 3, C = (A + 2) % 3;
         if (p->nH[A] > 0 && !a.lICE[A]) return fail("cev_adjoint: lICE missing for a PML axis");
         if (p->nD[A] > 0 && !a.lICH[A]) return fail("cev_adjoint: lICH missing for a PML axis");
@@ -1198,6 +1197,16 @@ int fill_adj(const cev_fdtd* p, const cev_state* fwd, const cev_adjoint* adj, Ad
     }
     a.cdt = (AT)(p->parity * p->cdt);
     a.inv_dL = (AT)(1.0 / p->dL);
+    // design box (logical x0, x1, y0, y1, z0, z1; all zero = the whole grid) in internal axis order
+    bool whole = true;
+    for (int q = 0; q < 6; ++q) whole = whole && adj->g_box[q] == 0;
+    for (int A = 0; A < 3; ++A) {
+        const int L = p->to_logical(A);
+        const int64_t lo = whole ? 0 : adj->g_box[2 * L], hi = whole ? p->Nl[L] : adj->g_box[2 * L + 1];
+        if (lo < 0 || hi > p->Nl[L] || lo > hi) return fail("cev_adjoint: g_box outside the grid");
+        a.gb[2 * A] = (int)lo;
+        a.gb[2 * A + 1] = (int)hi;
+    }
     return 0;
 }
 
@@ -1208,9 +1217,8 @@ int launch_adjoint_step(cev_fdtd* p, const cev_state* fwd, const cev_adjoint* ad
     const dim3 blk(64, 4);
     const dim3 grd((a.Nz + 63) / 64, (a.Ny + 3) / 4, a.Nx);
     if (grd.y > 65535 || grd.z > 65535) return fail("adjoint kernels: grid extent too large");
-    k_adj_D<T, AT><<<grd, blk, 0, s>>>(a);
     k_adj_H<T, AT><<<grd, blk, 0, s>>>(a);
-    k_adj_E<T, AT><<<grd, blk, 0, s>>>(a);
+    k_adj_ED<T, AT><<<grd, blk, 0, s>>>(a);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -1224,6 +1232,35 @@ int launch_adjoint_seed(cev_fdtd* p, const cev_state* fwd, const cev_adjoint* ad
     fill_probe_table(p, pr);
     k_adj_seed<T, AT><<<p->n_slots, 128, 0, s>>>(a, pr, (const int32_t*)p->pr_owner.p, gbar_row, a.Dprev[0], a.Dprev[1], a.Dprev[2]);
     CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// One checkpoint segment of the reverse sweep, entirely on the device queue: recompute the forward steps from the
+// segment's start state keeping D after every step (hist[k] = D after k steps; hist[0] is the start D), then the
+// transposed steps in reverse order, each preceded by the probe-series seeds of its time step.
+template <typename T, typename AT>
+int adjoint_run(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* waveform, const double* gbar,
+                void* const (*hist)[3], const cev_adjoint* adj, cudaStream_t s) {
+    const int64_t Nx = p->N[0];
+    cev_state cur = *st;
+    for (int64_t k = 1; k <= nsteps; ++k) {
+        for (int c = 0; c < 3; ++c) cur.D[c] = hist[k - 1][c];
+        if (launch_H<T, AT>(p, &cur, nullptr, nullptr, 0, Nx, -1, nullptr, s)) return -1;
+        if (launch_D<T, AT>(p, &cur, hist[k], nullptr, nullptr, nullptr, nullptr,
+                            waveform ? waveform + (k - 1) * p->nsrc : nullptr, 0, Nx, -1, nullptr, s))
+            return -1;
+    }
+    cev_state fwd;
+    memset(&fwd, 0, sizeof fwd);
+    for (int c = 0; c < 3; ++c) fwd.inv_eps[c] = st->inv_eps[c];
+    for (int64_t k = nsteps; k >= 1; --k) {
+        if (gbar && p->n_slots > 0) {
+            for (int c = 0; c < 3; ++c) fwd.D[c] = hist[k][c];
+            if (launch_adjoint_seed<T, AT>(p, &fwd, adj, gbar + (k - 1) * p->nprobe, s)) return -1;
+        }
+        for (int c = 0; c < 3; ++c) fwd.D[c] = hist[k - 1][c];
+        if (launch_adjoint_step<T, AT>(p, &fwd, adj, s)) return -1;
+    }
     return 0;
 }
 
@@ -1526,6 +1563,21 @@ int cev_fdtd_adjoint_step(cev_fdtd* p, const cev_state* fwd, const cev_adjoint* 
     if (!p || !fwd || !adj) return fail("NULL argument");
     DeviceGuard guard(p->device);
     return DISPATCH(p, launch_adjoint_step, p, fwd, adj, (cudaStream_t)stream);
+}
+
+int cev_fdtd_adjoint_run(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* waveform, const double* gbar,
+                         void* const (*D_hist)[3], const cev_adjoint* adj, void* stream) {
+    if (!p || !st || !D_hist || !adj) return fail("NULL argument");
+    if (nsteps < 0) return fail("nsteps must be >= 0");
+    if (nsteps == 0) return 0;
+    if (p->n_src_pts > 0 && !waveform) return fail("plan has sources but waveform is NULL");
+    if (st->D_xhi[1] || st->D_xhi[2] || st->H_xlo[1] || st->H_xlo[2] || p->halo.on())
+        return fail("cev_fdtd_adjoint_run steps a whole (periodic) grid");
+    for (int64_t k = 0; k <= nsteps; ++k)
+        for (int c = 0; c < 3; ++c)
+            if (!D_hist[k][c]) return fail("D_hist needs nsteps + 1 slots of three arrays");
+    DeviceGuard guard(p->device);
+    return DISPATCH(p, adjoint_run, p, st, nsteps, p->n_src_pts > 0 ? waveform : nullptr, gbar, D_hist, adj, (cudaStream_t)stream);
 }
 
 int cev_fdtd_adjoint_seed(cev_fdtd* p, const cev_state* fwd, const cev_adjoint* adj, const double* gbar_row, void* stream) {

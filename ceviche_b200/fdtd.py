@@ -151,6 +151,9 @@ class fdtd:
         self._fused_step = True
         # skip field components that are provably zero (2-D TM / TE, 1-D): see coupled_components()
         self.specialise_components = True
+        # ((x0, x1), (y0, y1), (z0, z1)) or None: reverse-mode gradients w.r.t. eps_r are only wanted inside this box
+        # (the region being optimised); outside it the adjoint sweep skips the dL/d(1/eps) accumulation and returns 0
+        self.design_region = None
 
         eps_r = self._as_eps(eps_r, pad=True)
         self.Nx, self.Ny, self.Nz = self.grid_shape = tuple(eps_r.shape)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CEV_ABI_VERSION 1
+#define CEV_ABI_VERSION 2
 #define CEV_F32 0
 #define CEV_F64 1
 
@@ -80,8 +80,10 @@ typedef struct cev_tangent {
     const void* D_primal[3];
 } cev_tangent;
 
-/* Cotangent state of the reverse sweep (same layouts as cev_state: compact PML arrays), two scratch
- * vector fields, and the fp64 accumulators of dL/d(inv_eps).  G_mE entries may be NULL (not wanted). */
+/* Cotangent state of the reverse sweep (same layouts as cev_state: compact PML arrays), one scratch
+ * vector field, and the fp64 accumulators of dL/d(inv_eps).  G_mE entries may be NULL (not wanted).
+ * g_box = {x0, x1, y0, y1, z0, z1}: G_mE is only accumulated for cells inside this box (the design region; eps_r
+ * of cell (i,j,k) needs G_mE at (i,j,k), (i+1,j,k), (i,j+1,k), (i,j,k+1): utils.py:167-174); all zeros = whole grid. */
 typedef struct cev_adjoint {
     void*   lH[3];
     void*   lD[3];
@@ -89,9 +91,9 @@ typedef struct cev_adjoint {
     void*   lIH[3];
     void*   lICH[3];
     void*   lID[3];
-    void*   gC[3];
     void*   gC2[3];
     double* G_mE[3];
+    int64_t g_box[6];
 } cev_adjoint;
 
 const char* cev_last_error(void);
@@ -188,6 +190,14 @@ int cev_fdtd_jvp_run(cev_fdtd* plan, const cev_state* st, int B, const cev_state
  * cotangents of the state after step n-1 and G_mE has gained step n's term.  cev_fdtd_adjoint_seed adds
  * the probe-series cotangents gbar_row[n_probes] (device) of one step; there fwd->D is D after THAT step. */
 int cev_fdtd_adjoint_step(cev_fdtd* plan, const cev_state* fwd, const cev_adjoint* adj, void* stream);
+/* One checkpoint segment of the reverse sweep of a run, on the device queue (cev_fdtd_adjoint_run).
+ * st = the forward state at the START of the segment (H and the PML integrals are advanced in place by the
+ * recomputation: pass scratch copies; st->D is ignored).  D_hist = nsteps + 1 caller-owned slots of three full-grid
+ * arrays: slot 0 must hold D at the start of the segment, slot k receives D after k steps.  waveform / gbar: the
+ * segment's nsteps rows ([nsteps, n_sources] / [nsteps, n_probes], device; gbar nullable).  On return adj holds the
+ * cotangents of the state at the start of the segment and G_mE has gained the segment's terms. */
+int cev_fdtd_adjoint_run(cev_fdtd* plan, const cev_state* st, int64_t nsteps, const double* waveform, const double* gbar,
+                         void* const (*D_hist)[3], const cev_adjoint* adj, void* stream);
 int cev_fdtd_adjoint_seed(cev_fdtd* plan, const cev_state* fwd, const cev_adjoint* adj, const double* gbar_row,
                           void* stream);
 

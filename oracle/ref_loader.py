@@ -8,9 +8,11 @@ derivatives / fdtd by file path under a synthetic ``ceviche`` package
 (``ceviche/__init__.py`` is NOT executed: it would pull in the FDFD modules,
 which need the real autograd).
 
-Only usable where /root/reference exists (the build container).  It never
-travels to the GPU box; tests that need it skip there and rely on
-``tests/golden/`` instead.
+Where it loads from: /root/reference/ceviche in the build container; else ``oracle/_ref/ceviche`` -- UNMODIFIED
+copies of the four files (+ LICENSE) that ``__graft_entry__.build()`` makes where /root/reference exists.  That
+directory is git-ignored (never part of the repository's history) but travels with the gpurun snapshot, so that
+``bench.py --impl reference`` can time the reference's own code on the GPU box's host cores.  Tests that need the
+reference skip where neither exists and rely on ``tests/golden/`` instead.
 """
 import importlib.util
 import os
@@ -18,11 +20,38 @@ import sys
 import types
 import warnings
 
-REFERENCE_DIR = os.environ.get("CEVICHE_REFERENCE_DIR", "/root/reference/ceviche")
+VENDORED_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "ceviche")
+FILES = ("constants.py", "utils.py", "derivatives.py", "fdtd.py")
+
+
+def _find():
+    for d in (os.environ.get("CEVICHE_REFERENCE_DIR"), "/root/reference/ceviche", VENDORED_DIR):
+        if d and all(os.path.isfile(os.path.join(d, f)) for f in FILES):
+            return d
+    return os.environ.get("CEVICHE_REFERENCE_DIR") or "/root/reference/ceviche"
+
+
+REFERENCE_DIR = _find()
 
 
 def available():
-    return os.path.isfile(os.path.join(REFERENCE_DIR, "fdtd.py"))
+    return all(os.path.isfile(os.path.join(REFERENCE_DIR, f)) for f in FILES)
+
+
+def vendor(src="/root/reference"):
+    """Copy the reference's four FDTD files and its licence, unmodified, into git-ignored oracle/_ref/ (called by
+    __graft_entry__.build() in the build container).  Returns the directory, or None when there is no reference."""
+    import shutil
+    pkg = os.path.join(src, "ceviche")
+    if not all(os.path.isfile(os.path.join(pkg, f)) for f in FILES):
+        return None
+    os.makedirs(VENDORED_DIR, exist_ok=True)
+    for f in FILES:
+        shutil.copyfile(os.path.join(pkg, f), os.path.join(VENDORED_DIR, f))
+    for lic in ("LICENSE", "LICENSE.md", "LICENSE.txt"):
+        if os.path.isfile(os.path.join(src, lic)):
+            shutil.copyfile(os.path.join(src, lic), os.path.join(os.path.dirname(VENDORED_DIR), lic))
+    return VENDORED_DIR
 
 
 def load():
