@@ -31,7 +31,7 @@ class cev_tangent(C.Structure):
 
 
 class cev_adjoint(C.Structure):
-    _fields_ = [(n, c_void_p3) for n in ("lH", "lD", "lICE", "lIH", "lICH", "lID", "gC2", "G_mE")] + [("g_box", C.c_int64 * 6)]
+    _fields_ = [(n, c_void_p3) for n in ("lH", "lD", "lICE", "lIH", "lICH", "lID", "gC2", "G_mE")] + [("g_box", C.c_int64 * 6), ("gC", c_void_p3)]
 
 
 class cev_halo_layout(C.Structure):

@@ -52,9 +52,11 @@ def _state(H, D, mE, pml):
     return st
 
 
-def _adjoint(lH, lD, lpml, gC2, G, box=None):
+def _adjoint(lH, lD, lpml, gC2, G, box=None, gC=None):
     adj = _lib.cev_adjoint()
     adj.lH, adj.lD, adj.gC2, adj.G_mE = _p3(lH), _p3(lD), _p3(gC2), _p3(G)
+    if gC is not None:
+        adj.gC = _p3(gC)
     for f, fam in enumerate(_FAMS):
         setattr(adj, "l" + fam, _p3(lpml[3 * f:3 * f + 3]))
     if box is not None:
@@ -214,9 +216,10 @@ class _RunFn(torch.autograd.Function):
             zf = lambda: [torch.zeros(sim.grid_shape, dtype=sim.dtype, device=sim.device) for _ in range(3)]
             lH, lD = zf(), zf()
             gC2 = [torch.empty(sim.grid_shape, dtype=sim.dtype, device=sim.device) for _ in range(3)]
+            gC = [torch.empty(sim.grid_shape, dtype=sim.dtype, device=sim.device) for _ in range(3)]
             lp = [torch.zeros(shapes[q], dtype=sim.dtype, device=sim.device) for q in range(12)]
             G = [torch.zeros(sim.grid_shape, dtype=torch.float64, device=sim.device) for _ in range(3)]
-            adj = _adjoint(lH, lD, lp, gC2, G, _grad_box(sim))
+            adj = _adjoint(lH, lD, lp, gC2, G, _grad_box(sim), gC)
             # D after every step of a segment (the only forward quantity the transposed step needs: the step is linear
             # in the state): one ring of slots for the whole sweep, written straight by the out-of-place D half-steps
             longest = max(t1 - t0 for t0, t1, *_ in ctx.checkpoints)

@@ -37,6 +37,7 @@ struct AdjArgs {
     T* lIH[3];
     T* lICH[3];
     T* lID[3];
+    T* gC[3];        // cev_fdtd_adjoint_run's tensor-map kernels only (adjoint_v5.cuh): cotangent of curl_H(H_n), carried
     T* gC2[3];       // scratch: cotangent of curl_E(E_{n-1})
     double* G[3];    // dL/d(mE), accumulated in fp64 whatever the storage type
     int gb[6];       // design box (internal axes: x0, x1, y0, y1, z0, z1): G is only accumulated inside
@@ -229,6 +230,95 @@ __global__ void k_adj_seed(const AdjArgs<T, AT> a, ProbeTable pr, const int32_t*
         } else {
             atomicAdd(&a.lH[c][cell], (T)gw);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Tensor-map path of cev_fdtd_adjoint_run (adjoint_v5.cuh), start of a segment: the cell-local D part of the segment's last step applied to the TRUE cotangent lD
+// (-> lDp in place, gC, lICH, lID).  One thread per cell; once per checkpoint segment.
+template <typename T, typename AT>
+__global__ void __launch_bounds__(256) k_adj_Dlocal(const AdjArgs<T, AT> a) {
+    CEV_CELL_INDEX();
+    const int mx = a.mapD[0][i], my = a.mapD[1][j], mz = a.mapD[2][k];
+    const AT s = a.cdt;
+    if ((mx & my & mz) < 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a.gC[c][o] = (T)(s * (AT)a.lD[c][o]);
+        return;
+    }
+    const AT ux = a.uD[0][i], uy = a.uD[1][j], uz = a.uD[2][k];
+    const AT rx = a.rD[0][i], ry = a.rD[1][j], rz = a.rD[2][k];
+    {
+        const int64_t ic = (mx >= 0) ? ((int64_t)mx * a.Ny + j) * a.Nz + k : -1;
+        const int64_t is = (my >= 0 && mz >= 0) ? ((int64_t)i * a.nD[1] + my) * a.nD[2] + mz : -1;
+        a.gC[0][o] = (T)adj_component<T, AT>((AT)a.lD[0][o], uy, ry, uz, rz, ux, s, a.lD[0], o, a.lICH[0], ic, a.lID[0], is);
+    }
+    {
+        const int64_t ic = (my >= 0) ? ((int64_t)i * a.nD[1] + my) * a.Nz + k : -1;
+        const int64_t is = (mx >= 0 && mz >= 0) ? ((int64_t)mx * a.Ny + j) * a.nD[2] + mz : -1;
+        a.gC[1][o] = (T)adj_component<T, AT>((AT)a.lD[1][o], ux, rx, uz, rz, uy, s, a.lD[1], o, a.lICH[1], ic, a.lID[1], is);
+    }
+    {
+        const int64_t ic = (mz >= 0) ? ((int64_t)i * a.Ny + j) * a.nD[2] + mz : -1;
+        const int64_t is = (mx >= 0 && my >= 0) ? ((int64_t)mx * a.nD[1] + my) * a.Nz + k : -1;
+        a.gC[2][o] = (T)adj_component<T, AT>((AT)a.lD[2][o], ux, rx, uy, ry, uz, s, a.lD[2], o, a.lICH[2], ic, a.lID[2], is);
+    }
+}
+
+// Probe-series seeds of step k in the eager form: a seed v on the true lD of cell o (E-probe: v = mE g w, D-probe:
+// v = g w) is, after the D part of step k, (m1 + m4) v on lDp, (m2 + m3) v on gC, m3 v on lICH, m4 v on lID (the D
+// part is linear).  H-probe seeds go to lH unchanged.  One thread per point, atomics (probes may share cells).
+template <typename T, typename AT>
+__global__ void k_adj_seed_eager(const AdjArgs<T, AT> a, ProbeTable pr, const int32_t* __restrict__ slot_owner,
+                                 const double* __restrict__ gbar_row, const T* D0, const T* D1, const T* D2) {
+    const int slot = blockIdx.x;
+    const int field = pr.slot_field[slot];
+    const int c = field % 3;
+    const int64_t n = pr.slot_n[slot], wb = pr.slot_wbegin[slot], ib = pr.slot_ibegin[slot], c0 = pr.slot_cell0[slot];
+    const double gb = gbar_row[slot_owner[slot]];
+    if (gb == 0.0) return;
+    const T* Dn = c == 0 ? D0 : (c == 1 ? D1 : D2);
+    const int64_t pl = (int64_t)a.Ny * a.Nz;
+    for (int64_t q = threadIdx.x; q < n; q += blockDim.x) {
+        const int64_t cell = (ib < 0) ? (c0 + q) : pr.idx[ib + q];
+        const double gw = gb * pr.weight[wb + q];
+        if (field >= 6) {
+            atomicAdd(&a.lH[c][cell], (T)gw);
+            continue;
+        }
+        const int i = (int)(cell / pl), j = (int)((cell % pl) / a.Nz), k = (int)(cell % a.Nz);
+        double v = gw;
+        if (field < 3) {
+            v = (double)a.mE[c][cell] * gw;
+            if (a.G[c] && i >= a.gb[0] && i < a.gb[1] && j >= a.gb[2] && j < a.gb[3] && k >= a.gb[4] && k < a.gb[5])
+                atomicAdd(&a.G[c][cell], gw * (double)Dn[cell]);
+        }
+        const int m[3] = {a.mapD[0][i], a.mapD[1][j], a.mapD[2][k]};
+        const int ijk[3] = {i, j, k};
+        const int A = (c + 1) % 3, B = (c + 2) % 3;
+        const double ua = (double)a.uD[A][ijk[A]], ub = (double)a.uD[B][ijk[B]], uc = (double)a.uD[c][ijk[c]];
+        const double rr = (double)a.rD[A][ijk[A]] * (double)a.rD[B][ijk[B]];
+        const double s = (double)a.cdt;
+        const double m1 = 2 * rr - 1, m2 = s * rr, m3 = s * 2 * uc * rr, m4 = -4 * ua * ub * rr;
+        double dl = m1 * v, dg = m2 * v;
+        if (m[c] >= 0) {
+            int64_t ic;
+            if (c == 0) ic = ((int64_t)m[0] * a.Ny + j) * a.Nz + k;
+            else if (c == 1) ic = ((int64_t)i * a.nD[1] + m[1]) * a.Nz + k;
+            else ic = ((int64_t)i * a.Ny + j) * a.nD[2] + m[2];
+            atomicAdd(&a.lICH[c][ic], (T)(m3 * v));
+            dg += m3 * v;
+        }
+        if (m[A] >= 0 && m[B] >= 0) {
+            int64_t is;
+            if (c == 0) is = ((int64_t)i * a.nD[1] + m[1]) * a.nD[2] + m[2];
+            else if (c == 1) is = ((int64_t)m[0] * a.Ny + j) * a.nD[2] + m[2];
+            else is = ((int64_t)m[0] * a.nD[1] + m[1]) * a.Nz + k;
+            atomicAdd(&a.lID[c][is], (T)(m4 * v));
+            dl += m4 * v;
+        }
+        atomicAdd(&a.lD[c][cell], (T)dl);
+        atomicAdd(&a.gC[c][cell], (T)dg);
     }
 }
 

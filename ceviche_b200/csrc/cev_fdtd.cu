@@ -20,6 +20,7 @@
 #include "step_v3.cuh"
 #include "step_v4.cuh"
 #include "step_v5.h"
+#include "adjoint_v5.h"
 #include "adjoint.cuh"
 
 namespace {
@@ -89,6 +90,9 @@ struct cev_fdtd {
                                  // 6 tensor-map TMA kernels (step_v5.cuh) wherever they apply
     int tma_rows = 4, tma_stages_H = 3, tma_stages_D = 4;   // tile rows / ring depths of the tensor-map kernels
     int auto_v5 = 1;                    // kernel_variant 0 (auto) picks them on large 3-D grids
+    int adjoint_variant = 0;            // reverse sweep of cev_fdtd_adjoint_run: 0 auto, 1 simple kernels (adjoint.cuh),
+                                        // 2 tensor-map kernels (adjoint_v5.cuh) wherever they apply
+    int tma_stages_adjH = 4, tma_stages_adjED = 3;
     // x-slab halo exchange through peer-mapped memory (cev_fdtd_halo_attach): this slab's exchange block and the
     // neighbours' (device pointers valid on this device), and how many H / D half-steps have used them
     struct Halo {
@@ -1175,6 +1179,7 @@ int fill_adj(const cev_fdtd* p, const cev_state* fwd, const cev_adjoint* adj, Ad
         a.lIH[A] = (T*)adj->lIH[L];
         a.lICH[A] = (T*)adj->lICH[L];
         a.lID[A] = (T*)adj->lID[L];
+        a.gC[A] = (T*)adj->gC[L];
         a.gC2[A] = (T*)adj->gC2[L];
         a.G[A] = adj->G_mE[L];
         a.mE[A] = (const T*)fwd->inv_eps[L];
@@ -1235,6 +1240,52 @@ int launch_adjoint_seed(cev_fdtd* p, const cev_state* fwd, const cev_adjoint* ad
     return 0;
 }
 
+// The tensor-map kernels of the reverse sweep (adjoint_v5.cuh) serve whole 3-D grids with the forward kernels' tile
+// constraints; they carry the cotangents in the "eager" form and need the third scratch vector field adj->gC.
+template <typename T, typename AT>
+bool adjoint_v5_ok(cev_fdtd* p, const AdjArgs<T, AT>& a) {
+    constexpr int V = vec_width<T>();
+    if (p->adjoint_variant == 1) return false;
+    if (p->perm[0] != 0 || p->perm[1] != 1 || p->perm[2] != 2 || p->on != 63u) return false;
+    if (a.Ny < p->tma_rows || a.Ny % p->tma_rows != 0 || a.Nz % V != 0 || a.Nz < 32 * V) return false;
+    if (p->adjoint_variant != 2 && (int64_t)a.Ny * a.Nz < (1 << 14)) return false;     // small planes: too few CTAs per chunk
+    auto al = [](const void* q) { return ((uintptr_t)q % 16) == 0; };
+    for (int c = 0; c < 3; ++c) {
+        if (!a.gC[c]) return false;
+        if (!al(a.lH[c]) || !al(a.lD[c]) || !al(a.gC[c]) || !al(a.gC2[c]) || !al(a.mE[c]) || !al(a.lICE[c]) || !al(a.lIH[c]) ||
+            !al(a.lICH[c]) || !al(a.lID[c]))
+            return false;
+    }
+    return true;
+}
+
+// StepArgs of the two tensor-map adjoint kernels (field re-use documented at AdjV5Extra)
+template <typename T, typename AT>
+void adjoint_v5_args(cev_fdtd* p, const AdjArgs<T, AT>& a, StepArgs<T, AT>& aH, StepArgs<T, AT>& aED) {
+    memset(&aH, 0, sizeof aH);
+    aH.Nx = a.Nx; aH.Ny = a.Ny; aH.Nz = a.Nz;
+    for (int A = 0; A < 3; ++A) {
+        aH.mapH[A] = a.mapH[A]; aH.mapD[A] = a.mapD[A];
+        aH.nH[A] = a.nH[A]; aH.nD[A] = a.nD[A];
+        aH.uH[A] = a.uH[A]; aH.rH[A] = a.rH[A]; aH.uD[A] = a.uD[A]; aH.rD[A] = a.rD[A];
+        aH.mE[A] = a.mE[A];
+    }
+    aH.cdt = a.cdt;
+    aH.inv_dL = a.inv_dL;
+    aH.on = 63u;
+    aH.t_probe = -1;
+    aED = aH;
+    for (int A = 0; A < 3; ++A) {
+        aH.Din[A] = a.gC[A]; aH.Hin[A] = a.lH[A]; aH.Hout[A] = a.lH[A]; aH.Eout[A] = a.gC2[A];
+        aH.ICE[A] = a.lICE[A]; aH.IH[A] = a.lIH[A];
+        aED.Hin[A] = a.gC2[A]; aED.Din[A] = a.lD[A]; aED.Dout[A] = a.lD[A]; aED.Eout[A] = a.gC[A];
+        aED.ICH[A] = a.lICH[A]; aED.ID[A] = a.lID[A];
+    }
+    v5_set_tiles(aH, 0, a.Nx, p->tma_rows, p->xchunk);
+    v5_set_tiles(aED, 0, a.Nx, p->tma_rows, p->xchunk);
+    if (!p->v5) p->v5 = v5_cache_create();
+}
+
 // One checkpoint segment of the reverse sweep, entirely on the device queue: recompute the forward steps from the
 // segment's start state keeping D after every step (hist[k] = D after k steps; hist[0] is the start D), then the
 // transposed steps in reverse order, each preceded by the probe-series seeds of its time step.
@@ -1253,8 +1304,39 @@ int adjoint_run(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* 
     cev_state fwd;
     memset(&fwd, 0, sizeof fwd);
     for (int c = 0; c < 3; ++c) fwd.inv_eps[c] = st->inv_eps[c];
+    for (int c = 0; c < 3; ++c) fwd.D[c] = hist[nsteps][c];
+    AdjArgs<T, AT> a;
+    if (fill_adj(p, &fwd, adj, a)) return -1;
+    const bool seeds = gbar && p->n_slots > 0;
+    if (adjoint_v5_ok(p, a)) {
+        // tensor-map kernels, cotangents in the eager form between the segment's steps (adjoint_v5.cuh)
+        StepArgs<T, AT> aH, aED;
+        adjoint_v5_args(p, a, aH, aED);
+        ProbeTable pr;
+        fill_probe_table(p, pr);
+        const dim3 blk(64, 4);
+        const dim3 grd((a.Nz + 63) / 64, (a.Ny + 3) / 4, a.Nx);
+        if (grd.y > 65535 || grd.z > 65535) return fail("adjoint kernels: grid extent too large");
+        k_adj_Dlocal<T, AT><<<grd, blk, 0, s>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        for (int64_t k = nsteps; k >= 1; --k) {
+            if (seeds) {
+                const T* Dk[3];
+                for (int A = 0; A < 3; ++A) Dk[A] = (const T*)hist[k][p->to_logical(A)];
+                k_adj_seed_eager<T, AT><<<p->n_slots, 128, 0, s>>>(a, pr, (const int32_t*)p->pr_owner.p,
+                                                                   gbar + (k - 1) * p->nprobe, Dk[0], Dk[1], Dk[2]);
+                CUDA_TRY(cudaGetLastError());
+            }
+            if (v5_launch_adj_H<T, AT>(p->v5, aH, p->tma_rows, p->tma_stages_adjH, s)) return fail("%s", v5_last_error());
+            const void* Dprev[3];
+            for (int A = 0; A < 3; ++A) Dprev[A] = hist[k - 1][p->to_logical(A)];
+            if (v5_launch_adj_ED<T, AT>(p->v5, aED, Dprev, a.G, a.gb, k > 1 ? 1 : 0, p->tma_rows, p->tma_stages_adjED, s))
+                return fail("%s", v5_last_error());
+        }
+        return 0;
+    }
     for (int64_t k = nsteps; k >= 1; --k) {
-        if (gbar && p->n_slots > 0) {
+        if (seeds) {
             for (int c = 0; c < 3; ++c) fwd.D[c] = hist[k][c];
             if (launch_adjoint_seed<T, AT>(p, &fwd, adj, gbar + (k - 1) * p->nprobe, s)) return -1;
         }
@@ -1458,6 +1540,12 @@ int cev_fdtd_set_option(cev_fdtd* p, const char* name, int64_t value) {
         const char which = name[10] ? name[11] : 0;             // "tma_stages" sets both
         if (which != 'D') p->tma_stages_H = (int)value;
         if (which != 'H') p->tma_stages_D = (int)value;
+    } else if (!strcmp(name, "adjoint_variant")) {
+        if (value < 0 || value > 2) return fail("adjoint_variant must be 0 (auto), 1 (simple kernels) or 2 (tensor-map kernels)");
+        p->adjoint_variant = (int)value;
+    } else if (!strcmp(name, "tma_stages_adjH") || !strcmp(name, "tma_stages_adjED")) {
+        if (!v5_supported_shape(p->tma_rows, (int)value)) return fail("%s must be 3 or 4", name);
+        (name[14] == 'H' ? p->tma_stages_adjH : p->tma_stages_adjED) = (int)value;
     } else if (!strcmp(name, "halo_pause")) {
         if (value != 0 && value != 1) return fail("halo_pause must be 0 or 1");
         p->halo.paused = value != 0;

@@ -9,6 +9,7 @@
 #include <unordered_map>
 
 #include "step_v5.cuh"
+#include "step_v5_maps.h"
 
 namespace cev {
 
@@ -35,7 +36,6 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
     return fn;
 }
 
-enum BoxKind { BOX_MAIN = 0, BOX_ROW = 1, BOX_PLN = 2 };
 
 struct Key {
     const void* ptr;
@@ -61,10 +61,9 @@ void v5_cache_destroy(V5MapCache* c) { delete c; }
 const char* v5_last_error() { return g_v5_err.c_str(); }
 bool v5_supported_shape(int rows, int stages) { return (rows == 4 || rows == 8) && (stages == 3 || stages == 4); }
 
-namespace {
-
-// descriptor of `nx` planes of (Ny, Nz) cells of `esize` bytes at `ptr`, box kind / rows as given
-int get_map(V5MapCache* c, const void* ptr, int64_t nx, int Ny, int Nz, int esize, int kind, int rows, CUtensorMap* out) {
+// descriptor of `nx` planes of (Ny, Nz) cells of `esize` bytes at `ptr`, box kind / rows as given (also used by
+// adjoint_v5.cu: declared in step_v5_maps.h)
+int v5_get_map(V5MapCache* c, const void* ptr, int64_t nx, int Ny, int Nz, int esize, int kind, int rows, CUtensorMap* out) {
     if (c->Ny != Ny || c->Nz != Nz) {       // (a cache belongs to one plan: one plane shape)
         c->maps.clear();
         c->Ny = Ny;
@@ -99,6 +98,19 @@ int get_map(V5MapCache* c, const void* ptr, int64_t nx, int Ny, int Nz, int esiz
     *out = m;
     return 0;
 }
+
+int v5_set_smem_attr(const void* kernel, size_t bytes, int* done) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && done[dev]) return 0;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return v5_fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: ", cudaGetErrorString(e));
+    if (dev < 64) done[dev] = 1;
+    return 0;
+}
+int v5_fail_msg(const char* what, const char* detail) { return v5_fail(what, detail); }
+
+namespace {
 
 // dynamic shared memory opt-in, once per device and kernel instantiation (`done` is a static of the CALLER, which is
 // a distinct function per instantiation; the kernel pointer TYPE is shared by all of them)
@@ -184,17 +196,17 @@ int v5_launch_H(V5MapCache* c, const StepArgs<T, AT>& a, int rows, int stages, i
     constexpr int es = (int)sizeof(T);
     V5MapsH m;
     for (int q = 0; q < 3; ++q) {
-        if (get_map(c, a.Din[q], a.Nx, a.Ny, a.Nz, es, BOX_MAIN, rows, &m.D[q])) return -1;
-        if (get_map(c, a.mE[q], a.Nx, a.Ny, a.Nz, es, BOX_MAIN, rows, &m.M[q])) return -1;
-        if (get_map(c, a.Hin[q], a.Nx, a.Ny, a.Nz, es, BOX_PLN, rows, &m.H[q])) return -1;
+        if (v5_get_map(c, a.Din[q], a.Nx, a.Ny, a.Nz, es, BOX_MAIN, rows, &m.D[q])) return -1;
+        if (v5_get_map(c, a.mE[q], a.Nx, a.Ny, a.Nz, es, BOX_MAIN, rows, &m.M[q])) return -1;
+        if (v5_get_map(c, a.Hin[q], a.Nx, a.Ny, a.Nz, es, BOX_PLN, rows, &m.H[q])) return -1;
     }
     for (int r = 0; r < 2; ++r) {
         const int cr = r == 0 ? 0 : 2, ch = r == 0 ? 1 : 2;
-        if (get_map(c, a.Din[cr], a.Nx, a.Ny, a.Nz, es, BOX_ROW, rows, &m.Drow[r])) return -1;
-        if (get_map(c, a.mE[cr], a.Nx, a.Ny, a.Nz, es, BOX_ROW, rows, &m.Mrow[r])) return -1;
+        if (v5_get_map(c, a.Din[cr], a.Nx, a.Ny, a.Nz, es, BOX_ROW, rows, &m.Drow[r])) return -1;
+        if (v5_get_map(c, a.mE[cr], a.Nx, a.Ny, a.Nz, es, BOX_ROW, rows, &m.Mrow[r])) return -1;
         // the plane standing for i = Nx: ONE plane at a.Dhi (plane 0 of the array itself on a periodic grid)
-        if (get_map(c, a.Dhi[ch], 1, a.Ny, a.Nz, es, BOX_MAIN, rows, &m.Dhi[r])) return -1;
-        if (get_map(c, a.mEhi[ch], 1, a.Ny, a.Nz, es, BOX_MAIN, rows, &m.Mhi[r])) return -1;
+        if (v5_get_map(c, a.Dhi[ch], 1, a.Ny, a.Nz, es, BOX_MAIN, rows, &m.Dhi[r])) return -1;
+        if (v5_get_map(c, a.mEhi[ch], 1, a.Ny, a.Nz, es, BOX_MAIN, rows, &m.Mhi[r])) return -1;
     }
     m.x_hi = 0;
 #define CEV_V5_H(BY, NS) return launch_H_shape<T, AT, BY, NS>(a, m, n_aux, s)
@@ -212,14 +224,14 @@ int v5_launch_D(V5MapCache* c, const StepArgs<T, AT>& a, int rows, int stages, i
     constexpr int es = (int)sizeof(T);
     V5MapsD m;
     for (int q = 0; q < 3; ++q) {
-        if (get_map(c, a.Hin[q], a.Nx, a.Ny, a.Nz, es, BOX_MAIN, rows, &m.H[q])) return -1;
-        if (get_map(c, a.Din[q], a.Nx, a.Ny, a.Nz, es, BOX_PLN, rows, &m.D[q])) return -1;
+        if (v5_get_map(c, a.Hin[q], a.Nx, a.Ny, a.Nz, es, BOX_MAIN, rows, &m.H[q])) return -1;
+        if (v5_get_map(c, a.Din[q], a.Nx, a.Ny, a.Nz, es, BOX_PLN, rows, &m.D[q])) return -1;
     }
     for (int r = 0; r < 2; ++r) {
         const int cr = r == 0 ? 0 : 2, cl = r == 0 ? 1 : 2;
-        if (get_map(c, a.Hin[cr], a.Nx, a.Ny, a.Nz, es, BOX_ROW, rows, &m.Hrow[r])) return -1;
+        if (v5_get_map(c, a.Hin[cr], a.Nx, a.Ny, a.Nz, es, BOX_ROW, rows, &m.Hrow[r])) return -1;
         // the plane standing for i = -1: ONE plane at a.Hlo (the array's last plane on a periodic grid)
-        if (get_map(c, a.Hlo[cl], 1, a.Ny, a.Nz, es, BOX_MAIN, rows, &m.Hlo[r])) return -1;
+        if (v5_get_map(c, a.Hlo[cl], 1, a.Ny, a.Nz, es, BOX_MAIN, rows, &m.Hlo[r])) return -1;
     }
     m.x_lo = 0;
 #define CEV_V5_D(BY, NS) return launch_D_shape<T, AT, BY, NS>(a, m, n_aux, s)

@@ -256,6 +256,76 @@ struct PmlLean {
         if (fx && fy) stv<T, V>(Is[2] + mx * (n1 * Nz) + o_is2, s2v);
     }
 
+    // Transposed update of the reverse sweep (adjoint_v5.cuh).  g[c][e] = cotangent of the component's NEW value ->
+    // lout = cotangent of its OLD value (m1 g + gIself), gc = cotangent of its curl (m2 g + gIcurl); the cotangents of
+    // the integrals (the same compact arrays, their old values fetched by load()) gain m3 g / m4 g.  Plain arithmetic:
+    // the adjoint has a tolerance to meet, not the reference's rounding sequence, so FMA contraction is welcome.
+    __device__ __forceinline__ void apply_adj(const StepArgs<T, AT>& a, int i, int mx, AT ux, AT rx, AT s, const AT (*g)[V],
+                                              Vec<T, V>* lout, Vec<T, V>* gc) {
+        T* const* Ic = IS_H ? a.ICE : a.ICH;
+        T* const* Is = IS_H ? a.IH : a.ID;
+        const bool fx = mx >= 0;
+        const AT su2x = s * (ux + ux);
+        const AT n4ux = AT(-4) * ux;
+        const AT rrz = rx * ry;
+        const AT m1z = rrz + rrz - AT(1), m2z = s * rrz, m4z = n4ux * uy * rrz;
+        Vec<T, V> n0, n1v, s2v;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            {   // x: (a, b) = (y, z)
+                const AT rr = rrx[e], gg = g[0][e];
+                AT l = (rr + rr - AT(1)) * gg, c = s * rr * gg;
+                if (fx) {
+                    const AT I = (AT)I0.v[e] + su2x * rr * gg;
+                    n0.v[e] = (T)I;
+                    c += I;
+                }
+                if (fy && fz[e]) {
+                    const AT I = (AT)S0[e] + m4x[e] * gg;
+                    Is[0][i * (n1 * n2) + o_is0 + mz[e]] = (T)I;
+                    l += I;
+                }
+                lout[0].v[e] = (T)l;
+                gc[0].v[e] = (T)c;
+            }
+            {   // y: (a, b) = (x, z)
+                const AT rr = rx * rz[e], gg = g[1][e];
+                AT l = (rr + rr - AT(1)) * gg, c = s * rr * gg;
+                if (fy) {
+                    const AT I = (AT)I1.v[e] + su2y * rr * gg;
+                    n1v.v[e] = (T)I;
+                    c += I;
+                }
+                if (fx && fz[e]) {
+                    const AT I = (AT)S1[e] + n4ux * uz[e] * rr * gg;
+                    Is[1][mx * (Ny * n2) + o_is1 + mz[e]] = (T)I;
+                    l += I;
+                }
+                lout[1].v[e] = (T)l;
+                gc[1].v[e] = (T)c;
+            }
+            {   // z: (a, b) = (x, y)
+                const AT gg = g[2][e];
+                AT l = m1z * gg, c = m2z * gg;
+                if (fz[e]) {
+                    const AT I = (AT)I2[e] + su2z[e] * rrz * gg;
+                    Ic[2][i * (Ny * n2) + o_ic2 + mz[e]] = (T)I;
+                    c += I;
+                }
+                if (fx && fy) {
+                    const AT I = (AT)S2.v[e] + m4z * gg;
+                    s2v.v[e] = (T)I;
+                    l += I;
+                }
+                lout[2].v[e] = (T)l;
+                gc[2].v[e] = (T)c;
+            }
+        }
+        if (fx) stv<T, V>(Ic[0] + mx * (Ny * Nz) + orow, n0);
+        if (fy) stv<T, V>(Ic[1] + i * (n1 * Nz) + o_ic1, n1v);
+        if (fx && fy) stv<T, V>(Is[2] + mx * (n1 * Nz) + o_is2, s2v);
+    }
+
     __device__ __forceinline__ bool fz_any() const {
         bool f = false;
 #pragma unroll

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CEV_ABI_VERSION 2
+#define CEV_ABI_VERSION 3
 #define CEV_F32 0
 #define CEV_F64 1
 
@@ -94,6 +94,8 @@ typedef struct cev_adjoint {
     void*   gC2[3];
     double* G_mE[3];
     int64_t g_box[6];
+    void*   gC[3];      /* second scratch vector field: optional (all NULL = the simple kernels); with it
+                         * cev_fdtd_adjoint_run may use the tensor-map kernels (csrc/adjoint_v5.cuh) */
 } cev_adjoint;
 
 const char* cev_last_error(void);

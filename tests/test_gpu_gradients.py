@@ -211,3 +211,47 @@ def test_hips_autograd_registration_callables():
     d = rng.standard_normal(case["eps"].shape)
     t_hips = reg["jvp"][1][0](d, series, case["eps"], F, case["steps"], case["sources"], case["probes"])
     assert abs(float((t_hips * v).sum()) - float((g_hips * d).sum())) <= 1e-9 * abs(float((g_hips * d).sum()))   # <v, J d> = <J^T v, d>
+
+
+@pytest.mark.parametrize("every", [None, 5])
+@pytest.mark.parametrize("dtype,shape,region", [(torch.float64, (12, 8, 64), None), (torch.float64, (9, 12, 70), ((2, 7), (3, 9), (20, 61))),
+                                                (torch.float32, (10, 12, 128), None)])
+def test_tensor_map_adjoint_matches_simple_kernels(dtype, shape, region, every):
+    """cev_fdtd_adjoint_run's tensor-map kernels (csrc/adjoint_v5.cuh: the transposed step re-phased into two marching
+    kernels, cotangents in the eager form) against the simple transposed-step kernels (csrc/adjoint.cuh, themselves
+    <= 1e-10 from the autograd oracle above) on grids the tensor-map tiles serve: PML on all axes, probes on E / D / H
+    incl. inside the PML corners, several checkpoint segments, with and without a design box."""
+    import ceviche_b200
+    case = cases._small3d(shape, (3, 2, 5), 23, 77)
+    grads = {}
+    for variant in (1, 2):
+        eps = torch.as_tensor(case["eps"]).cuda().requires_grad_(True)
+        F = ceviche_b200.fdtd(eps, case["dL"], case["npml"], dtype=dtype)
+        F.set_option("adjoint_variant", variant)
+        F.design_region = region
+        series = F.run(case["steps"], case["sources"], case["probes"], checkpoint_every=every)
+        (g,) = torch.autograd.grad(_loss(series, case), eps)
+        g = g.double().cpu().numpy()
+        if region is not None:      # only the region's cells carry the gradient
+            g = g[tuple(slice(lo, hi) for lo, hi in region)]
+        grads[variant] = g
+    assert np.abs(grads[1]).max() > 0
+    assert rel_l2(grads[2], grads[1]) <= (1e-12 if dtype == torch.float64 else 2e-5)
+
+
+def test_tensor_map_adjoint_identity():
+    """<gbar, J v> = <J^T gbar, v> with J^T from the tensor-map adjoint kernels and J v from the tangent sweep."""
+    import ceviche_b200
+    case = cases._small3d((12, 8, 64), (3, 2, 5), 23, 78)
+    rng = np.random.default_rng(9)
+    v = torch.as_tensor(rng.standard_normal(case["eps"].shape))
+    gbar = torch.as_tensor(rng.standard_normal((case["steps"], len(case["probes"])))).cuda()
+    eps = torch.as_tensor(case["eps"]).cuda().requires_grad_(True)
+    F = ceviche_b200.fdtd(eps, case["dL"], case["npml"])
+    F.set_option("adjoint_variant", 2)
+    series = F.run(case["steps"], case["sources"], case["probes"], checkpoint_every=6)
+    (g,) = torch.autograd.grad((series * gbar).sum(), eps)
+    F2 = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"])
+    _, ds = F2.jvp_run(case["steps"], v[None], case["sources"], case["probes"])
+    lhs, rhs = float((gbar * ds[0]).sum()), float((g * v.cuda()).sum())
+    assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), abs(rhs)), (lhs, rhs)

@@ -44,7 +44,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), name
     assert set(_lib.EXPORTS) == declared
-    assert lib.cev_abi_version() == 2
+    assert lib.cev_abi_version() == 3
 
 
 def test_no_cpu_fallback_without_cuda():
@@ -142,7 +142,7 @@ int main(void) {
                         "-o", exe], check=True)
         out = subprocess.run([exe], capture_output=True, text=True)
         assert out.returncode == 0, out.stdout + out.stderr
-        assert out.stdout.split()[0] == "2" and "dtype" in out.stdout
+        assert out.stdout.split()[0] == "3" and "dtype" in out.stdout
 
 
 def test_hips_binding_is_a_soft_dependency():
