@@ -82,6 +82,20 @@ def _grad_box(sim):
     return box
 
 
+def _record_fits(sim, box, steps):
+    """Can the reverse sweep run from a D-box record (no checkpoints, no recomputation)?  The tensor-map adjoint
+    kernels must serve the grid, and the record (steps + 1 slots of the box) must fit in a quarter of the free memory."""
+    plan = sim._ensure_plan()
+    if not plan.lib.cev_fdtd_adjoint_boxed_supported(plan.handle) or sim._n_mon_pts > 0:
+        return False
+    cells = 1
+    for lo, hi in box:
+        cells *= hi - lo
+    need = (steps + 1) * 3 * cells * (8 if sim.dtype == torch.float64 else 4)
+    free, _ = torch.cuda.mem_get_info(sim.device)
+    return need <= free // 4
+
+
 def _flat_pml(sim):
     return [t for fam in _FAMS for t in sim._pml[fam]]
 
@@ -188,6 +202,29 @@ class _RunFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, sim, steps, waveforms, every, mEx, mEy, mEz):
         ctx.sim, ctx.steps, ctx.waveforms = sim, steps, waveforms
+        ctx.record = None
+        box = _grad_box(sim)
+        if box is not None and every is None and steps > 0 and _record_fits(sim, box, steps):
+            # gradients wanted inside a design box only: record D of the box after every step instead of checkpointing the
+            # state -- the reverse sweep then needs no recomputation at all (cev_fdtd_adjoint_run_boxed)
+            plan = sim._ensure_plan()
+            with torch.cuda.device(sim.device):
+                bx, by, bz = [hi - lo for lo, hi in box]
+                rec = torch.empty((steps + 1, 3, bx, by, bz), dtype=sim.dtype, device=sim.device)
+                sl = tuple(slice(lo, hi) for lo, hi in box)
+                for c in range(3):
+                    rec[0, c].copy_(sim._D[c][sl])
+                flat = (C.c_int64 * 6)(*[int(v) for pair in box for v in pair])
+                _lib.check(plan.lib.cev_fdtd_set_recorder(plan.handle, flat, rec[1].data_ptr(), steps))
+                try:
+                    out = sim._run_raw(steps, waveforms, refresh=True, fused=False)
+                finally:
+                    _lib.check(plan.lib.cev_fdtd_set_recorder(plan.handle, None, None, 0))
+            ctx.record, ctx.box = rec, box
+            ctx.mE = [m.clone() for m in sim._mE]
+            ctx.n_probes = sim._n_probes
+            ctx.active = sim._active
+            return out
         every = max(1, int(every or math.ceil(math.sqrt(max(steps, 1)))))
         ctx.every = every
         ctx.checkpoints = []
@@ -219,6 +256,13 @@ class _RunFn(torch.autograd.Function):
             gC = [torch.empty(sim.grid_shape, dtype=sim.dtype, device=sim.device) for _ in range(3)]
             lp = [torch.zeros(shapes[q], dtype=sim.dtype, device=sim.device) for q in range(12)]
             G = [torch.zeros(sim.grid_shape, dtype=torch.float64, device=sim.device) for _ in range(3)]
+            if ctx.record is not None:      # no recomputation: the forward run recorded D of the design box
+                adj = _adjoint(lH, lD, lp, gC2, G, ctx.box, gC)
+                st = _state(lH, lH, ctx.mE, [None] * 12)          # only inv_eps is read
+                _lib.check(lib.cev_fdtd_adjoint_run_boxed(h, C.byref(st), ctx.steps, _ptr(gbar) if ctx.n_probes else None,
+                                                          ctx.record.data_ptr(), C.byref(adj), s))
+                sim._apply_active(sim._active)
+                return (None, None, None, None, *G)
             adj = _adjoint(lH, lD, lp, gC2, G, _grad_box(sim), gC)
             # D after every step of a segment (the only forward quantity the transposed step needs: the step is linear
             # in the state): one ring of slots for the whole sweep, written straight by the out-of-place D half-steps

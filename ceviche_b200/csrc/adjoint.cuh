@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) k_adj_Dlocal(const AdjArgs<T, AT> a) {
 // part is linear).  H-probe seeds go to lH unchanged.  One thread per point, atomics (probes may share cells).
 template <typename T, typename AT>
 __global__ void k_adj_seed_eager(const AdjArgs<T, AT> a, ProbeTable pr, const int32_t* __restrict__ slot_owner,
-                                 const double* __restrict__ gbar_row, const T* D0, const T* D1, const T* D2) {
+                                 const double* __restrict__ gbar_row, const T* D0, const T* D1, const T* D2, int boxed) {
     const int slot = blockIdx.x;
     const int field = pr.slot_field[slot];
     const int c = field % 3;
@@ -290,8 +290,11 @@ __global__ void k_adj_seed_eager(const AdjArgs<T, AT> a, ProbeTable pr, const in
         double v = gw;
         if (field < 3) {
             v = (double)a.mE[c][cell] * gw;
-            if (a.G[c] && i >= a.gb[0] && i < a.gb[1] && j >= a.gb[2] && j < a.gb[3] && k >= a.gb[4] && k < a.gb[5])
-                atomicAdd(&a.G[c][cell], gw * (double)Dn[cell]);
+            if (a.G[c] && i >= a.gb[0] && i < a.gb[1] && j >= a.gb[2] && j < a.gb[3] && k >= a.gb[4] && k < a.gb[5]) {
+                // (boxed: D_k is the forward run's record of the design box only, C-order)
+                const int64_t dn = boxed ? ((int64_t)(i - a.gb[0]) * (a.gb[3] - a.gb[2]) + (j - a.gb[2])) * (a.gb[5] - a.gb[4]) + (k - a.gb[4]) : cell;
+                atomicAdd(&a.G[c][cell], gw * (double)Dn[dn]);
+            }
         }
         const int m[3] = {a.mapD[0][i], a.mapD[1][j], a.mapD[2][k]};
         const int ijk[3] = {i, j, k};

@@ -53,7 +53,7 @@ int v5_launch_adj_H(V5MapCache* c, const StepArgs<T, AT>& a, int rows, int stage
 
 template <typename T, typename AT>
 int v5_launch_adj_ED(V5MapCache* c, const StepArgs<T, AT>& a, const void* const Dprev[3], double* const G[3], const int gb[6],
-                     int eager, int rows, int stages, cudaStream_t s) {
+                     int eager, int boxed, int rows, int stages, cudaStream_t s) {
     constexpr int es = (int)sizeof(T);
     V5MapsAdjED m;
     AdjV5Extra<T> x;
@@ -68,6 +68,7 @@ int v5_launch_adj_ED(V5MapCache* c, const StepArgs<T, AT>& a, const void* const 
         if (v5_get_map(c, a.Hin[r == 0 ? 0 : 2], a.Nx, a.Ny, a.Nz, es, BOX_ROW, rows, &m.Crow[r])) return -1;
     for (int q = 0; q < 6; ++q) x.gb[q] = gb[q];
     x.eager = eager;
+    x.boxed = boxed;
 #define CEV_ADJ_ED(BY, NS) return launch_adj_ED_shape<T, AT, BY, NS>(a, m, x, s)
     if (rows == 4 && stages == 3) CEV_ADJ_ED(4, 3);
     if (rows == 4 && stages == 4) CEV_ADJ_ED(4, 4);
@@ -80,7 +81,7 @@ int v5_launch_adj_ED(V5MapCache* c, const StepArgs<T, AT>& a, const void* const 
 #define CEV_ADJ_V5_INSTANTIATE(T, AT)                                                                              \
     template int v5_launch_adj_H<T, AT>(V5MapCache*, const StepArgs<T, AT>&, int, int, cudaStream_t);              \
     template int v5_launch_adj_ED<T, AT>(V5MapCache*, const StepArgs<T, AT>&, const void* const[3], double* const[3], \
-                                         const int[6], int, int, int, cudaStream_t);
+                                         const int[6], int, int, int, int, cudaStream_t);
 CEV_ADJ_V5_INSTANTIATE(double, double)
 CEV_ADJ_V5_INSTANTIATE(float, double)
 CEV_ADJ_V5_INSTANTIATE(float, float)

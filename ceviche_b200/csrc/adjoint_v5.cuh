@@ -38,6 +38,7 @@ struct AdjV5Extra {
     double* G[3];          // dL/d(1/eps), fp64, nullable per component
     int gb[6];             // design box x0, x1, y0, y1, z0, z1 (internal axes)
     int eager;             // 1: apply the D part of step k-1 (gC, lDp, integrals); 0: leave the true lD in Dout
+    int boxed;             // 1: Dprev[c] holds the design box only, C-order (gb extents): the forward run's D-box record
 };
 
 struct V5MapsAdjH {
@@ -304,6 +305,9 @@ __global__ void __launch_bounds__(32 * BY) k_adj_ED_v5(const StepArgs<T, AT> a, 
         gbox_e[e] = active && j >= x.gb[2] && j < x.gb[3] && k0 + e >= x.gb[4] && k0 + e < x.gb[5];
         gbox_any |= gbox_e[e];
     }
+    // where the forward D of this thread's cells lives: the full-grid array, or the box record
+    const int bzx = x.gb[5] - x.gb[4], bpl = (x.gb[3] - x.gb[2]) * bzx;
+    const int drow = x.boxed ? (j - x.gb[2]) * bzx + (k0 - x.gb[4]) : orow;
 
     int sc = 0;                                      // stage of plane i-1
     uint32_t ph = 0;
@@ -337,7 +341,7 @@ __global__ void __launch_bounds__(32 * BY) k_adj_ED_v5(const StepArgs<T, AT> a, 
 #pragma unroll
                 for (int e = 0; e < V; ++e)
                     if (gbox_e[e] && x.G[c]) {
-                        dprev[c][e] = x.Dprev[c][pbase + orow + e];
+                        dprev[c][e] = x.Dprev[c][(x.boxed ? (i - x.gb[0]) * bpl : pbase) + drow + e];
                         gold[c][e] = x.G[c][(int64_t)pbase + orow + e];
                     }
         }

@@ -104,6 +104,12 @@ struct cev_fdtd {
         bool on() const { return own && !paused; }
     } halo;
     cev::V5MapCache* v5 = nullptr;      // CUtensorMap descriptors of this plan's arrays
+    // D-box recorder (cev_fdtd_set_recorder): cev_fdtd_run stores D of the box after every step into slot count++
+    struct Recorder {
+        void* buf = nullptr;
+        int64_t capacity = 0, count = 0;
+        int box[6] = {0, 0, 0, 0, 0, 0};     // internal axes
+    } rec;
     int fused_shape = 0;         // tile shape of the fused kernel: 0 auto, else LZ*100 + BY
     int xchunk = 0;              // 0 auto
     int pf_dist = 1;             // L2 prefetch distance of the marching kernels (planes)
@@ -834,6 +840,35 @@ int get_run_graph(cev_fdtd* p, const cev_state* st, cudaGraphExec_t* out) {
     return 0;
 }
 
+// D of the recorder's box after a step -> one slot [3][bx][by][bz] of the record (storage type)
+template <typename T>
+__global__ void k_record_box(const T* D0, const T* D1, const T* D2, T* out, int Ny, int Nz, int x0, int y0, int z0, int bx,
+                             int by, int bz) {
+    const int64_t n = (int64_t)bx * by * bz;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int k = (int)(q % bz), j = (int)((q / bz) % by), i = (int)(q / ((int64_t)bz * by));
+    const int64_t o = ((int64_t)(x0 + i) * Ny + (y0 + j)) * Nz + (z0 + k);
+    out[q] = D0[o];
+    out[n + q] = D1[o];
+    out[2 * n + q] = D2[o];
+}
+
+template <typename T, typename AT>
+int record_box(cev_fdtd* p, const cev_state* st, cudaStream_t s) {
+    auto& r = p->rec;
+    if (r.count >= r.capacity) return fail("D-box recorder is full (%lld slots)", (long long)r.capacity);
+    const int bx = r.box[1] - r.box[0], by = r.box[3] - r.box[2], bz = r.box[5] - r.box[4];
+    const int64_t n = (int64_t)bx * by * bz;
+    const T* D[3];
+    for (int A = 0; A < 3; ++A) D[A] = (const T*)st->D[p->to_logical(A)];
+    k_record_box<T><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(D[0], D[1], D[2], (T*)r.buf + r.count * 3 * n, p->N[1], p->N[2],
+                                                                 r.box[0], r.box[2], r.box[4], bx, by, bz);
+    CUDA_TRY(cudaGetLastError());
+    r.count++;
+    return 0;
+}
+
 template <typename T, typename AT>
 int run_loop(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* waveform, double* partials,
              cudaStream_t s) {
@@ -841,7 +876,8 @@ int run_loop(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* wav
     int64_t n0 = 0;
     const int64_t cells = (int64_t)p->N[0] * p->N[1] * p->N[2];
     const bool monitors = p->n_mon_pts > 0 && p->mon_acc;     // (their phasor row changes every step: no graph replay)
-    const bool graphs = !monitors && !p->halo.on() &&      // (the halo targets change with every step: no static graph)
+    const bool recording = p->rec.buf != nullptr;
+    const bool graphs = !monitors && !recording && !p->halo.on() &&      // (the halo targets change with every step: no static graph)
                         (p->use_graph == 1 || (p->use_graph < 0 && cells <= GRAPH_MAX_CELLS));
     if (graphs && nsteps >= 2 * GRAPH_K + 1) {
         // step 0 the ordinary way (it also builds the source tilings and sets kernel attributes), then whole blocks
@@ -872,6 +908,7 @@ int run_loop(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* wav
                             Nx, n, partials, s))
             return -1;
         if (monitors && launch_monitors<T, AT>(p, st, n, s)) return -1;
+        if (recording && record_box<T, AT>(p, st, s)) return -1;
     }
     if (nsteps > 0 && launch_probe_only<T, AT>(p, st, nullptr, 0, nsteps - 1, partials, s)) return -1;
     return 0;
@@ -1286,6 +1323,34 @@ void adjoint_v5_args(cev_fdtd* p, const AdjArgs<T, AT>& a, StepArgs<T, AT>& aH, 
     if (!p->v5) p->v5 = v5_cache_create();
 }
 
+// The reverse sweep of nsteps steps with the tensor-map kernels (adjoint_v5.cuh), cotangents in the eager form between
+// the steps.  D[k * 3 + A] = forward D (internal component A) after k steps: full-grid arrays, or (boxed) the
+// design-box record.
+template <typename T, typename AT>
+int adjoint_v5_sweep(cev_fdtd* p, const AdjArgs<T, AT>& a, int64_t nsteps, const double* gbar, const void* const* D, int boxed,
+                     cudaStream_t s) {
+    StepArgs<T, AT> aH, aED;
+    adjoint_v5_args(p, a, aH, aED);
+    ProbeTable pr;
+    fill_probe_table(p, pr);
+    const dim3 blk(64, 4);
+    const dim3 grd((a.Nz + 63) / 64, (a.Ny + 3) / 4, a.Nx);
+    if (grd.y > 65535 || grd.z > 65535) return fail("adjoint kernels: grid extent too large");
+    k_adj_Dlocal<T, AT><<<grd, blk, 0, s>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    for (int64_t k = nsteps; k >= 1; --k) {
+        if (gbar && p->n_slots > 0) {
+            k_adj_seed_eager<T, AT><<<p->n_slots, 128, 0, s>>>(a, pr, (const int32_t*)p->pr_owner.p, gbar + (k - 1) * p->nprobe,
+                                                               (const T*)D[k * 3], (const T*)D[k * 3 + 1], (const T*)D[k * 3 + 2], boxed);
+            CUDA_TRY(cudaGetLastError());
+        }
+        if (v5_launch_adj_H<T, AT>(p->v5, aH, p->tma_rows, p->tma_stages_adjH, s)) return fail("%s", v5_last_error());
+        if (v5_launch_adj_ED<T, AT>(p->v5, aED, D + (k - 1) * 3, a.G, a.gb, k > 1 ? 1 : 0, boxed, p->tma_rows, p->tma_stages_adjED, s))
+            return fail("%s", v5_last_error());
+    }
+    return 0;
+}
+
 // One checkpoint segment of the reverse sweep, entirely on the device queue: recompute the forward steps from the
 // segment's start state keeping D after every step (hist[k] = D after k steps; hist[0] is the start D), then the
 // transposed steps in reverse order, each preceded by the probe-series seeds of its time step.
@@ -1309,31 +1374,10 @@ int adjoint_run(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* 
     if (fill_adj(p, &fwd, adj, a)) return -1;
     const bool seeds = gbar && p->n_slots > 0;
     if (adjoint_v5_ok(p, a)) {
-        // tensor-map kernels, cotangents in the eager form between the segment's steps (adjoint_v5.cuh)
-        StepArgs<T, AT> aH, aED;
-        adjoint_v5_args(p, a, aH, aED);
-        ProbeTable pr;
-        fill_probe_table(p, pr);
-        const dim3 blk(64, 4);
-        const dim3 grd((a.Nz + 63) / 64, (a.Ny + 3) / 4, a.Nx);
-        if (grd.y > 65535 || grd.z > 65535) return fail("adjoint kernels: grid extent too large");
-        k_adj_Dlocal<T, AT><<<grd, blk, 0, s>>>(a);
-        CUDA_TRY(cudaGetLastError());
-        for (int64_t k = nsteps; k >= 1; --k) {
-            if (seeds) {
-                const T* Dk[3];
-                for (int A = 0; A < 3; ++A) Dk[A] = (const T*)hist[k][p->to_logical(A)];
-                k_adj_seed_eager<T, AT><<<p->n_slots, 128, 0, s>>>(a, pr, (const int32_t*)p->pr_owner.p,
-                                                                   gbar + (k - 1) * p->nprobe, Dk[0], Dk[1], Dk[2]);
-                CUDA_TRY(cudaGetLastError());
-            }
-            if (v5_launch_adj_H<T, AT>(p->v5, aH, p->tma_rows, p->tma_stages_adjH, s)) return fail("%s", v5_last_error());
-            const void* Dprev[3];
-            for (int A = 0; A < 3; ++A) Dprev[A] = hist[k - 1][p->to_logical(A)];
-            if (v5_launch_adj_ED<T, AT>(p->v5, aED, Dprev, a.G, a.gb, k > 1 ? 1 : 0, p->tma_rows, p->tma_stages_adjED, s))
-                return fail("%s", v5_last_error());
-        }
-        return 0;
+        std::vector<const void*> slots((size_t)(nsteps + 1) * 3);
+        for (int64_t k = 0; k <= nsteps; ++k)
+            for (int A = 0; A < 3; ++A) slots[k * 3 + A] = hist[k][p->to_logical(A)];
+        return adjoint_v5_sweep<T, AT>(p, a, nsteps, seeds ? gbar : nullptr, slots.data(), 0, s);
     }
     for (int64_t k = nsteps; k >= 1; --k) {
         if (seeds) {
@@ -1344,6 +1388,29 @@ int adjoint_run(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* 
         if (launch_adjoint_step<T, AT>(p, &fwd, adj, s)) return -1;
     }
     return 0;
+}
+
+// The reverse sweep WITHOUT recomputation: the transposed step is linear in the cotangents and needs the forward
+// solution only for dL/d(1/eps) += lE D, which is only wanted inside the design box -- so the forward run records D of
+// that box after every step (cev_fdtd_set_recorder) and the sweep reads the record.
+template <typename T, typename AT>
+int adjoint_run_boxed(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* gbar, const void* rec, const cev_adjoint* adj,
+                      cudaStream_t s) {
+    cev_state fwd;
+    memset(&fwd, 0, sizeof fwd);
+    for (int c = 0; c < 3; ++c) {
+        fwd.inv_eps[c] = st->inv_eps[c];
+        fwd.D[c] = const_cast<void*>(st->inv_eps[c]);       // (fill_adj wants a non-NULL forward D; the sweep reads the record instead)
+    }
+    AdjArgs<T, AT> a;
+    if (fill_adj(p, &fwd, adj, a)) return -1;
+    if (!adjoint_v5_ok(p, a)) return fail("cev_fdtd_adjoint_run_boxed needs a grid the tensor-map adjoint kernels serve (cev_fdtd_adjoint_boxed_supported) and adj->gC");
+    const int64_t n = (int64_t)(a.gb[1] - a.gb[0]) * (a.gb[3] - a.gb[2]) * (a.gb[5] - a.gb[4]);
+    if (n <= 0) return fail("cev_fdtd_adjoint_run_boxed: empty g_box");
+    std::vector<const void*> slots((size_t)(nsteps + 1) * 3);
+    for (int64_t k = 0; k <= nsteps; ++k)
+        for (int A = 0; A < 3; ++A) slots[k * 3 + A] = (const T*)rec + (k * 3 + A) * n;
+    return adjoint_v5_sweep<T, AT>(p, a, nsteps, p->n_slots > 0 ? gbar : nullptr, slots.data(), 1, s);
 }
 
 #define DISPATCH(plan, fn, ...)                                                       \
@@ -1668,6 +1735,42 @@ int cev_fdtd_adjoint_run(cev_fdtd* p, const cev_state* st, int64_t nsteps, const
     return DISPATCH(p, adjoint_run, p, st, nsteps, p->n_src_pts > 0 ? waveform : nullptr, gbar, D_hist, adj, (cudaStream_t)stream);
 }
 
+int cev_fdtd_adjoint_boxed_supported(const cev_fdtd* p) {
+    if (!p) return 0;
+    const int V = p->dtype == CEV_F64 ? 2 : 4;
+    if (p->adjoint_variant == 1 || p->perm[0] != 0 || p->perm[1] != 1 || p->perm[2] != 2 || p->on != 63u) return 0;
+    if (p->N[1] < p->tma_rows || p->N[1] % p->tma_rows != 0 || p->N[2] % V != 0 || p->N[2] < 32 * V) return 0;
+    if (p->adjoint_variant != 2 && (int64_t)p->N[1] * p->N[2] < (1 << 14)) return 0;
+    return 1;
+}
+
+int cev_fdtd_set_recorder(cev_fdtd* p, const int64_t box[6], void* buf, int64_t capacity) {
+    if (!p) return fail("NULL argument");
+    if (!buf || !box) {
+        p->rec = cev_fdtd::Recorder();
+        return 0;
+    }
+    if (p->perm[0] != 0 || p->perm[1] != 1 || p->perm[2] != 2) return fail("the D-box recorder needs a 3-D grid");
+    if (capacity <= 0) return fail("recorder capacity must be positive");
+    for (int A = 0; A < 3; ++A)
+        if (box[2 * A] < 0 || box[2 * A + 1] > p->Nl[A] || box[2 * A] >= box[2 * A + 1]) return fail("recorder box outside the grid");
+    p->rec.buf = buf;
+    p->rec.capacity = capacity;
+    p->rec.count = 0;
+    for (int q = 0; q < 6; ++q) p->rec.box[q] = (int)box[q];
+    return 0;
+}
+
+int cev_fdtd_adjoint_run_boxed(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* gbar, const void* D_box_record,
+                               const cev_adjoint* adj, void* stream) {
+    if (!p || !st || !D_box_record || !adj) return fail("NULL argument");
+    if (nsteps < 0) return fail("nsteps must be >= 0");
+    if (nsteps == 0) return 0;
+    if (p->halo.on()) return fail("cev_fdtd_adjoint_run_boxed steps a whole (periodic) grid");
+    DeviceGuard guard(p->device);
+    return DISPATCH(p, adjoint_run_boxed, p, st, nsteps, gbar, D_box_record, adj, (cudaStream_t)stream);
+}
+
 int cev_fdtd_adjoint_seed(cev_fdtd* p, const cev_state* fwd, const cev_adjoint* adj, const double* gbar_row, void* stream) {
     if (!p || !fwd || !adj || !gbar_row) return fail("NULL argument");
     DeviceGuard guard(p->device);
@@ -1898,6 +2001,7 @@ int cev_fdtd_run_fused(cev_fdtd* p, const cev_state* st, const cev_state* shadow
     if (p->n_src_pts > 0 && !waveform) return fail("plan has sources but waveform is NULL");
     if (p->n_slots > 0 && !partials) return fail("plan has probes but partials is NULL");
     if (st->D_xhi[1] || st->D_xhi[2] || st->H_xlo[1] || st->H_xlo[2]) return fail("cev_fdtd_run_fused steps a whole (periodic) grid; slabs are driven per half-step");
+    if (p->rec.buf) return fail("the D-box recorder works with cev_fdtd_run, not cev_fdtd_run_fused");
     DeviceGuard guard(p->device);
     return DISPATCH(p, run_loop_fused, p, st, shadow, nsteps, p->n_src_pts > 0 ? waveform : nullptr, partials,
                     (cudaStream_t)stream);

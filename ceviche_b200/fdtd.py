@@ -555,7 +555,7 @@ class fdtd:
         waveforms = self._prepare_run(steps, sources, probes, waveforms)
         return autodiff.jvp_run(self, steps, waveforms, eps_tangents)
 
-    def _run_raw(self, steps, waveforms, refresh=True):
+    def _run_raw(self, steps, waveforms, refresh=True, fused=True):
         plan = self._ensure_plan()
         with torch.cuda.device(self.device):
             if self._published:   # the in-place loop must not touch tensors handed out earlier
@@ -570,7 +570,7 @@ class fdtd:
                 ang = (-2 * np.pi * self.dt) * n[:, None] * torch.as_tensor(self._mon_freqs, device=self.device)[None, :]
                 phasors = torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).contiguous()
                 _lib.check(plan.lib.cev_fdtd_bind_monitors(plan.handle, _ptr(phasors), _ptr(self._mon_acc)))
-            if self._use_fused(steps) and not monitoring:
+            if fused and self._use_fused(steps) and not monitoring:
                 # one kernel per time step (H and D half-steps fused): needs ping-pong scratch for H, D, ICE, IH
                 sh = self._shadow_state()
                 _lib.check(plan.lib.cev_fdtd_run_fused(plan.handle, C.byref(st), C.byref(sh), steps, _ptr(waveforms),

@@ -202,6 +202,20 @@ int cev_fdtd_adjoint_run(cev_fdtd* plan, const cev_state* st, int64_t nsteps, co
                          void* const (*D_hist)[3], const cev_adjoint* adj, void* stream);
 int cev_fdtd_adjoint_seed(cev_fdtd* plan, const cev_state* fwd, const cev_adjoint* adj, const double* gbar_row,
                           void* stream);
+/* Reverse sweep WITHOUT recomputation, for gradients wanted inside a design box only.  The transposed step is linear
+ * in the cotangents; the forward solution enters only dL/d(1/eps) += lE * D, so it suffices to keep D of the box:
+ *   cev_fdtd_set_recorder(plan, box, buf, capacity): from now on every time step of cev_fdtd_run stores D (three
+ *     components, the plan's storage type, C-order [3][bx][by][bz]) of box = {x0, x1, y0, y1, z0, z1} after the step
+ *     into the next of `capacity` slots of the caller's device buffer `buf`; buf = NULL switches it off.
+ *   cev_fdtd_adjoint_run_boxed(plan, st, nsteps, gbar, record, adj, stream): the nsteps transposed steps in reverse
+ *     order with the probe-series seeds gbar [nsteps, n_probes] (device, nullable); only st->inv_eps is read.
+ *     record = nsteps + 1 slots: slot 0 holds D of the box BEFORE the first step, slot k after step k;
+ *     adj->g_box must be the recorded box and adj->gC must be set.
+ * Served by the tensor-map kernels only (csrc/adjoint_v5.cuh): cev_fdtd_adjoint_boxed_supported(plan) tells. */
+int cev_fdtd_adjoint_boxed_supported(const cev_fdtd* plan);
+int cev_fdtd_set_recorder(cev_fdtd* plan, const int64_t box[6], void* buf, int64_t capacity);
+int cev_fdtd_adjoint_run_boxed(cev_fdtd* plan, const cev_state* st, int64_t nsteps, const double* gbar,
+                               const void* D_box_record, const cev_adjoint* adj, void* stream);
 
 /* ---- x-slab decomposition over the GPUs of one box: halo planes through peer-mapped memory ----
  * The reference has no parallel path (single-thread numpy); this is the multi-GPU boundary SURVEY 8(b) sketched as
