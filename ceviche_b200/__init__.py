@@ -5,7 +5,7 @@ its caller loop and its eps_r derivatives -- nothing else of ceviche (see DESIGN
 from .constants import C_0, EPSILON_0, ETA_0, MU_0
 from .fdtd import fdtd
 from .jacobians import jacobian
-from . import modes, optimizers, utils
+from . import modes, optimizers, parametrization, utils
 
 __version__ = "0.1.0"
-__all__ = ["fdtd", "jacobian", "utils", "modes", "optimizers", "C_0", "EPSILON_0", "MU_0", "ETA_0"]
+__all__ = ["fdtd", "jacobian", "utils", "modes", "optimizers", "parametrization", "C_0", "EPSILON_0", "MU_0", "ETA_0"]

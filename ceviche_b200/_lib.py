@@ -70,12 +70,14 @@ def _declare(lib):
         "cev_fdtd_adjoint_step": [C.c_void_p, P(cev_state), P(cev_adjoint), C.c_void_p],
         "cev_fdtd_adjoint_seed": [C.c_void_p, P(cev_state), P(cev_adjoint), C.c_void_p, C.c_void_p],
         "cev_fdtd_adjoint_run": [C.c_void_p, P(cev_state), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, P(cev_adjoint), C.c_void_p],
+        "cev_fdtd_adjoint_part": [C.c_void_p, C.c_int, P(cev_state), P(cev_adjoint), P(c_void_p3), C.c_void_p],
         "cev_fdtd_adjoint_boxed_supported": [C.c_void_p],
         "cev_fdtd_set_recorder": [C.c_void_p, P(C.c_int64), C.c_void_p, C.c_int64],
         "cev_fdtd_adjoint_run_boxed": [C.c_void_p, P(cev_state), C.c_int64, C.c_void_p, C.c_void_p, P(cev_adjoint), C.c_void_p],
         "cev_fdtd_set_sources": [C.c_void_p, C.c_int, P(cev_points)],
         "cev_fdtd_set_probes": [C.c_void_p, C.c_int, P(cev_points), P(C.c_int64)],
         "cev_fdtd_probe_slots": [C.c_void_p, P(C.c_int32)],
+        "cev_fdtd_fold_probes": [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p],
         "cev_fdtd_set_monitors": [C.c_void_p, C.c_int, P(cev_points), C.c_int, P(C.c_int64)],
         "cev_fdtd_bind_monitors": [C.c_void_p, C.c_void_p, C.c_void_p],
         "cev_fdtd_run": [C.c_void_p, P(cev_state), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
@@ -100,9 +102,9 @@ def _declare(lib):
 EXPORTS = ("cev_last_error", "cev_abi_version", "cev_fdtd_create", "cev_fdtd_destroy", "cev_fdtd_pml_shapes",
            "cev_fdtd_set_option",
            "cev_fdtd_step_H", "cev_fdtd_step_D", "cev_fdtd_compute_E", "cev_fdtd_set_sources",
-           "cev_fdtd_set_probes", "cev_fdtd_probe_slots", "cev_fdtd_set_monitors", "cev_fdtd_bind_monitors", "cev_fdtd_run", "cev_fdtd_run_fused", "cev_fdtd_step_H_ex", "cev_fdtd_step_D_ex",
+           "cev_fdtd_set_probes", "cev_fdtd_probe_slots", "cev_fdtd_fold_probes", "cev_fdtd_set_monitors", "cev_fdtd_bind_monitors", "cev_fdtd_run", "cev_fdtd_run_fused", "cev_fdtd_step_H_ex", "cev_fdtd_step_D_ex",
            "cev_fdtd_sample_probes", "cev_fdtd_jvp_run", "cev_fdtd_adjoint_step", "cev_fdtd_adjoint_seed", "cev_fdtd_adjoint_run",
-           "cev_fdtd_adjoint_boxed_supported", "cev_fdtd_set_recorder", "cev_fdtd_adjoint_run_boxed",
+           "cev_fdtd_adjoint_part", "cev_fdtd_adjoint_boxed_supported", "cev_fdtd_set_recorder", "cev_fdtd_adjoint_run_boxed",
            "cev_fdtd_halo_layout", "cev_halo_alloc", "cev_halo_open", "cev_halo_close", "cev_halo_free",
            "cev_fdtd_halo_attach", "cev_fdtd_halo_push_static", "cev_fdtd_halo_reset", "cev_fdtd_halo_error")
 

@@ -341,4 +341,5 @@ def jvp_run(sim, steps, waveforms, eps_tangents):
         if sim._n_probes == 0:
             return (torch.zeros((steps, 0), dtype=torch.float64, device=sim.device),
                     torch.zeros((B, steps, 0), dtype=torch.float64, device=sim.device))
-        return partials @ sim._slot_fold, tpart @ sim._slot_fold
+        from .fdtd import fold_probes
+        return (fold_probes(plan, partials, sim._n_probes, sim._stream()), fold_probes(plan, tpart, sim._n_probes, sim._stream()))

@@ -325,4 +325,84 @@ __global__ void k_adj_seed_eager(const AdjArgs<T, AT> a, ProbeTable pr, const in
     }
 }
 
+// ---- the transposed step in three parts with STORED stencil inputs and x-halo planes: the form the x-slab
+// decomposition drives (one process per GPU, slab.py): k_adj_Dlocal (above; cell-local D part: lD -> m1 lD + gID,
+// gC), then the two stencil parts below.  A slab's +x / -x neighbour planes of gC / gC2 (components y, z: the only
+// ones differenced along x) come from the neighbouring rank; NULL = periodic wrap inside the array.
+template <typename T, typename AT>
+__global__ void __launch_bounds__(256) k_adj_H_stored(const AdjArgs<T, AT> a, const T* gCy_hi, const T* gCz_hi) {
+    CEV_CELL_INDEX();
+    const int jp = (j + 1 == a.Ny) ? 0 : j + 1;
+    const int kp = (k + 1 == a.Nz) ? 0 : k + 1;
+    const int64_t row = (int64_t)j * a.Nz + k;
+    const int64_t o_jp = i * plane + (int64_t)jp * a.Nz + k;
+    const int64_t o_kp = i * plane + (int64_t)j * a.Nz + kp;
+    const AT inv = a.inv_dL;
+    const AT gx = (AT)a.gC[0][o], gy = (AT)a.gC[1][o], gz = (AT)a.gC[2][o];
+    AT gy_ip, gz_ip;
+    if (i + 1 < a.Nx) {
+        gy_ip = (AT)a.gC[1][o + plane];
+        gz_ip = (AT)a.gC[2][o + plane];
+    } else {
+        gy_ip = gCy_hi ? (AT)gCy_hi[row] : (AT)a.gC[1][row];
+        gz_ip = gCz_hi ? (AT)gCz_hi[row] : (AT)a.gC[2][row];
+    }
+    // curl_E (forward differences, derivatives.py:16-22) of gC
+    const AT cx = ((AT)a.gC[2][o_jp] - gz) * inv - ((AT)a.gC[1][o_kp] - gy) * inv;
+    const AT cy = ((AT)a.gC[0][o_kp] - gx) * inv - (gz_ip - gz) * inv;
+    const AT cz = (gy_ip - gy) * inv - ((AT)a.gC[0][o_jp] - gx) * inv;
+    const AT ux = a.uH[0][i], uy = a.uH[1][j], uz = a.uH[2][k];
+    const AT rx = a.rH[0][i], ry = a.rH[1][j], rz = a.rH[2][k];
+    const int mx = a.mapH[0][i], my = a.mapH[1][j], mz = a.mapH[2][k];
+    const AT s = -a.cdt;
+    {
+        const int64_t ic = (mx >= 0) ? ((int64_t)mx * a.Ny + j) * a.Nz + k : -1;
+        const int64_t is = (my >= 0 && mz >= 0) ? ((int64_t)i * a.nH[1] + my) * a.nH[2] + mz : -1;
+        a.gC2[0][o] = (T)adj_component<T, AT>((AT)a.lH[0][o] + cx, uy, ry, uz, rz, ux, s, a.lH[0], o, a.lICE[0], ic, a.lIH[0], is);
+    }
+    {
+        const int64_t ic = (my >= 0) ? ((int64_t)i * a.nH[1] + my) * a.Nz + k : -1;
+        const int64_t is = (mx >= 0 && mz >= 0) ? ((int64_t)mx * a.Ny + j) * a.nH[2] + mz : -1;
+        a.gC2[1][o] = (T)adj_component<T, AT>((AT)a.lH[1][o] + cy, ux, rx, uz, rz, uy, s, a.lH[1], o, a.lICE[1], ic, a.lIH[1], is);
+    }
+    {
+        const int64_t ic = (mz >= 0) ? ((int64_t)i * a.Ny + j) * a.nH[2] + mz : -1;
+        const int64_t is = (mx >= 0 && my >= 0) ? ((int64_t)mx * a.nH[1] + my) * a.Nz + k : -1;
+        a.gC2[2][o] = (T)adj_component<T, AT>((AT)a.lH[2][o] + cz, ux, rx, uy, ry, uz, s, a.lH[2], o, a.lICE[2], ic, a.lIH[2], is);
+    }
+}
+
+// lE = curl_H(gC2) (backward differences, derivatives.py:24-30); lD += mE lE (lD already holds the cell-local D
+// part); G_mE += lE D_{n-1} inside the design box
+template <typename T, typename AT>
+__global__ void __launch_bounds__(256) k_adj_E_stored(const AdjArgs<T, AT> a, const T* gC2y_lo, const T* gC2z_lo) {
+    CEV_CELL_INDEX();
+    const int jm = (j == 0) ? a.Ny - 1 : j - 1;
+    const int km = (k == 0) ? a.Nz - 1 : k - 1;
+    const int64_t row = (int64_t)j * a.Nz + k;
+    const int64_t o_jm = i * plane + (int64_t)jm * a.Nz + k;
+    const int64_t o_km = i * plane + (int64_t)j * a.Nz + km;
+    const AT inv = a.inv_dL;
+    const AT c0 = (AT)a.gC2[0][o], c1 = (AT)a.gC2[1][o], c2 = (AT)a.gC2[2][o];
+    AT c1_im, c2_im;
+    if (i > 0) {
+        c1_im = (AT)a.gC2[1][o - plane];
+        c2_im = (AT)a.gC2[2][o - plane];
+    } else {
+        const int64_t last = (int64_t)(a.Nx - 1) * plane + row;
+        c1_im = gC2y_lo ? (AT)gC2y_lo[row] : (AT)a.gC2[1][last];
+        c2_im = gC2z_lo ? (AT)gC2z_lo[row] : (AT)a.gC2[2][last];
+    }
+    AT lE[3];
+    lE[0] = (c2 - (AT)a.gC2[2][o_jm]) * inv - (c1 - (AT)a.gC2[1][o_km]) * inv;
+    lE[1] = (c0 - (AT)a.gC2[0][o_km]) * inv - (c2 - c2_im) * inv;
+    lE[2] = (c1 - c1_im) * inv - (c0 - (AT)a.gC2[0][o_jm]) * inv;
+    const bool in_box = i >= a.gb[0] && i < a.gb[1] && j >= a.gb[2] && j < a.gb[3] && k >= a.gb[4] && k < a.gb[5];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        a.lD[c][o] = (T)((AT)a.lD[c][o] + (AT)a.mE[c][o] * lE[c]);
+        if (in_box && a.G[c]) a.G[c][o] += (double)lE[c] * (double)a.Dprev[c][o];
+    }
+}
+
 }  // namespace cev

@@ -1323,6 +1323,26 @@ void adjoint_v5_args(cev_fdtd* p, const AdjArgs<T, AT>& a, StepArgs<T, AT>& aH, 
     if (!p->v5) p->v5 = v5_cache_create();
 }
 
+// One part of the transposed step with stored stencil inputs and caller-supplied x-halo planes (x-slabs).
+template <typename T, typename AT>
+int launch_adjoint_part(cev_fdtd* p, int part, const cev_state* fwd, const cev_adjoint* adj, const void* const halo[3], cudaStream_t s) {
+    AdjArgs<T, AT> a;
+    if (fill_adj(p, fwd, adj, a)) return -1;
+    for (int c = 0; c < 3; ++c)
+        if (!a.gC[c]) return fail("cev_fdtd_adjoint_part needs adj->gC");
+    const dim3 blk(64, 4);
+    const dim3 grd((a.Nz + 63) / 64, (a.Ny + 3) / 4, a.Nx);
+    if (grd.y > 65535 || grd.z > 65535) return fail("adjoint kernels: grid extent too large");
+    const T* h1 = halo ? (const T*)halo[p->to_logical(1)] : nullptr;
+    const T* h2 = halo ? (const T*)halo[p->to_logical(2)] : nullptr;
+    if ((h1 == nullptr) != (h2 == nullptr)) return fail("cev_fdtd_adjoint_part: give both halo planes or none");
+    if (part == 0) k_adj_Dlocal<T, AT><<<grd, blk, 0, s>>>(a);
+    else if (part == 1) k_adj_H_stored<T, AT><<<grd, blk, 0, s>>>(a, h1, h2);
+    else k_adj_E_stored<T, AT><<<grd, blk, 0, s>>>(a, h1, h2);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // The reverse sweep of nsteps steps with the tensor-map kernels (adjoint_v5.cuh), cotangents in the eager form between
 // the steps.  D[k * 3 + A] = forward D (internal component A) after k steps: full-grid arrays, or (boxed) the
 // design-box record.
@@ -1735,6 +1755,33 @@ int cev_fdtd_adjoint_run(cev_fdtd* p, const cev_state* st, int64_t nsteps, const
     return DISPATCH(p, adjoint_run, p, st, nsteps, p->n_src_pts > 0 ? waveform : nullptr, gbar, D_hist, adj, (cudaStream_t)stream);
 }
 
+// series[t, p] = sum of the partial sums of probe p's slots, in slot order: a fixed summation order whatever the
+// number of rows (a GEMM with the 0/1 fold matrix picks its tiling, hence its order, by shape)
+__global__ void k_fold_slots(const double* __restrict__ partials, const int32_t* __restrict__ owner, int n_slots, int n_probes,
+                             int64_t rows, double* __restrict__ out) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= rows * n_probes) return;
+    const int64_t t = q / n_probes;
+    const int pr = (int)(q % n_probes);
+    double acc = 0.0;
+    for (int sl = 0; sl < n_slots; ++sl)
+        if (owner[sl] == pr) acc += partials[t * n_slots + sl];
+    out[q] = acc;
+}
+
+int cev_fdtd_fold_probes(cev_fdtd* p, const double* partials, int64_t rows, double* series, void* stream) {
+    if (!p || !series) return fail("NULL argument");
+    if (rows < 0) return fail("rows must be >= 0");
+    if (rows == 0 || p->nprobe == 0) return 0;
+    if (!partials && p->n_slots > 0) return fail("partials is NULL");
+    DeviceGuard guard(p->device);
+    const int64_t n = rows * p->nprobe;
+    k_fold_slots<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(partials, (const int32_t*)p->pr_owner.p, p->n_slots,
+                                                                                p->nprobe, rows, series);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 int cev_fdtd_adjoint_boxed_supported(const cev_fdtd* p) {
     if (!p) return 0;
     const int V = p->dtype == CEV_F64 ? 2 : 4;
@@ -1769,6 +1816,15 @@ int cev_fdtd_adjoint_run_boxed(cev_fdtd* p, const cev_state* st, int64_t nsteps,
     if (p->halo.on()) return fail("cev_fdtd_adjoint_run_boxed steps a whole (periodic) grid");
     DeviceGuard guard(p->device);
     return DISPATCH(p, adjoint_run_boxed, p, st, nsteps, gbar, D_box_record, adj, (cudaStream_t)stream);
+}
+
+int cev_fdtd_adjoint_part(cev_fdtd* p, int part, const cev_state* fwd, const cev_adjoint* adj, const void* const halo[3],
+                          void* stream) {
+    if (!p || !fwd || !adj) return fail("NULL argument");
+    if (part < 0 || part > 2) return fail("part must be 0 (cell-local D part), 1 (H part) or 2 (E part)");
+    if (halo && !p->x_is_x()) return fail("x-halo planes need Ny > 1 or Nz > 1 (no slab decomposition of a 1-D grid)");
+    DeviceGuard guard(p->device);
+    return DISPATCH(p, launch_adjoint_part, p, part, fwd, adj, halo, (cudaStream_t)stream);
 }
 
 int cev_fdtd_adjoint_seed(cev_fdtd* p, const cev_state* fwd, const cev_adjoint* adj, const double* gbar_row, void* stream) {

@@ -112,6 +112,17 @@ class _Plan:
             pass
 
 
+def fold_probes(plan, partials, n_probes, stream):
+    """Slot partial sums [..., n_slots] -> probe series [..., n_probes], summed in slot order on the device
+    (cev_fdtd_fold_probes: the same bits whatever the number of rows; a matmul with a 0/1 matrix is not)."""
+    out = torch.empty(partials.shape[:-1] + (n_probes,), dtype=torch.float64, device=partials.device)
+    rows = out.numel() // max(1, n_probes)
+    if rows == 0 or n_probes == 0:
+        return out
+    _lib.check(plan.lib.cev_fdtd_fold_probes(plan.handle, _ptr(partials), rows, _ptr(out), stream))
+    return out
+
+
 class fdtd:
 
     def __new__(cls, eps_r=None, dL=None, npml=None, *, devices=None, global_shape=None, **kw):
@@ -585,7 +596,7 @@ class fdtd:
                 self._refresh_E()
             if self._n_probes == 0:
                 return torch.zeros((steps, 0), dtype=torch.float64, device=self.device)
-            return partials @ self._slot_fold
+            return fold_probes(plan, partials, self._n_probes, self._stream())
 
     def _use_fused(self, steps):
         """The fused full-step kernel (step_v4.cuh) moves 15 instead of 21 words per cell but recomputes a halo.

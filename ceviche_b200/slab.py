@@ -79,7 +79,7 @@ class CudaSlabBackend:
         z = lambda s: torch.zeros(s, dtype=dtype, device=device)
         self.H = [z(shape_local) for _ in range(3)]
         self.D = [z(shape_local) for _ in range(3)]
-        self.mE = [m.to(device=device, dtype=dtype).contiguous() for m in inv_eps]
+        self.mE = [m.detach().to(device=device, dtype=dtype).contiguous() for m in inv_eps]
         shapes = self.plan.pml_shapes
         self.pml = {fam: [z(shapes[f * 3 + c]) for c in range(3)] for f, fam in enumerate(_PML_FAMILIES)}
         plane = (self.Ny, self.Nz)
@@ -175,7 +175,11 @@ class CudaSlabBackend:
                                               self.partials.data_ptr() if self.n_slots and steps else None, self._s()))
 
     def series(self):
-        return self.partials @ self.fold
+        from .fdtd import fold_probes
+        if self.fold.shape[1] == 0:
+            return torch.zeros((self.partials.shape[0], 0), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            return fold_probes(self.plan, self.partials, self.fold.shape[1], self._s())
 
     def field(self, key):
         c = "xyz".index(key[1])
@@ -249,13 +253,15 @@ class SlabFDTD:
             e = e.to(device)
         own = e[1:]
         inv_eps = [1 / ((own + e[:-1]) / 2), 1 / ((own + torch.roll(own, 1, 1)) / 2), 1 / ((own + torch.roll(own, 1, 2)) / 2)]
+        self._mE64 = inv_eps              # (carries the autograd graph back to eps_r when it requires grad)
+        self.design_region = None         # ((x0, x1), (y0, y1), (z0, z1)) GLOBAL cells: see fdtd.design_region
         local_shape = (self.nx, self.Ny, self.Nz)
         if backend_factory is None:
             dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
             self.be = CudaSlabBackend(dev, dtype, local_shape, dL, self.dt, sH, sD, inv_eps,
                                       arith_f64=arith in ("f64", torch.float64))
         else:
-            self.be = backend_factory(local_shape, dL, self.dt, sH, sD, [m.cpu().numpy() for m in inv_eps])
+            self.be = backend_factory(local_shape, dL, self.dt, sH, sD, [m.detach().cpu().numpy() for m in inv_eps])
         self.right = (self.rank + 1) % self.P
         self.left = (self.rank - 1) % self.P
         self._pending = []
@@ -409,7 +415,7 @@ class SlabFDTD:
         self.n_probes = len(probes)
         self.n_sources = len(sources)
 
-    def run(self, steps, sources=None, probes=None, waveforms=None):
+    def run(self, steps, sources=None, probes=None, waveforms=None, checkpoint_every=None):
         """`steps` leap-frog steps (the loop of ceviche/utils.py:325-331 on every slab).  Same arguments as the
         single-GPU `fdtd.run`: sources [(component, profile[, waveform])] / probes [(field key, mask)] (None = keep
         the prepared ones), waveforms [steps, n_sources].  Returns the probe series [steps, n_probes] summed over
@@ -434,6 +440,15 @@ class SlabFDTD:
             wf = wf.to(be.device)
         if tuple(wf.shape) != (steps, getattr(self, "n_sources", wf.shape[1] if wf.dim() == 2 else 0)):
             raise ValueError("waveforms must have shape (steps, n_sources)")
+        if be.is_cuda and torch.is_grad_enabled() and any(bool(m.requires_grad) for m in self._mE64):
+            # eps_r requires grad: the run is an autograd node whose backward is the adjoint FDTD on the slabs
+            if self.t_index != 0:
+                raise RuntimeError("a differentiable run() must start from initialize_fields()")
+            return _SlabRunFn.apply(self, steps, wf, checkpoint_every, *self._mE64)
+        return self._run_plain(steps, wf)
+
+    def _run_plain(self, steps, wf):
+        be, nx, P = self.be, self.nx, self.P
         be.new_partials(steps)
         if self.path in ("peer", "none") and be.is_cuda:
             be.run_c(steps, wf)                   # the time loop in C; peer path: halos travel inside the kernels
@@ -465,6 +480,29 @@ class SlabFDTD:
             if self.path == "peer":
                 self._peer_check()
         return series
+
+    def _local_grad_box(self):
+        """design_region (global cells) -> this slab's part of the G_mE box as six local ints (x range clipped to the slab,
+        possibly empty), or None = everywhere.  One more cell on the high side of every axis: eps_r[i, j, k] enters the
+        Yee averages of cells (i..i+1, j..j+1, k..k+1) (utils.py:167-174)."""
+        if self.design_region is None:
+            return None
+        (x0, x1), (y0, y1), (z0, z1) = [(int(a), int(b)) for a, b in self.design_region]
+        if x1 + 1 > self.Nx or y1 + 1 > self.Ny or z1 + 1 > self.Nz:
+            return None
+        lx0, lx1 = max(x0, self.lo) - self.lo, min(x1 + 1, self.hi) - self.lo
+        if lx1 <= lx0:
+            return [1, 1, 0, 0, 0, 0]      # the box does not touch this slab: an empty x-range
+        return [lx0, lx1, y0, y1 + 1, z0, z1 + 1]
+
+    def _restore_halos(self, peer):
+        """After the reverse sweep put the end-of-run state's halo planes back in place (a collective)."""
+        be = self.be
+        if peer:        # the exchange blocks were paused, not touched: they still hold the end-of-run planes
+            self.set_option("halo_pause", 0)
+        else:
+            self._exchange([be.D[1][0], be.D[2][0]], self.left, [be.D_hi[1], be.D_hi[2]], self.right)
+            self._wait()
 
     def forward(self, Jx=None, Jy=None, Jz=None):
         """One time step with dense GLOBAL J arrays (the reference's per-step call, fdtd.py:74-144), for API
@@ -522,6 +560,142 @@ class SlabFDTD:
             dist.broadcast(buf, src=r, group=self.group)
 
 
+class _AllReduceGrad(torch.autograd.Function):
+    """Identity whose backward sums the gradient over the ranks: every rank differentiates its own slab's share of the
+    objective w.r.t. the GLOBAL eps_r, and ends up with the complete gradient."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        if dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
+            if g.is_cuda:
+                dist.all_reduce(g, group=ctx.group)
+            else:                                   # NCCL groups reduce device tensors only
+                dev = torch.device("cuda", torch.cuda.current_device())
+                gd = g.to(dev)
+                dist.all_reduce(gd, group=ctx.group)
+                g = gd.to(g.device)
+        return g, None
+
+
+class _SlabRunFn(torch.autograd.Function):
+    """run() on x-slabs as an autograd node: forward = the plain slab run with state checkpoints every K steps;
+    backward = per segment, recompute the slab's forward steps keeping D per step, then the transposed steps in reverse
+    order (cev_fdtd_adjoint_part: cell-local D part, H part, E part) with one plane pair exchanged between the parts --
+    the +x plane of gC for the H part, the -x plane of gC2 for the E part, mirroring the forward half-steps' halos."""
+
+    @staticmethod
+    def forward(ctx, sim, steps, wf, every, mEx, mEy, mEz):
+        be = sim.be
+        every = max(1, int(every or np.ceil(np.sqrt(max(steps, 1)))))
+        ctx.sim, ctx.steps, ctx.wf = sim, steps, wf
+        ctx.checkpoints, chunks = [], []
+        for t0 in range(0, steps, every):
+            t1 = min(steps, t0 + every)
+            ctx.checkpoints.append((t0, t1, [t.clone() for t in be.H], [t.clone() for t in be.D],
+                                    {fam: [t.clone() for t in be.pml[fam]] for fam in _PML_FAMILIES}))
+            chunks.append(sim._run_plain(t1 - t0, wf[t0:t1]))
+        return torch.cat(chunks) if chunks else torch.zeros((0, sim.n_probes), dtype=torch.float64, device=be.device)
+
+    @staticmethod
+    def backward(ctx, gbar):
+        sim, be = ctx.sim, ctx.sim.be
+        lib, h = be.plan.lib, be.plan.handle
+        shape, dev, dt_ = (be.nx, be.Ny, be.Nz), be.device, be.dtype
+        P = sim.P
+        with torch.cuda.device(dev):
+            gbar = gbar.detach().to(torch.float64).contiguous()
+            z3 = lambda dtype=dt_: [torch.zeros(shape, dtype=dtype, device=dev) for _ in range(3)]
+            lH, lD, gC, gC2, G = z3(), z3(), z3(), z3(), z3(torch.float64)
+            lp = {fam: [torch.zeros_like(t) for t in be.pml[fam]] for fam in _PML_FAMILIES}
+            plane = (be.Ny, be.Nz)
+            gC_hi = [None] + [torch.zeros(plane, dtype=dt_, device=dev) for _ in range(2)]
+            gC2_lo = [None] + [torch.zeros(plane, dtype=dt_, device=dev) for _ in range(2)]
+            p3 = lambda ts: _lib.c_void_p3(*[None if (t is None or t.numel() == 0) else t.data_ptr() for t in ts])
+            adj = _lib.cev_adjoint()
+            adj.lH, adj.lD, adj.gC, adj.gC2, adj.G_mE = p3(lH), p3(lD), p3(gC), p3(gC2), p3(G)
+            for fam in _PML_FAMILIES:
+                setattr(adj, "l" + fam, p3(lp[fam]))
+            box = sim._local_grad_box()
+            if box is not None:
+                adj.g_box = (C.c_int64 * 6)(*box)
+            skip_G = box is not None and box[0] >= box[1]          # the design box does not touch this slab
+
+            def fwd_state(D):
+                st = _lib.cev_state()
+                st.D, st.inv_eps = p3(D), p3(be.mE)
+                return st
+
+            # the state at the end of the run comes back after the sweep (the recomputation runs in the slab's own arrays)
+            end = ([t.clone() for t in be.H], [t.clone() for t in be.D],
+                   {fam: [t.clone() for t in be.pml[fam]] for fam in _PML_FAMILIES}, sim.t_index)
+            peer = sim.path == "peer"
+            if peer:         # recompute with caller-owned halo planes (NCCL), the exchange blocks paused
+                sim.set_option("halo_pause", 1)
+            be.halo = P > 1
+            be._st = None
+            try:
+                for t0, t1, H0, D0, P0 in reversed(ctx.checkpoints):
+                    for dst, src in zip(be.H + be.D, H0 + D0):
+                        dst.copy_(src)
+                    for fam in _PML_FAMILIES:
+                        for dst, src in zip(be.pml[fam], P0[fam]):
+                            dst.copy_(src)
+                    n = t1 - t0
+                    hist = [[t.clone() for t in be.D]]
+                    be.new_partials(1)
+                    be._st = None
+                    if P > 1:     # D halo of the checkpoint time: plane 0 of the right neighbour
+                        sim._exchange([be.D[1][0], be.D[2][0]], sim.left, [be.D_hi[1], be.D_hi[2]], sim.right)
+                        sim._wait()
+                    for k in range(n):
+                        be.step_H(0, be.nx, -1)
+                        if P > 1:
+                            sim._exchange([be.H[1][be.nx - 1], be.H[2][be.nx - 1]], sim.right, [be.H_lo[1], be.H_lo[2]], sim.left)
+                            sim._wait()
+                        be.step_D(0, be.nx, -1, ctx.wf[t0 + k])
+                        if P > 1:
+                            sim._exchange([be.D[1][0], be.D[2][0]], sim.left, [be.D_hi[1], be.D_hi[2]], sim.right)
+                            sim._wait()
+                        hist.append([t.clone() for t in be.D])
+                    s = be._s()
+                    for k in range(n, 0, -1):
+                        if sim.n_probes:
+                            _lib.check(lib.cev_fdtd_adjoint_seed(h, C.byref(fwd_state(hist[k])), C.byref(adj), gbar[t0 + k - 1].data_ptr(), s))
+                        st = fwd_state(hist[k - 1])
+                        _lib.check(lib.cev_fdtd_adjoint_part(h, 0, C.byref(st), C.byref(adj), None, s))
+                        halo = None
+                        if P > 1:
+                            sim._exchange([gC[1][0], gC[2][0]], sim.left, [gC_hi[1], gC_hi[2]], sim.right)
+                            sim._wait()
+                            halo = C.byref(p3(gC_hi))
+                        _lib.check(lib.cev_fdtd_adjoint_part(h, 1, C.byref(st), C.byref(adj), halo, s))
+                        if P > 1:
+                            sim._exchange([gC2[1][be.nx - 1], gC2[2][be.nx - 1]], sim.right, [gC2_lo[1], gC2_lo[2]], sim.left)
+                            sim._wait()
+                            halo = C.byref(p3(gC2_lo))
+                        _lib.check(lib.cev_fdtd_adjoint_part(h, 2, C.byref(st), C.byref(adj), halo, s))
+                    del hist
+            finally:
+                for dst, src in zip(be.H + be.D, end[0] + end[1]):
+                    dst.copy_(src)
+                for fam in _PML_FAMILIES:
+                    for dst, src in zip(be.pml[fam], end[2][fam]):
+                        dst.copy_(src)
+                be.halo = sim.path == "nccl"
+                be._st = None
+                if P > 1:      # the halo planes / exchange blocks of the end-of-run state, for a following run()
+                    sim._restore_halos(peer)
+            if skip_G:
+                G = [torch.zeros_like(g) for g in G]
+        return (None, None, None, None, *G)
+
+
 def make_slab_fdtd(eps_r, dL, npml, *, devices, global_shape=None, dtype=torch.float64, device=None, arith=None,
                    group=None, path=None):
     """What `ceviche_b200.fdtd(eps_r, dL, npml, devices=[...])` builds: one SlabFDTD per process.  `devices` lists the
@@ -539,5 +713,7 @@ def make_slab_fdtd(eps_r, dL, npml, *, devices, global_shape=None, dtype=torch.f
         global_shape = tuple(e.shape)
         lo, hi = partition(global_shape[0], P)[rank]
         idx = torch.arange(lo - 1, hi) % global_shape[0]
+        if torch.is_tensor(e) and e.requires_grad:     # every rank ends up with the complete gradient w.r.t. eps_r
+            e = _AllReduceGrad.apply(e, group)
         eps_r = e[idx.to(e.device)]
     return SlabFDTD(global_shape, eps_r, dL, npml, dtype=dtype, device=device, group=group, path=path, arith=arith)

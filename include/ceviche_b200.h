@@ -157,6 +157,9 @@ int cev_fdtd_set_sources(cev_fdtd* plan, int nsrc, const cev_points* src);
 int cev_fdtd_set_probes(cev_fdtd* plan, int nprobe, const cev_points* probe, int64_t* n_slots);
 /* slot -> probe map (host array of n_slots ints) so the caller can fold partial sums. */
 int cev_fdtd_probe_slots(const cev_fdtd* plan, int32_t* slot_probe);
+/* Probe series from the slot partial sums: series[t, p] = sum over probe p's slots of partials[t, slot], in slot
+ * order (deterministic, independent of `rows`).  partials [rows, n_slots], series [rows, n_probes], device fp64. */
+int cev_fdtd_fold_probes(cev_fdtd* plan, const double* partials, int64_t rows, double* series, void* stream);
 
 /* Running-DFT monitors (frequency-domain fields of a region without storing its time series; replaces
  * storing field snapshots and transforming them, ceviche/utils.py:316-332 + 373-400).  Each monitor is a
@@ -202,6 +205,17 @@ int cev_fdtd_adjoint_run(cev_fdtd* plan, const cev_state* st, int64_t nsteps, co
                          void* const (*D_hist)[3], const cev_adjoint* adj, void* stream);
 int cev_fdtd_adjoint_seed(cev_fdtd* plan, const cev_state* fwd, const cev_adjoint* adj, const double* gbar_row,
                           void* stream);
+/* The transposed step in three parts with stored stencil inputs, for x-slabs (one process per GPU): the caller
+ * exchanges one plane pair between the parts, as the forward half-steps do.
+ *   part 0  cell-local D part: lD <- m1 lD + gID, gC <- m2 lD + gICH (lICH, lID advanced)
+ *   part 1  H part: gH = lH + curl_E(gC); halo = the +x neighbour plane (local i = nx) of gC: entries of the two
+ *           components differenced along x (y, z) = plane 0 of the right neighbour's gC; lH, gC2 written
+ *   part 2  E part: lE = curl_H(gC2); halo = the -x neighbour plane (local i = -1) of gC2 = the left neighbour's last
+ *           plane; lD += inv_eps lE, G_mE += lE D (fwd->D = D before the step) inside g_box
+ * halo = NULL: periodic wrap inside the array (then parts 0, 1, 2 in a row equal cev_fdtd_adjoint_step).
+ * Needs adj->gC. */
+int cev_fdtd_adjoint_part(cev_fdtd* plan, int part, const cev_state* fwd, const cev_adjoint* adj,
+                          const void* const halo[3], void* stream);
 /* Reverse sweep WITHOUT recomputation, for gradients wanted inside a design box only.  The transposed step is linear
  * in the cotangents; the forward solution enters only dL/d(1/eps) += lE * D, so it suffices to keep D of the box:
  *   cev_fdtd_set_recorder(plan, box, buf, capacity): from now on every time step of cev_fdtd_run stores D (three

@@ -218,3 +218,36 @@ def test_running_dft_monitors_equal_dft_of_the_time_series(shape, npml, dtype):
     assert rel_l2(got.real, fft.real) <= tol * 10 and rel_l2(got.imag, fft.imag) <= tol * 10
     F.initialize_fields()
     assert all(float(v.abs().max()) == 0.0 for v in F.monitor_values())
+
+
+def test_measure_fields_and_aniplot_against_the_oracle_loop(capsys):
+    """ceviche/utils.py:316-332 (measure_fields) and :279-313 (aniplot) on the drop-in object: both source forms of
+    measure_fields -- the reference's callable t -> J array (one forward() per step) and (profile, waveform) (the fused
+    device loop) -- against the oracle's caller loop; aniplot's panels against the oracle's snapshots."""
+    import ceviche_b200
+    from ceviche_b200.utils import aniplot, measure_fields
+    from oracle.fdtd_numpy import OracleFDTD
+    shape, npml, steps = (40, 30, 1), [6, 5, 0], 60
+    rng = np.random.default_rng(3)
+    eps = 1 + 2 * rng.random(shape)
+    prof = cases.one_hot(shape, (20, 15, 0), 3.0)
+    wave = cases.gaussian(steps, 20, 6, 2.0)
+    probes = [cases.one_hot(shape, (25, 12, 0)), rng.random(shape)]
+    for comp in ("Ez", "Hy"):
+        O = OracleFDTD(eps, cases.DL, npml)
+        want, _ = O.run(steps, [("z", prof, wave)], [(comp, p) for p in probes])
+        F = ceviche_b200.fdtd(eps, cases.DL, npml)
+        got_loop = measure_fields(F, lambda t: prof * wave[t], steps, probes, component=comp, verbose=True)
+        assert "% done" in capsys.readouterr().out                     # the reference's progress lines
+        got_run = measure_fields(F, (prof, wave), steps, probes, component=comp)
+        assert got_loop.shape == got_run.shape == (steps, 2)
+        for p in range(2):
+            assert rel_l2(got_loop[:, p], want[:, p]) <= 1e-10 and rel_l2(got_run[:, p], want[:, p]) <= 1e-10
+        single = measure_fields(F, (prof, wave), steps, probes[0], component=comp)     # a bare probe, not a list
+        assert np.array_equal(single[:, 0], got_run[:, 0])
+    O = OracleFDTD(eps, cases.DL, npml)
+    _, snaps = O.run(steps, [("z", prof, wave)], [], snapshots=tuple(range(1, steps + 1)))
+    panels = aniplot(ceviche_b200.fdtd(eps, cases.DL, npml), lambda t: prof * wave[t], steps, num_panels=5, show=False)
+    assert [t for t, _ in panels] == [0, 12, 24, 36, 48]
+    for t, arr in panels:
+        assert rel_l2(arr, snaps[t + 1]["Ez"][:, :, 0]) <= 1e-10
