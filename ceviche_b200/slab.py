@@ -637,6 +637,10 @@ class _SlabRunFn(torch.autograd.Function):
             peer = sim.path == "peer"
             if peer:         # recompute with caller-owned halo planes (NCCL), the exchange blocks paused
                 sim.set_option("halo_pause", 1)
+                if not getattr(sim, "_mE_hi_filled", False):       # the static 1/eps halo lives in the blocks on this path
+                    sim._exchange([be.mE[1][0], be.mE[2][0]], sim.left, [be.mE_hi[1], be.mE_hi[2]], sim.right)
+                    sim._wait()
+                    sim._mE_hi_filled = True
             be.halo = P > 1
             be._st = None
             try:
