@@ -53,13 +53,16 @@ struct V5MapsAdjED {
     CUtensorMap Crow[2];   // row boxes of gC2: components x, z
 };
 
-// minimum resident CTAs per SM asked of the compiler (register cap = 65536 / (threads * this)); 0 = no cap
-#ifndef CEV_ADJ_MINB_H
-#define CEV_ADJ_MINB_H 0
+// minimum resident CTAs per SM asked of the compiler (register cap = 65536 / (threads * this)).  Measured on B200
+// (profiles/r2_tune_adjoint_min_blocks.log, config 4): fp32 storage gains 14 % with 3 CTAs (168 registers instead of
+// 214-254: the four-cell vectors of a thread), fp64 is indifferent, 4 CTAs spill and lose.
+#ifndef CEV_ADJ_MINB_F32
+#define CEV_ADJ_MINB_F32 3
 #endif
-#ifndef CEV_ADJ_MINB_ED
-#define CEV_ADJ_MINB_ED 0
+#ifndef CEV_ADJ_MINB_F64
+#define CEV_ADJ_MINB_F64 0
 #endif
+#define CEV_ADJ_MINB(T) (sizeof(T) == 4 ? CEV_ADJ_MINB_F32 : CEV_ADJ_MINB_F64)
 
 template <typename T, int V, int BY>
 struct AdjV5Layout {
@@ -73,7 +76,7 @@ struct AdjV5Layout {
 // ---------------------------------------------------------------------------------------------------------
 // H part of the transposed step.  Same tiling, ring and wrap handling as k_step_H_v5.
 template <typename T, typename AT, int V, int BY, int NS>
-__global__ void __launch_bounds__(32 * BY, CEV_ADJ_MINB_H) k_adj_H_v5(const StepArgs<T, AT> a, const __grid_constant__ V5MapsAdjH maps) {
+__global__ void __launch_bounds__(32 * BY, CEV_ADJ_MINB(T)) k_adj_H_v5(const StepArgs<T, AT> a, const __grid_constant__ V5MapsAdjH maps) {
     using L = V5Layout<T, V, BY>;
     constexpr int BZ = L::BZ, ROWP = L::ROWP, BLK = L::BLK, LOFF = 3 * L::BLK;
     constexpr int STAGE = AdjV5Layout<T, V, BY>::H_STAGE;
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(32 * BY, CEV_ADJ_MINB_H) k_adj_H_v5(const Step
 // E and D parts.  Same tiling, ring and wrap handling as k_step_D_v5 (boxes of the stencil input start one vector
 // before the tile along z; the halo row j-1 is row BY of each block).
 template <typename T, typename AT, int V, int BY, int NS>
-__global__ void __launch_bounds__(32 * BY, CEV_ADJ_MINB_ED) k_adj_ED_v5(const StepArgs<T, AT> a, const __grid_constant__ V5MapsAdjED maps,
+__global__ void __launch_bounds__(32 * BY, CEV_ADJ_MINB(T)) k_adj_ED_v5(const StepArgs<T, AT> a, const __grid_constant__ V5MapsAdjED maps,
                                                         const AdjV5Extra<T> x) {
     using L = V5Layout<T, V, BY>;
     constexpr int BZ = L::BZ, ROWP = L::ROWP, BLK = L::BLK, LOFF = 3 * L::BLK, MOFF = 3 * L::BLK + 3 * L::PLN;

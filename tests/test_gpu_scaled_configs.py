@@ -36,6 +36,32 @@ def test_config2_scaled_2000_steps(golden_dir):
         assert rel_l2(s32[:, p], gold["series"][:1000, p]) <= 1e-5, p
 
 
+@pytest.mark.parametrize("arith", [None, "f64"])
+def test_config2_fp32_at_the_10k_step_horizon(arith):
+    """fp32 storage at config 2's own horizon (10 000 steps; 96^3 copy, drive off after step 2000) against the fp64 GPU run,
+    itself <= 1e-10 from the reference (test above).  What holds at 1e-5 -- and is asserted: the probe series over ALL
+    10 000 steps, and the nine fields while the excitation is in the domain (step 1000).  What does not (measured,
+    profiles/r2_fp32_drift.json): the late residual field, whose energy is < 1e-4 of the peak's and on
+    which rounding noise amplified by the sigma-PML's late-time behaviour reaches 1e-4 of the PEAK field norm by step
+    10 000 -- with fp32 or fp64 arithmetic alike, so it is a property of fp32 storage of this scheme, not of the kernels."""
+    import ceviche_b200
+    case = cases.scaled_case("c2_96")
+    steps = 10000
+    srcs = [(c, p, np.concatenate([w, np.zeros(steps - len(w))])) for c, p, w in case["sources"]]
+    out = {}
+    for name, dtype, ar in (("f64", torch.float64, None), ("f32", torch.float32, arith)):
+        F = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"], dtype=dtype, arith=ar)
+        s1 = F.run(1000, [(c, p, w[:1000]) for c, p, w in srcs], case["probes"])
+        f1 = {k: F.fields[k].double().cpu().numpy() for k in FIELD_KEYS}
+        wf = np.stack([w[1000:] for _, _, w in srcs], 1)
+        s2 = F.run(steps - 1000, waveforms=wf)
+        out[name] = (torch.cat([s1, s2]).cpu().numpy(), f1)
+    for p in range(out["f64"][0].shape[1]):
+        assert rel_l2(out["f32"][0][:, p], out["f64"][0][:, p]) <= 1e-5, p
+    allf = lambda f: np.concatenate([f[k].ravel() for k in FIELD_KEYS])
+    assert rel_l2(allf(out["f32"][1]), allf(out["f64"][1])) <= 1e-5
+
+
 def test_config4_scaled_gradient(golden_dir):
     import ceviche_b200
     case = cases.grad_case("c4_small")
