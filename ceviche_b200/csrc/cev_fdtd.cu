@@ -162,6 +162,9 @@ struct cev_fdtd {
     std::vector<cudaStream_t> side;        // forward mode: one side stream (+ event) per tangent state
     std::vector<cudaEvent_t> side_ev;
     cudaEvent_t main_ev = nullptr;
+    int jvp_batch = -1;          // -1 auto / 1: the B tangent half-steps of a forward-mode sweep as ONE launch each
+                                 // (k_step_{H,D}_v2_batch) wherever the marching kernels serve them; 0: one launch per tangent
+    DeviceBuf batch_tab_H, batch_tab_D;     // per-tangent StepArgs of those launches
     int jvp_streams = -1;        // -1 auto (2-D grids <= 2^23 cells, any grid <= 2^20 cells), 0 never, 1 always
     uint64_t epoch = 1;          // bumped whenever sources, probes or options change
     int use_graph = -1;          // -1 auto (small grids), 0 never, 1 whenever possible
@@ -914,6 +917,68 @@ int run_loop(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* wav
     return 0;
 }
 
+// ---- batched tangent half-steps: the B launches of one half-step as ONE (step_v2.cuh, k_step_*_v2_batch) -----------
+// Per-tangent StepArgs exactly as launch_H / launch_D would build them, uploaded once per sweep (the probe row is a
+// kernel parameter).  which = 0: tangent H half-steps (E = mE dD + dmE D), 1: tangent D half-steps on masked
+// single-row-plane grids (2-D TM / TE).  Returns 1 if the batch was built, 0 if this plan / state is not served
+// (callers fall back to one launch per tangent), -1 on error.
+template <typename T, typename AT>
+int build_tangent_batch(cev_fdtd* p, int which, int B, const cev_state* tst, const cev_tangent* tan, double* tpartials,
+                        int64_t stride, int64_t Nx, int* n_tiles, int* aux, unsigned* mask, cudaStream_t s) {
+    if (p->halo.on() || p->variant == 1) return 0;
+    std::vector<StepArgs<T, AT>> tab((size_t)B);
+    const int saved_chunk = p->xchunk;
+    for (int b = 0; b < B; ++b) {
+        StepArgs<T, AT>& a = tab[b];
+        if (fill_args(p, &tst[b], a, which == 0 ? &tan[b] : nullptr)) return -1;
+        if (!can_march(p, a, which == 0)) return 0;
+        if (which == 1 && !(a.Ny == 1 && a.on != 63u)) return 0;       // D: only the masked 2-D path is batched
+        if (a.Ny == 1 && p->xchunk <= 0) p->xchunk = 32;                // B x as many CTAs: long chunks still fill the GPU
+        if (which == 0) set_tiles_v2(p, a, 0, Nx, 0, 0, 32);
+        else set_tiles_v2(p, a, 0, Nx, 0);
+        p->xchunk = saved_chunk;
+        if (which == 1 && !a.wz) return 0;
+        a.aux_slot0 = which == 0 ? 0 : p->n_slots_ED;
+        a.partials = tpartials ? tpartials + b * stride : nullptr;
+        a.t_probe = -1;
+        if (b > 0 && (a.n_tiles != tab[0].n_tiles || a.on != tab[0].on)) return 0;
+    }
+    *n_tiles = tab[0].n_tiles;
+    *aux = (tpartials && p->n_slots > 0) ? (which == 0 ? p->n_slots_ED : p->n_slots - p->n_slots_ED) : 0;
+    *mask = tab[0].on;
+    DeviceBuf& buf = which == 0 ? p->batch_tab_H : p->batch_tab_D;
+    const size_t bytes = (size_t)B * sizeof(StepArgs<T, AT>);
+    if (buf.bytes < bytes) {
+        buf.release();
+        if (buf.alloc(bytes)) return -1;
+    }
+    CUDA_TRY(cudaMemcpyAsync(buf.p, tab.data(), bytes, cudaMemcpyHostToDevice, s));
+    return 1;
+}
+
+template <typename T, typename AT>
+int launch_tangent_batch(cev_fdtd* p, int which, int B, int n_tiles, int aux, unsigned mask, bool wz, int64_t probe_t, cudaStream_t s) {
+    constexpr int V = vec_width<T>();
+    const dim3 blk(32, V2_BY);
+    const int per = n_tiles + (probe_t >= 0 ? aux : 0);
+    if (per == 0) return 0;
+    const unsigned g = (unsigned)per * (unsigned)B;
+    if (which == 0) {
+        const StepArgs<T, AT>* tab = (const StepArgs<T, AT>*)p->batch_tab_H.p;
+        if (mask == 63u) k_step_H_v2_batch<T, AT, V, 32, false, 63, true><<<g, blk, 0, s>>>(tab, B, probe_t);
+        else if (wz && mask == (unsigned)MASK_TM) k_step_H_v2_batch<T, AT, V, 32, false, MASK_TM, true><<<g, blk, 0, s>>>(tab, B, probe_t);
+        else if (wz && mask == (unsigned)MASK_TE) k_step_H_v2_batch<T, AT, V, 32, false, MASK_TE, true><<<g, blk, 0, s>>>(tab, B, probe_t);
+        else k_step_H_v2_batch<T, AT, V, 32, false, -1, true><<<g, blk, 0, s>>>(tab, B, probe_t);
+    } else {
+        const StepArgs<T, AT>* tab = (const StepArgs<T, AT>*)p->batch_tab_D.p;
+        if (mask == (unsigned)MASK_TM) k_step_D_v2_batch<T, AT, V, 32, false, false, MASK_TM><<<g, blk, 0, s>>>(tab, B, probe_t);
+        else if (mask == (unsigned)MASK_TE) k_step_D_v2_batch<T, AT, V, 32, false, false, MASK_TE><<<g, blk, 0, s>>>(tab, B, probe_t);
+        else k_step_D_v2_batch<T, AT, V, 32, false, false, -1><<<g, blk, 0, s>>>(tab, B, probe_t);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 // Primal + B tangents in one sweep.  Per step: tangent H half-steps first (they need the primal D of
 // the previous step), then the primal step, then the tangent D half-steps (same linear update, J = 0).
 template <typename T, typename AT>
@@ -928,7 +993,18 @@ int jvp_loop(cev_fdtd* p, const cev_state* st, int B, const cev_state* tst, cons
     const int64_t cells = (int64_t)p->N[0] * p->N[1] * p->N[2];
     // auto: where it was measured to pay (scripts/tune2d.py) -- 2-D grids up to 2^23 cells, and small grids of any shape
     const bool small = cells <= ((int64_t)1 << 20) || (p->N[1] == 1 && cells <= ((int64_t)1 << 23));
-    const bool fork = B >= 2 && (p->jvp_streams == 1 || (p->jvp_streams < 0 && small));
+    // One launch per half-step for all B tangents where the marching kernels serve them (the H half-step everywhere, the D
+    // half-step on 2-D polarised grids); what is not batched runs as one launch per tangent, on side streams if `fork`.
+    int bH = 0, bD = 0, ntH = 0, auxH = 0, ntD = 0, auxD = 0;
+    unsigned maskH = 63u, maskD = 63u;
+    if (B >= 2 && p->jvp_batch != 0 && nsteps > 0) {
+        bH = build_tangent_batch<T, AT>(p, 0, B, tst, tan, tpartials, stride, Nx, &ntH, &auxH, &maskH, s);
+        if (bH < 0) return -1;
+        bD = build_tangent_batch<T, AT>(p, 1, B, tst, tan, tpartials, stride, Nx, &ntD, &auxD, &maskD, s);
+        if (bD < 0) return -1;
+    }
+    const bool wz_grid = p->N[1] == 1;
+    const bool fork = B >= 2 && !(bH && bD) && (p->jvp_streams == 1 || (p->jvp_streams < 0 && small));
     if (fork) {
         while ((int)p->side.size() < B) {
             cudaStream_t q;
@@ -943,22 +1019,37 @@ int jvp_loop(cev_fdtd* p, const cev_state* st, int B, const cev_state* tst, cons
     }
     auto ts = [&](int b) { return fork ? p->side[b] : s; };
     for (int64_t n = 0; n < nsteps; ++n) {
-        for (int b = 0; b < B; ++b) {
-            if (fork) CUDA_TRY(cudaStreamWaitEvent(ts(b), p->main_ev, 0));     // primal D of step n-1 is final
-            if (launch_H<T, AT>(p, &tst[b], &tan[b], nullptr, 0, Nx, n - 1, tpartials ? tpartials + b * stride : nullptr, ts(b))) return -1;
-            if (fork) CUDA_TRY(cudaEventRecord(p->side_ev[b], ts(b)));
+        if (bH) {
+            if (fork)      // (the tangent D half-steps of step n-1 ran on the side streams)
+                for (int b = 0; b < B; ++b) {
+                    CUDA_TRY(cudaEventRecord(p->side_ev[b], ts(b)));
+                    CUDA_TRY(cudaStreamWaitEvent(s, p->side_ev[b], 0));
+                }
+            if (launch_tangent_batch<T, AT>(p, 0, B, ntH, auxH, maskH, wz_grid, n - 1, s)) return -1;
+        } else {
+            for (int b = 0; b < B; ++b) {
+                if (fork) CUDA_TRY(cudaStreamWaitEvent(ts(b), p->main_ev, 0));     // primal D of step n-1 is final
+                if (launch_H<T, AT>(p, &tst[b], &tan[b], nullptr, 0, Nx, n - 1, tpartials ? tpartials + b * stride : nullptr, ts(b))) return -1;
+                if (fork) CUDA_TRY(cudaEventRecord(p->side_ev[b], ts(b)));
+            }
         }
         if (launch_H<T, AT>(p, st, nullptr, nullptr, 0, Nx, n - 1, partials, s)) return -1;
-        if (fork)
+        if (fork && !bH)
             for (int b = 0; b < B; ++b) CUDA_TRY(cudaStreamWaitEvent(s, p->side_ev[b], 0));   // they have read the primal D
         if (launch_D<T, AT>(p, st, nullptr, nullptr, nullptr, nullptr, nullptr, waveform ? waveform + n * p->nsrc : nullptr, 0,
                             Nx, n, partials, s))
             return -1;
         if (fork) CUDA_TRY(cudaEventRecord(p->main_ev, s));
-        for (int b = 0; b < B; ++b)
-            if (launch_D<T, AT>(p, &tst[b], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, Nx, n,
-                                tpartials ? tpartials + b * stride : nullptr, ts(b)))
-                return -1;
+        if (bD) {
+            if (launch_tangent_batch<T, AT>(p, 1, B, ntD, auxD, maskD, wz_grid, n, s)) return -1;
+        } else {
+            for (int b = 0; b < B; ++b) {
+                if (fork && bH) CUDA_TRY(cudaStreamWaitEvent(ts(b), p->main_ev, 0));   // the batched H half-step ran on the caller's stream
+                if (launch_D<T, AT>(p, &tst[b], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, Nx, n,
+                                    tpartials ? tpartials + b * stride : nullptr, ts(b)))
+                    return -1;
+            }
+        }
     }
     if (nsteps > 0) {
         if (launch_probe_only<T, AT>(p, st, nullptr, 0, nsteps - 1, partials, s)) return -1;
@@ -1609,7 +1700,10 @@ int cev_fdtd_destroy(cev_fdtd* p) {
 int cev_fdtd_set_option(cev_fdtd* p, const char* name, int64_t value) {
     if (!p || !name) return fail("NULL argument");
     p->epoch++;
-    if (!strcmp(name, "jvp_streams")) {
+    if (!strcmp(name, "jvp_batch")) {
+        if (value < -1 || value > 1) return fail("jvp_batch must be -1 (auto), 0 or 1");
+        p->jvp_batch = (int)value;
+    } else if (!strcmp(name, "jvp_streams")) {
         if (value < -1 || value > 1) return fail("jvp_streams must be -1 (auto), 0 or 1");
         p->jvp_streams = (int)value;
     } else if (!strcmp(name, "use_graph")) {

@@ -193,6 +193,25 @@ struct PmlCtx {
 // compile-time (lean kernels: the dead components cost neither registers nor instructions); -1 = read a.on at run time.
 constexpr int MASK_TM = 0b101010;   // 2-D grids are relabelled (x, z, y): logical {Dz, Hx, Hy} = internal {D_y, H_x, H_z}
 constexpr int MASK_TE = 0b010101;   //                                   logical {Dx, Dy, Hz} = internal {D_x, D_z, H_y}
+// A batch of launches of the same kernel on B independent states (the tangent states of a forward-mode sweep) as ONE
+// launch: CTA blockIdx.x serves state blockIdx.x % B (neighbouring CTAs work on the same tile of different states, so
+// the arrays the states share -- 1/eps and the primal D of a tangent H half-step -- are read from HBM once and hit in L2
+// for the others).  The per-state StepArgs live in a device table; the CTA copies its entry to shared memory.
+template <typename T, typename AT>
+__device__ __forceinline__ const StepArgs<T, AT>& batch_args(const StepArgs<T, AT>* table, int b, int64_t t_probe) {
+    __shared__ __align__(16) unsigned char raw[sizeof(StepArgs<T, AT>)];
+    static_assert(sizeof(StepArgs<T, AT>) % 4 == 0, "StepArgs is copied word by word");
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(table + b);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(raw);
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nth = blockDim.x * blockDim.y;
+    for (int q = tid; q < (int)(sizeof(StepArgs<T, AT>) / 4); q += nth) dst[q] = src[q];
+    __syncthreads();
+    StepArgs<T, AT>& a = *reinterpret_cast<StepArgs<T, AT>*>(raw);
+    if (tid == 0) a.t_probe = t_probe;
+    __syncthreads();
+    return a;
+}
+
 // TAN = forward-mode tangent step: the state is a TANGENT state and E = mE*D + dmE*D_primal (product rule on
 // fdtd.py:135-137), same rounding sequence as the baseline kernel; with TAN = false the extra loads fold away.
 template <bool TAN, typename T, typename AT, int V>
@@ -202,9 +221,7 @@ __device__ __forceinline__ AT e_of(const Vec<T, V>& m, const Vec<T, V>& d, const
 }
 
 template <typename T, typename AT, int V, int LZ, bool INTERIOR, int MASK = 63, bool TAN = false>
-__global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS : ((TAN && MASK != MASK_TM && MASK != MASK_TE) ? 2 : (sizeof(T) == 8 ? V2_H_MIN_CTAS : V2_H_MIN_CTAS + 1))))
-k_step_H_v2(const StepArgs<T, AT> a) {
-    const int bid = blockIdx.x;
+__device__ __forceinline__ void step_H_v2_body(const StepArgs<T, AT>& a, const int bid) {
     if (bid >= a.n_tiles) {
         probe_block<T, AT>(a, a.aux_slot0 + (bid - a.n_tiles));
         return;
@@ -377,12 +394,24 @@ k_step_H_v2(const StepArgs<T, AT> a) {
         }
     }
 }
+template <typename T, typename AT, int V, int LZ, bool INTERIOR, int MASK = 63, bool TAN = false>
+__global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS : ((TAN && MASK != MASK_TM && MASK != MASK_TE) ? 2 : (sizeof(T) == 8 ? V2_H_MIN_CTAS : V2_H_MIN_CTAS + 1))))
+k_step_H_v2(const StepArgs<T, AT> a) {
+    step_H_v2_body<T, AT, V, LZ, INTERIOR, MASK, TAN>(a, blockIdx.x);
+}
+
+template <typename T, typename AT, int V, int LZ, bool INTERIOR, int MASK = 63, bool TAN = false>
+__global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS : ((TAN && MASK != MASK_TM && MASK != MASK_TE) ? 2 : (sizeof(T) == 8 ? V2_H_MIN_CTAS : V2_H_MIN_CTAS + 1))))
+k_step_H_v2_batch(const StepArgs<T, AT>* table, int B, int64_t t_probe) {
+    const StepArgs<T, AT>& a = batch_args<T, AT>(table, blockIdx.x % B, t_probe);
+    step_H_v2_body<T, AT, V, LZ, INTERIOR, MASK, TAN>(a, blockIdx.x / B);
+}
+
 
 // EXTRAS = dense J input and/or E output (the per-step forward() API); the fused run() path
 // instantiates EXTRAS = false and carries neither.
 template <typename T, typename AT, int V, int LZ, bool EXTRAS, bool INTERIOR, int MASK = 63>
-__global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS : V2_D_MIN_CTAS)) k_step_D_v2(const StepArgs<T, AT> a) {
-    const int bid = blockIdx.x;
+__device__ __forceinline__ void step_D_v2_body(const StepArgs<T, AT>& a, const int bid) {
     if (bid >= a.n_tiles) {
         probe_block<T, AT>(a, a.aux_slot0 + (bid - a.n_tiles));
         return;
@@ -530,5 +559,17 @@ __global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS :
                                       a.src_id, a.src_cell, a.src_w, a.src_wave, a.Dout[0], a.Dout[1], a.Dout[2]);
     }
 }
+template <typename T, typename AT, int V, int LZ, bool EXTRAS, bool INTERIOR, int MASK = 63>
+__global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS : V2_D_MIN_CTAS)) k_step_D_v2(const StepArgs<T, AT> a) {
+    step_D_v2_body<T, AT, V, LZ, EXTRAS, INTERIOR, MASK>(a, blockIdx.x);
+}
+
+template <typename T, typename AT, int V, int LZ, bool EXTRAS, bool INTERIOR, int MASK = 63>
+__global__ void __launch_bounds__(32 * V2_BY, (INTERIOR ? V2_INTERIOR_MIN_CTAS : V2_D_MIN_CTAS))
+k_step_D_v2_batch(const StepArgs<T, AT>* table, int B, int64_t t_probe) {
+    const StepArgs<T, AT>& a = batch_args<T, AT>(table, blockIdx.x % B, t_probe);
+    step_D_v2_body<T, AT, V, LZ, EXTRAS, INTERIOR, MASK>(a, blockIdx.x / B);
+}
+
 
 }  // namespace cev

@@ -19,8 +19,8 @@ KEYS = ("Ex", "Ey", "Ez", "Dx", "Dy", "Dz", "Hx", "Hy", "Hz")
 MILESTONES = (1000, 2000, 5000, 10000)
 
 
-def run(eps, sources, probes, wave, dtype, arith):
-    F = ceviche_b200.fdtd(eps, cases.DL, [20, 20, 20], dtype=dtype, arith=arith)
+def run(eps, sources, probes, wave, dtype, arith, npml=(20, 20, 20)):
+    F = ceviche_b200.fdtd(eps, cases.DL, list(npml), dtype=dtype, arith=arith)
     F.prepare(sources, probes)
     wave = torch.as_tensor(wave).cuda()
     snaps, series, t = {}, [], 0
@@ -36,11 +36,11 @@ def rel(a, b):
     return float(torch.linalg.vector_norm(a - b)) / n if n > 0 else float(torch.linalg.vector_norm(a))
 
 
-def table(name, eps, sources, probes, wave):
-    ref_snaps, ref_series = run(eps, sources, probes, wave, torch.float64, None)
+def table(name, eps, sources, probes, wave, npml=(20, 20, 20)):
+    ref_snaps, ref_series = run(eps, sources, probes, wave, torch.float64, None, npml)
     out = {"grid": list(eps.shape), "case": name, "rows": []}
     for arith in ("f32", "f64"):
-        snaps, series = run(eps, sources, probes, wave, torch.float32, arith)
+        snaps, series = run(eps, sources, probes, wave, torch.float32, arith, npml)
         for m in MILESTONES:
             allf = torch.cat([snaps[m][k].ravel() for k in KEYS]), torch.cat([ref_snaps[m][k].ravel() for k in KEYS])
             e_only = torch.cat([snaps[m][k].ravel() for k in KEYS[:3]]), torch.cat([ref_snaps[m][k].ravel() for k in KEYS[:3]])
@@ -48,6 +48,7 @@ def table(name, eps, sources, probes, wave):
                                 "fields_rel_l2": rel(*allf), "E_rel_l2": rel(*e_only),
                                 "worst_field_rel_l2": max(rel(snaps[m][k], ref_snaps[m][k]) for k in KEYS),
                                 "series_rel_l2_up_to_here": rel(series[:m], ref_series[:m]),
+                                "series_rel_l2_per_probe": [rel(series[:m, q], ref_series[:m, q]) for q in range(series.shape[1])],
                                 "E_energy_vs_peak": float(sum(ref_snaps[m][k].pow(2).sum() for k in KEYS[:3])) /
                                 max(float(sum(ref_snaps[q][k].pow(2).sum() for k in KEYS[:3])) for q in MILESTONES)})
         del snaps
@@ -61,6 +62,7 @@ def main():
     srcs = [(c, p) for c, p, _ in case["sources"]]
     w = np.stack([np.concatenate([wv, np.zeros(MILESTONES[-1] - len(wv))]) for _, _, wv in case["sources"]], 1)
     res.append(table("config 2 scaled to 96^3 (pulse t0=300, sigma=60; zero drive after step 2000)", case["eps"], srcs, case["probes"], w))
+    res.append(table("the same with a 12-cell PML (the golden fixture's)", case["eps"], srcs, case["probes"], w, npml=[12, 12, 12]))
     shape = (256, 256, 256)
     wl = bench.workload(shape, MILESTONES[-1])
     res.append(table("config 2: 256^3 splitter, pulse t0=2000 sigma=100 (bench.py workload)", wl["eps"],
