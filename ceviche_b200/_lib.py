@@ -70,6 +70,7 @@ def _declare(lib):
         "cev_fdtd_adjoint_step": [C.c_void_p, P(cev_state), P(cev_adjoint), C.c_void_p],
         "cev_fdtd_adjoint_seed": [C.c_void_p, P(cev_state), P(cev_adjoint), C.c_void_p, C.c_void_p],
         "cev_fdtd_adjoint_run": [C.c_void_p, P(cev_state), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, P(cev_adjoint), C.c_void_p],
+        "cev_fdtd_adjoint_graph_replays": [C.c_void_p],
         "cev_fdtd_adjoint_part": [C.c_void_p, C.c_int, P(cev_state), P(cev_adjoint), P(c_void_p3), C.c_void_p],
         "cev_fdtd_adjoint_boxed_supported": [C.c_void_p],
         "cev_fdtd_set_recorder": [C.c_void_p, P(C.c_int64), C.c_void_p, C.c_int64],
@@ -96,6 +97,7 @@ def _declare(lib):
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int
+    lib.cev_fdtd_adjoint_graph_replays.restype = C.c_int64
     return sigs
 
 
@@ -104,7 +106,7 @@ EXPORTS = ("cev_last_error", "cev_abi_version", "cev_fdtd_create", "cev_fdtd_des
            "cev_fdtd_step_H", "cev_fdtd_step_D", "cev_fdtd_compute_E", "cev_fdtd_set_sources",
            "cev_fdtd_set_probes", "cev_fdtd_probe_slots", "cev_fdtd_fold_probes", "cev_fdtd_set_monitors", "cev_fdtd_bind_monitors", "cev_fdtd_run", "cev_fdtd_run_fused", "cev_fdtd_step_H_ex", "cev_fdtd_step_D_ex",
            "cev_fdtd_sample_probes", "cev_fdtd_jvp_run", "cev_fdtd_adjoint_step", "cev_fdtd_adjoint_seed", "cev_fdtd_adjoint_run",
-           "cev_fdtd_adjoint_part", "cev_fdtd_adjoint_boxed_supported", "cev_fdtd_set_recorder", "cev_fdtd_adjoint_run_boxed",
+           "cev_fdtd_adjoint_graph_replays", "cev_fdtd_adjoint_part", "cev_fdtd_adjoint_boxed_supported", "cev_fdtd_set_recorder", "cev_fdtd_adjoint_run_boxed",
            "cev_fdtd_halo_layout", "cev_halo_alloc", "cev_halo_open", "cev_halo_close", "cev_halo_free",
            "cev_fdtd_halo_attach", "cev_fdtd_halo_push_static", "cev_fdtd_halo_reset", "cev_fdtd_halo_error")
 

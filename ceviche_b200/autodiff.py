@@ -269,14 +269,18 @@ class _RunFn(torch.autograd.Function):
             longest = max(t1 - t0 for t0, t1, *_ in ctx.checkpoints)
             hist = torch.empty((longest + 1, 3) + tuple(sim.grid_shape), dtype=sim.dtype, device=sim.device)
             slots = (_lib.c_void_p3 * (longest + 1))(*[_p3(list(hist[k])) for k in range(longest + 1)])
+            # scratch state of the recomputation: the same buffers for every segment (H and the integrals are copies, so a
+            # second backward() finds the checkpoints intact; fixed buffers let the C side replay a captured segment)
+            Hs = [torch.empty_like(t) for t in ctx.checkpoints[0][2]]
+            Ps = [torch.empty_like(t) for t in ctx.checkpoints[0][4]]
+            st = _state(Hs, list(hist[0]), ctx.mE, Ps)
             for t0, t1, H0, D0, P0 in reversed(ctx.checkpoints):
                 # one C call per checkpoint segment: recompute + transposed steps (cev_fdtd_adjoint_run); the recomputation
                 # advances H and the PML integrals it is given in place
                 for c in range(3):
                     hist[0, c].copy_(D0[c])
-                # (H and the integrals are cloned: a second backward() finds the checkpoints intact)
-                Hs, Ps = [t.clone() for t in H0], [t.clone() for t in P0]
-                st = _state(Hs, D0, ctx.mE, Ps)
+                for dst, src in zip(Hs + Ps, list(H0) + list(P0)):
+                    dst.copy_(src)
                 _lib.check(lib.cev_fdtd_adjoint_run(h, C.byref(st), t1 - t0,
                                                     _ptr(ctx.waveforms[t0:t1]) if sim._n_sources else None,
                                                     _ptr(gbar[t0:t1]) if ctx.n_probes else None, slots, C.byref(adj), s))

@@ -158,6 +158,16 @@ struct cev_fdtd {
     };
     std::vector<RunGraph> graphs;
     DeviceBuf stage_w, stage_p;
+    // One checkpoint segment of the reverse sweep (recomputation + transposed steps) as a CUDA graph, for grids whose
+    // kernels are shorter than a launch: captured the second time the same segment (same arrays, same length) is asked
+    // for and replayed from then on; waveform / cotangent rows go through the staging buffers.
+    struct AdjGraph {
+        cudaGraphExec_t exec = nullptr;
+        std::vector<unsigned char> key, seen;       // key of the captured graph / of the last plain segment
+        uint64_t epoch = 0;
+        int64_t replays = 0;
+    } adj_graph;
+    DeviceBuf adj_stage_w, adj_stage_g;
     cudaStream_t cap_stream = nullptr;
     std::vector<cudaStream_t> side;        // forward mode: one side stream (+ event) per tangent state
     std::vector<cudaEvent_t> side_ev;
@@ -172,6 +182,8 @@ struct cev_fdtd {
         for (auto& g : graphs)
             if (g.exec) cudaGraphExecDestroy(g.exec);
         graphs.clear();
+        if (adj_graph.exec) cudaGraphExecDestroy(adj_graph.exec);
+        adj_graph = AdjGraph();
     }
 
     int to_internal(int logical_axis) const { return inv[logical_axis]; }
@@ -1466,8 +1478,8 @@ int adjoint_v5_sweep(cev_fdtd* p, const AdjArgs<T, AT>& a, int64_t nsteps, const
 // segment's start state keeping D after every step (hist[k] = D after k steps; hist[0] is the start D), then the
 // transposed steps in reverse order, each preceded by the probe-series seeds of its time step.
 template <typename T, typename AT>
-int adjoint_run(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* waveform, const double* gbar,
-                void* const (*hist)[3], const cev_adjoint* adj, cudaStream_t s) {
+int adjoint_run_enqueue(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* waveform, const double* gbar,
+                        void* const (*hist)[3], const cev_adjoint* adj, cudaStream_t s) {
     const int64_t Nx = p->N[0];
     cev_state cur = *st;
     for (int64_t k = 1; k <= nsteps; ++k) {
@@ -1498,6 +1510,64 @@ int adjoint_run(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* 
         for (int c = 0; c < 3; ++c) fwd.D[c] = hist[k - 1][c];
         if (launch_adjoint_step<T, AT>(p, &fwd, adj, s)) return -1;
     }
+    return 0;
+}
+
+template <typename T, typename AT>
+int adjoint_run(cev_fdtd* p, const cev_state* st, int64_t nsteps, const double* waveform, const double* gbar,
+                void* const (*hist)[3], const cev_adjoint* adj, cudaStream_t s) {
+    const int64_t cells = (int64_t)p->N[0] * p->N[1] * p->N[2];
+    const bool want = !p->halo.on() && !p->rec.buf && nsteps >= 4 &&
+                      (p->use_graph == 1 || (p->use_graph < 0 && cells <= GRAPH_MAX_CELLS));
+    if (!want) return adjoint_run_enqueue<T, AT>(p, st, nsteps, waveform, gbar, hist, adj, s);
+    // everything the captured launches depend on
+    std::vector<unsigned char> key;
+    auto put = [&](const void* q, size_t n) { key.insert(key.end(), (const unsigned char*)q, (const unsigned char*)q + n); };
+    put(st, sizeof *st);
+    put(adj, sizeof *adj);
+    put(&nsteps, sizeof nsteps);
+    put(hist, (size_t)(nsteps + 1) * sizeof hist[0]);
+    const int flags = (waveform ? 1 : 0) | (gbar ? 2 : 0);
+    put(&flags, sizeof flags);
+    auto& G = p->adj_graph;
+    if (G.epoch != p->epoch) {
+        if (G.exec) cudaGraphExecDestroy(G.exec);
+        G = cev_fdtd::AdjGraph();
+        G.epoch = p->epoch;
+    }
+    const size_t wbytes = (size_t)nsteps * std::max(1, p->nsrc) * 8, gbytes = (size_t)nsteps * std::max(1, p->nprobe) * 8;
+    if (!(G.exec && G.key == key)) {
+        if (G.seen != key) {          // first time: plain launches (they also build tilings / set kernel attributes)
+            G.seen = key;
+            return adjoint_run_enqueue<T, AT>(p, st, nsteps, waveform, gbar, hist, adj, s);
+        }
+        // second time: capture
+        if (p->adj_stage_w.bytes < wbytes) { p->adj_stage_w.release(); if (p->adj_stage_w.alloc(wbytes)) return -1; }
+        if (p->adj_stage_g.bytes < gbytes) { p->adj_stage_g.release(); if (p->adj_stage_g.alloc(gbytes)) return -1; }
+        if (!p->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking));
+        if (G.exec) cudaGraphExecDestroy(G.exec);
+        G.exec = nullptr;
+        CUDA_TRY(cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeRelaxed));
+        const int rc = adjoint_run_enqueue<T, AT>(p, st, nsteps, waveform ? (const double*)p->adj_stage_w.p : nullptr,
+                                                  gbar ? (const double*)p->adj_stage_g.p : nullptr, hist, adj, p->cap_stream);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(p->cap_stream, &graph);
+        if (rc || e != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc ? rc : fail("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+        }
+        const cudaError_t e2 = cudaGraphInstantiate(&G.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e2 != cudaSuccess) {
+            G.exec = nullptr;
+            return fail("cudaGraphInstantiate failed: %s", cudaGetErrorString(e2));
+        }
+        G.key = key;
+    }
+    if (waveform) CUDA_TRY(cudaMemcpyAsync(p->adj_stage_w.p, waveform, (size_t)nsteps * p->nsrc * 8, cudaMemcpyDeviceToDevice, s));
+    if (gbar) CUDA_TRY(cudaMemcpyAsync(p->adj_stage_g.p, gbar, (size_t)nsteps * p->nprobe * 8, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaGraphLaunch(G.exec, s));
+    G.replays++;
     return 0;
 }
 
@@ -1875,6 +1945,8 @@ int cev_fdtd_fold_probes(cev_fdtd* p, const double* partials, int64_t rows, doub
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
+
+int64_t cev_fdtd_adjoint_graph_replays(const cev_fdtd* p) { return p ? p->adj_graph.replays : -1; }
 
 int cev_fdtd_adjoint_boxed_supported(const cev_fdtd* p) {
     if (!p) return 0;

@@ -205,6 +205,12 @@ int cev_fdtd_adjoint_run(cev_fdtd* plan, const cev_state* st, int64_t nsteps, co
                          void* const (*D_hist)[3], const cev_adjoint* adj, void* stream);
 int cev_fdtd_adjoint_seed(cev_fdtd* plan, const cev_state* fwd, const cev_adjoint* adj, const double* gbar_row,
                           void* stream);
+/* On grids whose kernels are shorter than a launch (option "use_graph": auto = up to 2^18 cells) cev_fdtd_adjoint_run
+ * captures a segment -- recomputation and transposed steps -- into a CUDA graph the second time it is called with the
+ * same arrays and length, and replays it from then on (the waveform / gbar rows travel through staging buffers).
+ * Callers that want replays keep st, D_hist and adj on the same buffers from segment to segment.  Returns how many
+ * segments of this plan were graph replays so far (diagnostics / tests). */
+int64_t cev_fdtd_adjoint_graph_replays(const cev_fdtd* plan);
 /* The transposed step in three parts with stored stencil inputs, for x-slabs (one process per GPU): the caller
  * exchanges one plane pair between the parts, as the forward half-steps do.
  *   part 0  cell-local D part: lD <- m1 lD + gID, gC <- m2 lD + gICH (lICH, lID advanced)

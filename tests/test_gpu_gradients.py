@@ -255,3 +255,24 @@ def test_tensor_map_adjoint_identity():
     _, ds = F2.jvp_run(case["steps"], v[None], case["sources"], case["probes"])
     lhs, rhs = float((gbar * ds[0]).sum()), float((g * v.cuda()).sum())
     assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), abs(rhs)), (lhs, rhs)
+
+
+@pytest.mark.parametrize("shape,npml", [((40, 36, 1), (5, 4, 0)), ((14, 12, 10), (3, 2, 2))])
+def test_adjoint_segments_replayed_as_cuda_graphs(shape, npml):
+    """On launch-bound grids cev_fdtd_adjoint_run captures a checkpoint segment (recomputation + transposed steps) into a
+    CUDA graph the second time it sees it and replays it afterwards: same kernels, so the gradient is bit-identical to the
+    plain launches, and most segments must have been replays."""
+    import ceviche_b200
+    case = cases._small3d(shape, npml, 120, 31)
+    grads, replays = {}, {}
+    for use_graph in (0, -1):
+        eps = torch.as_tensor(case["eps"]).cuda().requires_grad_(True)
+        F = ceviche_b200.fdtd(eps, case["dL"], case["npml"])
+        F.set_option("use_graph", use_graph)
+        series = F.run(case["steps"], case["sources"], case["probes"], checkpoint_every=10)
+        (g,) = torch.autograd.grad(_loss(series, case), eps)
+        grads[use_graph] = g
+        plan = F._ensure_plan()
+        replays[use_graph] = plan.lib.cev_fdtd_adjoint_graph_replays(plan.handle)
+    assert replays[0] == 0 and replays[-1] >= 10          # 12 segments: one plain, one captured + replayed, ten replayed
+    assert torch.equal(grads[0], grads[-1])
