@@ -103,35 +103,43 @@ if "c4" in which:
         torch.cuda.empty_cache()
 
 if "c5" in which:
-    # config 5: forward-mode JVP over 16 eps_r perturbations on a 2-D 2048x2048 grating-like grid
+    # config 5: forward-mode JVP over 16 eps_r perturbations on a 2-D 2048x2048 grating-coupler grid (20 000 steps at its
+    # stated size: C5_STEPS=20000).  Geometry and directions after examples/forwardmode_grating_coupler.py:33-98, 138-162
+    # scaled to the grid (ceviche_b200.parametrization.grating_coupler): Si slab + teeth on SiO2, the teeth = sigmoid
+    # projection of sin^2 around 1 - fill factor; the 16 directions are d eps_r / d(fill factor of tooth group g).
+    from ceviche_b200.parametrization import grating_coupler
     shape = (2048, 2048, 1)
     steps = int(os.environ.get("C5_STEPS", "300"))
     B = 16
-    eps_np = np.full(shape, 1.44 ** 2)
-    eps_np[:, 1000:1048, 0] = 3.48 ** 2
-    V = np.zeros((B,) + shape)
-    for b in range(B):
-        x0 = 200 + b * 100
-        eps_np[x0:x0 + 50, 1048:1070, 0] = 3.48 ** 2
-        V[b, x0:x0 + 50, 1048:1070, 0] = 1.0
-    prof = np.zeros(shape); prof[100, 1000:1048, 0] = 1.0
-    mask = np.zeros(shape); mask[200:1800, 1300, 0] = 1.0
+    G = grating_coupler(2048, 2048, DL, 20, groups=B)
+    ff = torch.full((B,), 0.5, dtype=torch.float64, device="cuda")
+    eps_t = G.eps_r(ff)
+    Vt = G.fill_factor_directions(ff)                      # [16, 2048, 2048, 1] on the device
+    prof = np.zeros(shape); prof[G.source_x, G.y_base[0]:G.y_teeth[1], 0] = 1.0          # modal-like sheet across the slab
+    mask = np.zeros(shape); mask[G.x_grids[0]:G.x_grids[-1], G.probe_y, 0] = 1.0          # line probe above the grating
     t = np.arange(steps)
-    wave = np.exp(-(t - 100) ** 2 / (2 * 30 ** 2)) * np.cos(0.15 * t)
+    wave = np.exp(-(t - 400) ** 2 / (2 * 120.0 ** 2)) * np.cos(2 * np.pi * 299792458.0 / 1550e-9 * (0.5 * DL / (np.sqrt(3) * 299792458.0)) * t)
     for dtype, name in ((torch.float64, "f64"), (torch.float32, "f32")):
-        F = ceviche_b200.fdtd(eps_np, DL, [20, 20, 0], dtype=dtype)
-        Vt = torch.as_tensor(V)
+        F = ceviche_b200.fdtd(eps_t, DL, [20, 20, 0], dtype=dtype)
         F.jvp_run(10, Vt, [("z", prof, wave[:10])], [("Ez", mask)])
         F.initialize_fields()
-        s, _ = timed(lambda: F.jvp_run(steps, Vt, [("z", prof, wave)], [("Ez", mask)]))
+        s, (series, dseries) = timed(lambda: F.jvp_run(steps, Vt, [("z", prof, wave)], [("Ez", mask)]))
         cells = shape[0] * shape[1]
-        F2 = ceviche_b200.fdtd(eps_np, DL, [20, 20, 0], dtype=dtype)
+        F2 = ceviche_b200.fdtd(eps_t, DL, [20, 20, 0], dtype=dtype)
         F2.run(10, [("z", prof, wave[:10])], [("Ez", mask)])
         F2.initialize_fields()
         s1, _ = timed(lambda: F2.run(steps, [("z", prof, wave)], [("Ez", mask)]))
-        print(json.dumps({"config": "c5 batched JVP, 16 tangents + primal, 2-D 2048x2048 npml [20,20,0], %d steps" % steps,
-                          "dtype": name, "seconds": s, "gcell_per_s_incl_tangents": cells * steps * (1 + B) / s / 1e9,
+        w = 8 if name == "f64" else 4
+        gc = cells * steps * (1 + B) / s / 1e9
+        # 2-D TM byte model per cell and time step: primal 10 words; per tangent 8 (H half-step: dD, 1/eps, d(1/eps), D
+        # primal, H x2 in, H x2 out -- 1/eps and the primal D shared by the batch: 6 own words) + 4 (D half-step)
+        bytes_step = cells * w * (10 + B * 10)
+        print(json.dumps({"config": "c5 batched JVP, 16 fill-factor tangents + primal, 2-D 2048x2048 grating coupler npml [20,20,0], %d steps" % steps,
+                          "dtype": name, "seconds": s, "gcell_per_s_incl_tangents": gc,
                           "primal_only_seconds": s1, "primal_only_gcell_per_s": cells * steps / s1 / 1e9,
-                          "active_components": F._options.get("active_components", 63)}), flush=True)
+                          "byte_model_words_per_cell_step": 10 + B * 10,
+                          "model_GBps": bytes_step * steps / s / 1e9,
+                          "series_l2": float(series.norm()), "dseries_l2_per_direction": [float(dseries[b].norm()) for b in range(B)],
+                          "teeth": int(G.num_teeth), "active_components": F._options.get("active_components", 63)}), flush=True)
         del F, F2
         torch.cuda.empty_cache()
