@@ -159,3 +159,32 @@ def test_hips_binding_is_a_soft_dependency():
     prim = hips.register(ext)
     assert callable(prim) and [c[0] for c in calls] == ["vjp", "jvp"]
     assert all(c[1] == 5 and all(x is None for x in c[2]) for c in calls)
+
+
+def test_design_region_boxes():
+    """Host logic of the design-box gradients: eps_r[i, j, k] enters the Yee averages of cells (i..i+1, j..j+1, k..k+1)
+    (utils.py:167-174), so the 1/eps cotangent box is one cell larger on the high side; on x-slabs it is clipped to the
+    slab (possibly empty); a box whose +1 would wrap falls back to the whole grid."""
+    import types
+    from ceviche_b200 import autodiff
+    from ceviche_b200.slab import SlabFDTD, partition
+    sim = types.SimpleNamespace(design_region=((2, 5), (1, 4), (0, 3)), grid_shape=(8, 6, 4))
+    assert autodiff._grad_box(sim) == [(2, 6), (1, 5), (0, 4)]
+    sim.design_region = ((2, 8), (1, 4), (0, 3))           # x1 + 1 would wrap: everywhere
+    assert autodiff._grad_box(sim) is None
+    sim.design_region = None
+    assert autodiff._grad_box(sim) is None
+    sim.design_region = ((2, 9), (1, 4), (0, 3))
+    with pytest.raises(ValueError):
+        autodiff._grad_box(sim)
+    parts = partition(12, 3)
+    assert parts == [(0, 4), (4, 8), (8, 12)]
+    boxes = []
+    for lo, hi in parts:
+        slab = types.SimpleNamespace(design_region=((3, 6), (1, 4), (0, 3)), Nx=12, Ny=6, Nz=5, lo=lo, hi=hi)
+        boxes.append(SlabFDTD._local_grad_box(slab))
+    assert boxes[0] == [3, 4, 1, 5, 0, 4]                   # global planes 3..6 (+1) cut at the slab boundary
+    assert boxes[1] == [0, 3, 1, 5, 0, 4]
+    assert boxes[2][0] >= boxes[2][1]                       # does not touch the third slab: empty x-range
+    slab = types.SimpleNamespace(design_region=None, Nx=12, Ny=6, Nz=5, lo=0, hi=4)
+    assert SlabFDTD._local_grad_box(slab) is None
