@@ -242,6 +242,33 @@ class _RunFn(torch.autograd.Function):
         return torch.cat(chunks) if chunks else torch.zeros((0, sim._n_probes), dtype=torch.float64, device=sim.device)
 
     @staticmethod
+    def jvp(ctx, _sim, _steps, _wf, _every, *dmE64):
+        """Forward mode through the fused run (torch.autograd.forward_ad / jacobian(mode='forward')): one tangent sweep
+        (cev_fdtd_jvp_run, B = 1) on scratch states restarted from zero fields, with d(1/eps_yee) as torch hands it over.
+        For many directions call fdtd.jvp_run, which advances all of them in ONE sweep."""
+        sim = ctx.sim
+        plan = sim._ensure_plan()
+        sim._apply_active(ctx.active)
+        with torch.cuda.device(sim.device), torch.no_grad():
+            z = lambda ts: [torch.zeros_like(t) for t in ts]
+            dmE = [torch.zeros_like(ctx.mE[c]) if t is None else t.detach().to(sim.dtype).contiguous() for c, t in enumerate(dmE64)]
+            H, D, P = z(sim._H), z(sim._D), z(_flat_pml(sim))
+            tH, tD, tP = z(sim._H), z(sim._D), z(_flat_pml(sim))
+            tsts, tans = (_lib.cev_state * 1)(), (_lib.cev_tangent * 1)()
+            tsts[0] = _state(tH, tD, ctx.mE, tP)
+            tans[0].d_inv_eps, tans[0].D_primal = _p3(dmE), _p3(D)
+            partials = torch.zeros((ctx.steps, sim._n_slots), dtype=torch.float64, device=sim.device)
+            tpart = torch.zeros((1, ctx.steps, sim._n_slots), dtype=torch.float64, device=sim.device)
+            st = _state(H, D, ctx.mE, P)
+            _lib.check(plan.lib.cev_fdtd_jvp_run(plan.handle, C.byref(st), 1, tsts, tans, ctx.steps, _ptr(ctx.waveforms),
+                                                 _ptr(partials), _ptr(tpart), sim._stream()))
+            sim._apply_active(sim._active)
+            if ctx.n_probes == 0:
+                return torch.zeros((ctx.steps, 0), dtype=torch.float64, device=sim.device)
+            from .fdtd import fold_probes
+            return fold_probes(plan, tpart, ctx.n_probes, sim._stream())[0]
+
+    @staticmethod
     def backward(ctx, gbar):
         sim = ctx.sim
         plan = sim._ensure_plan()

@@ -92,7 +92,7 @@ struct cev_fdtd {
     int auto_v5 = 1;                    // kernel_variant 0 (auto) picks them on large 3-D grids
     int adjoint_variant = 0;            // reverse sweep of cev_fdtd_adjoint_run: 0 auto, 1 simple kernels (adjoint.cuh),
                                         // 2 tensor-map kernels (adjoint_v5.cuh) wherever they apply
-    int tma_stages_adjH = 4, tma_stages_adjED = 3;
+    int tma_stages_adjH = 3, tma_stages_adjED = 3;     // (profiles/r2_tune_adjoint_ring_depths.log)
     // x-slab halo exchange through peer-mapped memory (cev_fdtd_halo_attach): this slab's exchange block and the
     // neighbours' (device pointers valid on this device), and how many H / D half-steps have used them
     struct Halo {

@@ -78,6 +78,9 @@ if "c4" in which:
       for region in (None, box):      # gradient w.r.t. every eps_r cell | w.r.t. the design box only
         eps = torch.as_tensor(eps_np).cuda().requires_grad_(True)
         F = ceviche_b200.fdtd(eps, DL, [20, 20, 20], dtype=dtype)
+        for kv in os.environ.get("C4_OPTS", "").split(","):
+            if kv:
+                F.set_option(kv.split("=")[0], int(kv.split("=")[1]))
         F.design_region = region
         def fwd():
             F.eps_r = eps        # like the reference's objective (test_gradients_fdtd.py:73): new graph, fields reset

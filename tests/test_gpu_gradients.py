@@ -276,3 +276,38 @@ def test_adjoint_segments_replayed_as_cuda_graphs(shape, npml):
         replays[use_graph] = plan.lib.cev_fdtd_adjoint_graph_replays(plan.handle)
     assert replays[0] == 0 and replays[-1] >= 10          # 12 segments: one plain, one captured + replayed, ten replayed
     assert torch.equal(grads[0], grads[-1])
+
+
+def test_forward_mode_through_the_fused_run():
+    """torch forward-mode AD (what jacobian(mode='forward') uses) through fdtd.run(): the tangent of the probe series
+    equals the batched tangent sweep's, and jacobian(mode='forward') of a run()-based objective equals mode='reverse'."""
+    import torch.autograd.forward_ad as fwAD
+    import ceviche_b200
+    from ceviche_b200 import jacobian
+    case = cases.grad_case("probe3d")
+    rng = np.random.default_rng(4)
+    v = torch.as_tensor(rng.standard_normal(case["eps"].shape)).cuda()
+    eps = torch.as_tensor(case["eps"]).cuda()
+    with fwAD.dual_level():
+        F = ceviche_b200.fdtd(fwAD.make_dual(eps, v), case["dL"], case["npml"])
+        series = F.run(case["steps"], case["sources"], case["probes"])
+        primal, tangent = fwAD.unpack_dual(series)
+        primal, tangent = primal.clone(), tangent.clone()
+    F2 = ceviche_b200.fdtd(case["eps"], case["dL"], case["npml"])
+    s2, ds2 = F2.jvp_run(case["steps"], v[None], case["sources"], case["probes"])
+    assert torch.equal(primal, s2)
+    assert rel_l2(tangent.cpu().numpy(), ds2[0].cpu().numpy()) <= 1e-13
+
+    shape = case["eps"].shape
+    w = torch.as_tensor(cases.objective_weights(case["steps"], len(case["probes"]))).cuda()
+
+    def objective(c):          # two scalars in, one out: eps = c0 * eps0 + c1 * bump
+        bump = torch.zeros(shape, dtype=torch.float64, device="cuda")
+        bump[3:7, 2:6, 2:5] = 1.0
+        F = ceviche_b200.fdtd(c[0] * eps + c[1] * bump, case["dL"], case["npml"])
+        return (F.run(case["steps"], case["sources"], case["probes"]) ** 2 * w).sum()
+    x = np.array([1.0, 0.3])
+    jf = jacobian(objective, mode='forward')(x).cpu().numpy()
+    jr = jacobian(objective, mode='reverse')(x).cpu().numpy()
+    assert jf.shape == jr.shape == (1, 2)
+    assert rel_l2(jf, jr) <= 1e-10
