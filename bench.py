@@ -212,6 +212,28 @@ def cpu_leg(shape, n_steps, warm, kind, wl=None):
     return cells * n_steps / el / 1e9, el / n_steps, sample, f
 
 
+def config2_dict(shape, chunk, arith, w=8):
+    """`config` of the N = 1 line, shared by both arms (the reference arm measures a bounded sample of the same workload)."""
+    cells = shape[0] * shape[1] * shape[2]
+    return {"workload": "config 2: 3-D %dx%dx%d dielectric waveguide splitter, npml 20, Jz sheet source, 2 arm probes" % tuple(shape),
+            "time_steps_per_bench_step": chunk, "arith": arith,
+            "simulation": "one continuous run of steps x time_steps_per_bench_step time steps from zero fields (pulse at t = 2000)",
+            "l2": "state %.0f MB >> 126 MB L2 (inputs larger than L2, no flush needed)" % (cells * w * 9 / 1e6)}
+
+
+PEER_TEXT = ("direct stores into the neighbour's peer-mapped halo block from inside the half-step kernels "
+             "(CUDA IPC over NVLink), arrival counters, time loop in C")
+
+
+def config3_dict(shape, world, chunk, path_text, w=8):
+    """`config` of the N > 1 lines, shared by both arms."""
+    planes = shape[0] // world
+    local_cells = planes * shape[1] * shape[2]
+    return {"workload": "config 3: 3-D %dx%dx%d splitter, npml 20, x-slabs over %d GPUs" % (tuple(shape) + (world,)),
+            "halo_exchange": path_text, "time_steps_per_bench_step": chunk, "planes_per_gpu": planes,
+            "l2": "per-GPU state %.0f MB >> 126 MB L2" % (local_cells * w * 9 / 1e6)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -223,12 +245,25 @@ def run_reference(args):
     except MemoryError:
         shape = (128, 128, 128)
         val, sec, sample, _ = cpu_leg(shape, args.steps, args.warmup, kind)
-    sample = "one FDTD time step of the config-2 grid per bench step: " + sample
+    # the same config as our arm; each of the `steps` bench steps is a bounded sample of it: ONE time step measured,
+    # ms_per_step = that time step scaled to the bench step's time_steps_per_bench_step (the value is a rate: unaffected)
+    if args.gpus == 1:
+        scale = float(args.chunk)
+        sample = ("bounded sample: %d + %d single time steps of the config-2 run measured (ms_per_step extrapolates one to the "
+                  "%d time steps of a bench step): " % (args.warmup, args.steps, args.chunk)) + sample
+    else:     # config 3 (1024 x 1024 x 512) would need ~260 GB in the reference's 39 full-grid arrays: a 256^3 piece of the
+        # same splitter stands for it (the numpy step is memory-bound: its per-cell rate does not depend on the extent)
+        cells3 = float(args.slab_grid[0]) * args.slab_grid[1] * args.slab_grid[2]
+        scale = args.slab_chunk * cells3 / (shape[0] * shape[1] * shape[2])
+        sample = ("bounded sample of config 3: single time steps on a %dx%dx%d piece of the splitter (the reference needs "
+                  "~260 GB at the full extent); ms_per_step extrapolates by cells and by the %d time steps of a bench step: "
+                  % (shape + (args.slab_chunk,))) + sample
     line = {"impl": "reference", "metric": "Gcell-updates/s", "value": val, "unit": "Gcell/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config 2: 3-D %dx%dx%d dielectric waveguide splitter, npml 20, Jz sheet source, 2 arm probes" % shape,
-                       "sample": sample},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 * scale,
+            "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": (config2_dict(shape, args.chunk, "f64") if args.gpus == 1 else
+                       config3_dict(tuple(args.slab_grid), args.gpus, args.slab_chunk, PEER_TEXT)),
             "cpu_baseline": {"value": val, "unit": "Gcell/s", "cores": 1, "kind": kind, "sample": sample,
                              "host_cores": os.cpu_count(),
                              "note": "the reference is single-process numpy: roll / elementwise passes use 1 of the host cores"},
@@ -509,10 +544,7 @@ def run_ours(args):
     line = {"metric": "Gcell-updates/s", "value": value, "unit": "Gcell/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": "config 2: 3-D %dx%dx%d dielectric waveguide splitter, npml 20, Jz sheet source, 2 arm probes" % shape,
-                       "time_steps_per_bench_step": chunk, "arith": args.arith or args.dtype,
-                       "simulation": "one continuous run of steps x time_steps_per_bench_step time steps from zero fields (pulse at t = 2000)",
-                       "l2": "state %.0f MB >> 126 MB L2 (inputs larger than L2, no flush needed)" % (cells * w * 9 / 1e6)},
+            "config": config2_dict(shape, chunk, args.arith or args.dtype, w),
             "simulation_check": sim_check, "parity_check": parity,
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_val, "unit": "Gcell/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -597,9 +629,7 @@ def run_slabs(args, dist, dev, local, rank, world, dtype, w, hbm_peak, peak_src)
         line = {"metric": "Gcell-updates/s", "value": value, "unit": "Gcell/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-                "config": {"workload": "config 3: 3-D %dx%dx%d splitter, npml 20, x-slabs over %d GPUs" % (shape + (world,)),
-                           "halo_exchange": path, "time_steps_per_bench_step": chunk, "planes_per_gpu": hi - lo,
-                           "l2": "per-GPU state %.0f MB >> 126 MB L2" % (local_cells * w * 9 / 1e6)},
+                "config": config3_dict(shape, world, chunk, path, w),
                 "parity_check": parity,
                 "simulation_check": {"time_steps": int(series.shape[0]), "probe_series_l2": float(series.norm()),
                                      "finite": bool(torch.isfinite(series).all())},
