@@ -573,7 +573,7 @@ class _AllReduceGrad(torch.autograd.Function):
     def backward(ctx, g):
         g = g.contiguous().clone()
         if dist.is_initialized() and dist.get_world_size(ctx.group) > 1:
-            if g.is_cuda:
+            if g.is_cuda or dist.get_backend(ctx.group) != "nccl":
                 dist.all_reduce(g, group=ctx.group)
             else:                                   # NCCL groups reduce device tensors only
                 dev = torch.device("cuda", torch.cuda.current_device())

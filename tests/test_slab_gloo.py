@@ -83,3 +83,41 @@ def test_partition_and_localize():
     assert idx.tolist() == [5, 6] and w.tolist() == [1.5, -2.0]
     idx, w = localize_points(a, 4, 6, 6)
     assert idx.tolist() == [6 + 4] and w.tolist() == [3.0]
+
+
+def _grad_chain_worker(rank, world, port, shape, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    dist.init_process_group("gloo", init_method="file://" + port, rank=rank, world_size=world)
+    try:
+        from ceviche_b200.slab import SlabFDTD, _AllReduceGrad, partition
+        from slab_backend_cpu import NumpySlabBackend
+        rng = np.random.default_rng(3)
+        eps = torch.as_tensor(1 + 2 * rng.random(shape)).requires_grad_(True)
+        G = torch.as_tensor(rng.standard_normal((3,) + shape))           # stands for dL/d(1/eps_yee) of the adjoint sweep
+        lo, hi = partition(shape[0], world)[rank]
+        idx = torch.arange(lo - 1, hi) % shape[0]
+        sim = SlabFDTD(shape, _AllReduceGrad.apply(eps, None)[idx], cases.DL, [2, 0, 2], backend_factory=NumpySlabBackend)
+        loss = sum((sim._mE64[c] * G[c][lo:hi]).sum() for c in range(3))
+        (g,) = torch.autograd.grad(loss, eps)
+        np.save(out + ".%d.npy" % rank, g.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,shape", [(2, (8, 5, 4)), (3, (10, 4, 3))])
+def test_slab_gradient_chain_to_global_eps(world, shape, tmp_path):
+    """The host side of gradients on x-slabs: every rank differentiates through its slab's eps slice (with the extra plane
+    lo - 1 of the Yee average along x, utils.py:167, periodic) and the all-reduce in the backward of the slicing hands every
+    rank the complete gradient w.r.t. the global eps_r -- equal to differentiating the single-domain expression."""
+    out = str(tmp_path / "g")
+    mp.spawn(_grad_chain_worker, args=(world, _rendezvous(tmp_path), shape, out), nprocs=world, join=True)
+    rng = np.random.default_rng(3)
+    eps = torch.as_tensor(1 + 2 * rng.random(shape)).requires_grad_(True)
+    G = torch.as_tensor(rng.standard_normal((3,) + shape))
+    inv = [1 / ((eps + torch.roll(eps, 1, a)) / 2) for a in range(3)]
+    (want,) = torch.autograd.grad(sum((inv[c] * G[c]).sum() for c in range(3)), eps)
+    for r in range(world):
+        got = np.load(out + ".%d.npy" % r)
+        np.testing.assert_allclose(got, want.numpy(), rtol=1e-13, atol=1e-13)
