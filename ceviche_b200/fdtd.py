@@ -369,7 +369,11 @@ class fdtd:
         if not torch.is_tensor(J):
             J = torch.as_tensor(np.asarray(J))
         if J.is_complex():
-            raise NotImplementedError("complex J is not supported by the CUDA path")
+            # the reference raises here too: `self.Dx += Jx` (fdtd.py:125-127) adds in place into a float64 array, which
+            # numpy refuses for a complex right-hand side (UFuncTypeError, a TypeError)
+            raise TypeError("Cannot cast ufunc 'add' output from dtype('complex128') to dtype('{}') with casting rule "
+                            "'same_kind' (complex J: the reference's in-place D += J raises the same)".format(
+                                "float64" if self.dtype == torch.float64 else "float32"))
         J = J.to(device=self.device, dtype=self.dtype)
         if J.dim() < 3:
             J = J.reshape(tuple(J.shape) + (1,) * (3 - J.dim())) if J.dim() > 0 else J

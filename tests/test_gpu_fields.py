@@ -147,6 +147,8 @@ def test_reference_api_quirks():
         F.eps_r = eps                            # 2-D through the setter is an error in the reference too
     with pytest.raises(ValueError):
         ceviche_b200.fdtd(np.ones((2, 2, 2, 2)), 5e-8, [0, 0, 0])
+    with pytest.raises(TypeError):               # complex J: the reference's in-place `D += J` raises numpy's UFuncTypeError
+        F.forward(Jz=np.ones((10, 9, 1)) * (1 + 2j))     # (a TypeError; tests/test_oracle_vs_reference.py shows it)
     O = OracleFDTD(eps, 5e-8, [2, 2, 0])
     assert np.array_equal(F.eps_xx.cpu().numpy() / 2, O.eps_yee[0])
     assert repr(F) == "FDTD(eps_r.shape=(10, 9, 1), dL=5e-08, NPML=[2, 2, 0])"

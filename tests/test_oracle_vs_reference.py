@@ -54,3 +54,15 @@ def test_sigma_profiles_and_quirks():
         for q in range(4):
             assert np.array_equal(getattr(F, "mH%s%d" % (n, q + 1)) * np.ones(shape), O.mH[c][q])
             assert np.array_equal(getattr(F, "mD%s%d" % (n, q + 1)) * np.ones(shape), O.mD[c][q])
+
+
+def test_reference_rejects_complex_J():
+    """`self.Dx += Jx` (fdtd.py:125-127) is an in-place add into a float64 array: numpy raises a TypeError
+    (UFuncTypeError) for a complex J.  ceviche_b200.fdtd._as_J mirrors that (tests/test_gpu_fields.py)."""
+    ref = ref_loader.load()
+    F = ref.fdtd(np.ones((6, 5, 1)), 5e-8, [1, 1, 0])
+    J = np.zeros((6, 5, 1), dtype=complex)
+    J[3, 2, 0] = 1 + 2j
+    with pytest.raises(TypeError):
+        F.forward(Jz=J)
+
