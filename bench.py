@@ -561,21 +561,25 @@ def run_slabs(args, dist, dev, local, rank, world, dtype, w, hbm_peak, peak_src)
     as N grows (strong scaling)."""
     import torch
     import ceviche_b200
-    from ceviche_b200.slab import partition
+    from ceviche_b200.slab import XPML_PLANE_COST, partition
     shape = tuple(args.slab_grid)
     Nx, Ny, Nz = shape
     cells = Nx * Ny * Nz
     chunk = args.slab_chunk
     devices = list(range(world))
+    balance = XPML_PLANE_COST if args.balance < 0 else args.balance
 
     # ---- parity first: config 3's parity grid on the N slabs against one GPU, bit for bit --------------------
-    parity = slab_parity(dist, dev, rank, world, dtype, args.opt)
+    from ceviche_b200.slab import XPML_PLANE_COST as _cost
+    parity = slab_parity(dist, dev, rank, world, dtype, args.opt, _cost if args.balance < 0 else args.balance)
 
-    lo, hi = partition(Nx, world)[rank]
+    parts = partition(Nx, world, NPML[0], balance)      # cost-balanced: the end ranks carry the x-PML and get fewer planes
+    lo, hi = parts[rank]
     sources, probes = sparse_points(shape)
     n_total = chunk * (args.steps + args.warmup)
     wave = pulse(n_total, t0=0.5 * chunk, sigma=chunk / 8.0)[:, None]
-    sim = ceviche_b200.fdtd(splitter_eps_device(shape, dev, lo, hi), DL, NPML, dtype=dtype, devices=devices, global_shape=shape)
+    sim = ceviche_b200.fdtd(splitter_eps_device(shape, dev, lo, hi), DL, NPML, dtype=dtype, devices=devices, global_shape=shape,
+                            balance=balance)
     for kv in args.opt:
         k, v = kv.split("=")
         sim.set_option(k, int(v))
@@ -617,7 +621,8 @@ def run_slabs(args, dist, dev, local, rank, world, dtype, w, hbm_peak, peak_src)
     torch.cuda.empty_cache()
     dist.barrier()
     t0 = time.perf_counter()
-    sim2 = ceviche_b200.fdtd(eps_host.to(dev, non_blocking=True), DL, NPML, dtype=dtype, devices=devices, global_shape=shape)
+    sim2 = ceviche_b200.fdtd(eps_host.to(dev, non_blocking=True), DL, NPML, dtype=dtype, devices=devices, global_shape=shape,
+                             balance=balance)
     sim2.prepare(sources, probes)
     for q in range(3):
         sim2.run(chunk, waveforms=wave_host[q * chunk:(q + 1) * chunk].to(dev, non_blocking=True)).cpu()
@@ -650,7 +655,7 @@ def run_slabs(args, dist, dev, local, rank, world, dtype, w, hbm_peak, peak_src)
         sys.exit(3)
 
 
-def slab_parity(dist, dev, rank, world, dtype, opts=()):
+def slab_parity(dist, dev, rank, world, dtype, opts=(), balance=0.0):
     """BASELINE config 3's parity grid (256 x 128 x 64, npml 20) for 30 steps on the N slabs and on one GPU
     (every rank computes the single-GPU answer itself): all nine fields and the probe series must agree bit for bit."""
     import torch
@@ -677,9 +682,10 @@ def slab_parity(dist, dev, rank, world, dtype, opts=()):
     f1 = {k: one_gpu.fields[k].clone() for k in keys}
     del one_gpu
 
-    lo, hi = partition(shape[0], world)[rank]
+    parts = partition(shape[0], world, NPML[0], balance)       # the same (cost-balanced, uneven) cut as the timed run
+    lo, hi = parts[rank]
     eps_local = np.concatenate([eps[(lo - 1) % shape[0]][None], eps[lo:hi]], 0)
-    sim = ceviche_b200.fdtd(eps_local, DL, NPML, dtype=dtype, devices=list(range(world)), global_shape=shape)
+    sim = ceviche_b200.fdtd(eps_local, DL, NPML, dtype=dtype, devices=list(range(world)), global_shape=shape, balance=balance)
     for kv in opts:
         k, v = kv.split("=")
         sim.set_option(k, int(v))
@@ -691,7 +697,8 @@ def slab_parity(dist, dev, rank, world, dtype, opts=()):
     series_err = float((sN - s1).abs().max() / s1.abs().max())
     flag = torch.tensor([1.0 if (ok and series_err <= 1e-11) else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    res = {"ranks": world, "grid": list(shape), "time_steps": steps, "halo_exchange": sim.slab_path(),
+    res = {"ranks": world, "grid": list(shape), "planes_per_rank": [b - a for a, b in parts], "time_steps": steps,
+           "halo_exchange": sim.slab_path(),
            "bitwise_equal": bool(flag.item() == 1.0), "fields_compared": 9, "series_max_rel_diff": series_err,
            "vs": "the same grid stepped on one GPU (itself <= 1e-10 from the CPU oracle: tests/test_gpu_slab.py)"}
     del sim
@@ -711,6 +718,7 @@ def main():
     ap.add_argument("--grid", type=int, nargs=3, default=[256, 256, 256])
     ap.add_argument("--slab-grid", type=int, nargs=3, default=[1024, 1024, 512], help="global grid for N > 1 (config 3)")
     ap.add_argument("--slab-chunk", type=int, default=200, help="FDTD time steps per bench step for N > 1")
+    ap.add_argument("--balance", type=float, default=-1.0, help="x-PML plane cost of the slab partition (-1: the measured default, 0: equal plane counts)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline + oracle parity legs")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel tuning runs)")
     ap.add_argument("--no-extra", action="store_true", help="skip the other-dtype / 512^3 / scale-anchor measurements")

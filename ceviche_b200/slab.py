@@ -39,15 +39,35 @@ from .constants import C_0
 from .fdtd import _FIELD_CODE, _COMP, _PML_FAMILIES, reshape_to_ND, sigma_profiles
 
 
-def partition(Nx, P):
-    """Contiguous x-ranges [(lo, hi)] of P slabs, sizes differing by at most one plane."""
-    base, extra = divmod(Nx, P)
-    out, lo = [], 0
-    for r in range(P):
-        hi = lo + base + (1 if r < extra else 0)
-        out.append((lo, hi))
-        lo = hi
-    return out
+# Relative extra cost of an x-plane inside the x-PML in the half-step kernels (all three components take the PML path and
+# read-modify-write their integral there): measured on B200, scripts/slab_plane_cost.py (0.26 fp64 / 0.22 fp32).
+XPML_PLANE_COST = 0.25
+
+
+def partition(Nx, P, npml_x=0, alpha=0.0):
+    """Contiguous x-ranges [(lo, hi)] of P slabs.  alpha = 0: sizes differing by at most one plane.  alpha > 0: planes
+    inside the x-PML (the first and last npml_x planes) count 1 + alpha, and the slabs get equal COST -- the ring runs at
+    the pace of its slowest rank, and the two end ranks would otherwise carry all of the x-PML work."""
+    if alpha <= 0 or npml_x <= 0 or P < 3:
+        base, extra = divmod(Nx, P)
+        out, lo = [], 0
+        for r in range(P):
+            hi = lo + base + (1 if r < extra else 0)
+            out.append((lo, hi))
+            lo = hi
+        return out
+    cost = np.ones(Nx)
+    cost[:min(npml_x, Nx)] += alpha
+    cost[max(0, Nx - npml_x):] += alpha
+    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    cuts = [0]
+    for r in range(1, P):
+        target = cum[-1] * r / P
+        c = int(np.argmin(np.abs(cum - target)))
+        c = max(c, cuts[-1] + 2)                 # every slab keeps at least 2 planes
+        cuts.append(min(c, Nx - 2 * (P - r)))
+    cuts.append(Nx)
+    return [(cuts[r], cuts[r + 1]) for r in range(P)]
 
 
 def localize_points(arr, lo, hi, plane):
@@ -225,7 +245,7 @@ class SlabFDTD:
     materialise on every rank."""
 
     def __init__(self, global_shape, eps_local, dL, npml, *, dtype=torch.float64, device=None, group=None,
-                 backend_factory=None, path=None, arith=None, _ring=None):
+                 backend_factory=None, path=None, arith=None, balance=0.0, _ring=None):
         self.group = group
         if _ring is not None:                     # several slabs in one process (tests): (rank, world)
             self.rank, self.P = _ring
@@ -237,7 +257,9 @@ class SlabFDTD:
         self.N = self.Nx * self.Ny * self.Nz
         if self.Ny <= 1 and self.Nz <= 1:
             raise ValueError("slab decomposition needs a 2-D or 3-D grid (Ny > 1 or Nz > 1)")
-        self.lo, self.hi = partition(self.Nx, self.P)[self.rank]
+        self.balance = float(balance)      # x-PML plane cost of the partition (0 = equal plane counts); see partition()
+        self._parts = partition(self.Nx, self.P, int(npml[0]), self.balance)
+        self.lo, self.hi = self._parts[self.rank]
         self.nx = self.hi - self.lo
         if self.P > 1 and self.nx < 2:
             raise ValueError("each slab needs at least 2 x-planes")
@@ -548,7 +570,7 @@ class SlabFDTD:
         loc = loc if torch.is_tensor(loc) else torch.as_tensor(loc)
         if self.P == 1 or self._in_process:
             return loc
-        sizes = [hi - lo for lo, hi in partition(self.Nx, self.P)]
+        sizes = [hi - lo for lo, hi in self._parts]
         outs = [torch.empty((s, self.Ny, self.Nz), dtype=loc.dtype, device=loc.device) for s in sizes]
         dist.all_gather(outs, loc.contiguous(), group=self.group) if len(set(sizes)) == 1 else self._gather_uneven(outs, loc)
         return torch.cat(outs, 0)
@@ -701,7 +723,7 @@ class _SlabRunFn(torch.autograd.Function):
 
 
 def make_slab_fdtd(eps_r, dL, npml, *, devices, global_shape=None, dtype=torch.float64, device=None, arith=None,
-                   group=None, path=None):
+                   group=None, path=None, balance=None):
     """What `ceviche_b200.fdtd(eps_r, dL, npml, devices=[...])` builds: one SlabFDTD per process.  `devices` lists the
     CUDA device of every slab in rank order (one process per GPU, torch.distributed initialised with that many ranks)."""
     P = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -711,13 +733,18 @@ def make_slab_fdtd(eps_r, dL, npml, *, devices, global_shape=None, dtype=torch.f
     if device is None:
         d = devices[rank]
         device = torch.device("cuda", d) if isinstance(d, int) else torch.device(d)
+    # balance: None = automatic (cost-balanced slabs when the global eps_r is sliced here; equal plane counts when the
+    # caller pre-sliced its slab, who then says which partition it used)
+    if balance is None:
+        balance = XPML_PLANE_COST if global_shape is None else 0.0
     if global_shape is None:
         e = torch.as_tensor(np.asarray(eps_r, dtype=np.float64)) if not torch.is_tensor(eps_r) else eps_r
         e = reshape_to_ND(e, 3)
         global_shape = tuple(e.shape)
-        lo, hi = partition(global_shape[0], P)[rank]
+        lo, hi = partition(global_shape[0], P, int(npml[0]), balance)[rank]
         idx = torch.arange(lo - 1, hi) % global_shape[0]
         if torch.is_tensor(e) and e.requires_grad:     # every rank ends up with the complete gradient w.r.t. eps_r
             e = _AllReduceGrad.apply(e, group)
         eps_r = e[idx.to(e.device)]
-    return SlabFDTD(global_shape, eps_r, dL, npml, dtype=dtype, device=device, group=group, path=path, arith=arith)
+    return SlabFDTD(global_shape, eps_r, dL, npml, dtype=dtype, device=device, group=group, path=path, arith=arith,
+                    balance=balance)
