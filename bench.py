@@ -567,7 +567,7 @@ def run_slabs(args, dist, dev, local, rank, world, dtype, w, hbm_peak, peak_src)
     cells = Nx * Ny * Nz
     chunk = args.slab_chunk
     devices = list(range(world))
-    balance = XPML_PLANE_COST if args.balance < 0 else args.balance
+    balance = XPML_PLANE_COST if args.balance < 0 else args.balance      # (default 0: equal plane counts)
 
     # ---- parity first: config 3's parity grid on the N slabs against one GPU, bit for bit --------------------
     from ceviche_b200.slab import XPML_PLANE_COST as _cost
@@ -718,7 +718,9 @@ def main():
     ap.add_argument("--grid", type=int, nargs=3, default=[256, 256, 256])
     ap.add_argument("--slab-grid", type=int, nargs=3, default=[1024, 1024, 512], help="global grid for N > 1 (config 3)")
     ap.add_argument("--slab-chunk", type=int, default=200, help="FDTD time steps per bench step for N > 1")
-    ap.add_argument("--balance", type=float, default=-1.0, help="x-PML plane cost of the slab partition (-1: the measured default, 0: equal plane counts)")
+    ap.add_argument("--balance", type=float, default=0.0,
+                    help="x-PML plane cost of the slab partition (0: equal plane counts, the default; -1: the measured plane cost "
+                         "0.25 -- cost-balanced slabs, measured neutral on 8 B200)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline + oracle parity legs")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (kernel tuning runs)")
     ap.add_argument("--no-extra", action="store_true", help="skip the other-dtype / 512^3 / scale-anchor measurements")

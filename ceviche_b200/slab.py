@@ -733,10 +733,11 @@ def make_slab_fdtd(eps_r, dL, npml, *, devices, global_shape=None, dtype=torch.f
     if device is None:
         d = devices[rank]
         device = torch.device("cuda", d) if isinstance(d, int) else torch.device(d)
-    # balance: None = automatic (cost-balanced slabs when the global eps_r is sliced here; equal plane counts when the
-    # caller pre-sliced its slab, who then says which partition it used)
+    # balance: x-PML plane cost of the partition (see partition()); None / 0 = equal plane counts, the default: the
+    # cost-balanced cut (XPML_PLANE_COST) was measured neutral on 8 B200 (280.7 vs 277.3 Gcell/s fp64, 545.3 vs 545.9 fp32:
+    # under the power cap the ring is paced by its slowest GPU, not by the x-PML planes of the end ranks)
     if balance is None:
-        balance = XPML_PLANE_COST if global_shape is None else 0.0
+        balance = 0.0
     if global_shape is None:
         e = torch.as_tensor(np.asarray(eps_r, dtype=np.float64)) if not torch.is_tensor(eps_r) else eps_r
         e = reshape_to_ND(e, 3)
