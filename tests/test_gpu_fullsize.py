@@ -105,3 +105,90 @@ def test_full_size_linearity_is_exact_for_power_of_two_scales(dtype):
             assert int(clear.sum()) > 1000, k
             assert torch.equal(a[clear], b[clear]), k
             assert float((a - b)[~clear].abs().max()) <= 1e-32, k
+
+
+def test_config4_full_size_gradient_properties():
+    """Config 4 at its stated size (256 x 256 x 128, npml 20, 64 x 64 x 32 design box): size-independent checks of the
+    reverse sweep.  (i) the design-box gradient from the D-box record (tensor-map kernels, no recomputation)
+    equals the every-cell gradient (checkpoints + recomputation) inside the box; (ii) <grad, v> equals the directional
+    derivative of the forward-mode tangent sweep for a random v in the box; (iii) ... and a central finite difference of
+    the forward run."""
+    import ceviche_b200
+    shape, steps = (256, 256, 128), 320
+    box = ((96, 160), (96, 160), (48, 80))
+    sl = tuple(slice(lo, hi) for lo, hi in box)
+    rng = np.random.default_rng(1)
+    eps_np = np.ones(shape)
+    eps_np[sl] = 1 + 4.95 * rng.random((64, 64, 32))
+    prof = np.zeros(shape); prof[84, 123:133, 61:67] = 1.0                 # sheet source just before the box
+    mask = np.zeros(shape); mask[170, 118:138, 58:70] = rng.random((20, 12))    # weighted probe just behind it
+    t = np.arange(steps)
+    wave = 5 * np.exp(-(t - 60) ** 2 / (2 * 20.0 ** 2)) * np.cos(0.25 * t)
+    srcs, probes = [("z", prof, wave)], [("Ez", mask)]
+    w = torch.as_tensor(rng.random((steps, 1))).cuda()
+
+    def loss_of(eps_t, region):
+        F = ceviche_b200.fdtd(eps_t, DL, NPML)
+        F.design_region = region
+        return (F.run(steps, srcs, probes) ** 2 * w).sum()
+
+    grads = {}
+    for region in (None, box):
+        eps = torch.as_tensor(eps_np).cuda().requires_grad_(True)
+        L = loss_of(eps, region)
+        (g,) = torch.autograd.grad(L, eps)
+        grads[region is not None] = g[sl].clone()
+        del g, eps
+        torch.cuda.empty_cache()
+    assert float(grads[True].abs().max()) > 0
+    assert rel_l2(grads[True].cpu().numpy(), grads[False].cpu().numpy()) <= 1e-12
+    # (ii) the tangent sweep
+    v = torch.zeros(shape, dtype=torch.float64, device="cuda")
+    v[sl] = torch.as_tensor(rng.standard_normal((64, 64, 32))).cuda()
+    F = ceviche_b200.fdtd(eps_np, DL, NPML)
+    series, dseries = F.jvp_run(steps, v[None], srcs, probes)
+    d_fwd = float((2 * series * w * dseries[0]).sum())
+    d_rev = float((grads[True] * v[sl]).sum())
+    assert abs(d_fwd - d_rev) <= 1e-10 * abs(d_fwd), (d_fwd, d_rev)
+    # (iii) central finite difference of the forward run
+    h = 1e-5
+    with torch.no_grad():
+        eps0 = torch.as_tensor(eps_np).cuda()
+        fd = (float(loss_of(eps0 + h * v, None)) - float(loss_of(eps0 - h * v, None))) / (2 * h)
+    assert abs(fd - d_rev) <= 1e-6 * abs(fd), (fd, d_rev)
+
+
+def test_config5_full_size_batched_tangents():
+    """Config 5 at its stated grid (2-D 2048 x 2048 grating coupler, 16 fill-factor directions through the sigmoid
+    projection, examples/forwardmode_grating_coupler.py:138-162): the batched tangent launches are bit-identical to one
+    launch per tangent, and a tangent equals a central finite difference of the forward run."""
+    import ceviche_b200
+    from ceviche_b200.parametrization import grating_coupler
+    steps, B = 260, 16
+    G = grating_coupler(2048, 2048, DL, 20, groups=B)
+    ff = torch.full((B,), 0.5, dtype=torch.float64, device="cuda")
+    eps, V = G.eps_r(ff), G.fill_factor_directions(ff)
+    shape = (2048, 2048, 1)
+    prof = np.zeros(shape); prof[1000, G.y_base[0]:G.y_teeth[1], 0] = 1.0          # sheet across the slab, mid-grating
+    mask = np.zeros(shape); mask[900:1100, G.y_teeth[1] + 6, 0] = 1.0                # line probe just above the teeth
+    t = np.arange(steps)
+    wave = np.exp(-(t - 60) ** 2 / (2 * 20.0 ** 2)) * np.cos(0.3 * t)
+    srcs, probes = [("z", prof, wave)], [("Ez", mask)]
+    out = {}
+    for batch in (0, -1):
+        F = ceviche_b200.fdtd(eps, DL, [20, 20, 0])
+        F.set_option("jvp_batch", batch)
+        out[batch] = F.jvp_run(steps, V, srcs, probes)
+        assert F._active == 0b011100
+    assert torch.equal(out[0][0], out[-1][0]) and torch.equal(out[0][1], out[-1][1])
+    series, dseries = out[-1]
+    norms = dseries.flatten(1).norm(dim=1)
+    assert float(norms.max()) > 0
+    b = int(norms.argmax())                                   # the tooth group under the source / probe
+    h = 1e-5
+    runs = []
+    for sgn in (+1, -1):
+        F = ceviche_b200.fdtd(eps + sgn * h * V[b], DL, [20, 20, 0])
+        runs.append(F.run(steps, srcs, probes))
+    fd = (runs[0] - runs[1]) / (2 * h)
+    assert rel_l2(dseries[b].cpu().numpy(), fd.cpu().numpy()) <= 1e-6
