@@ -214,9 +214,11 @@ def test_hips_autograd_registration_callables():
 
 
 @pytest.mark.parametrize("every", [None, 5])
-@pytest.mark.parametrize("dtype,shape,region", [(torch.float64, (12, 8, 64), None), (torch.float64, (9, 12, 70), ((2, 7), (3, 9), (20, 61))),
-                                                (torch.float32, (10, 12, 128), None)])
-def test_tensor_map_adjoint_matches_simple_kernels(dtype, shape, region, every):
+@pytest.mark.parametrize("dtype,shape,region,arith", [(torch.float64, (12, 8, 64), None, None),
+                                                      (torch.float64, (9, 12, 70), ((2, 7), (3, 9), (20, 61)), None),
+                                                      (torch.float32, (10, 12, 128), None, None),
+                                                      (torch.float32, (10, 12, 128), ((2, 8), (3, 9), (30, 100)), "f64")])
+def test_tensor_map_adjoint_matches_simple_kernels(dtype, shape, region, arith, every):
     """cev_fdtd_adjoint_run's tensor-map kernels (csrc/adjoint_v5.cuh: the transposed step re-phased into two marching
     kernels, cotangents in the eager form) against the simple transposed-step kernels (csrc/adjoint.cuh, themselves
     <= 1e-10 from the autograd oracle above) on grids the tensor-map tiles serve: PML on all axes, probes on E / D / H
@@ -226,7 +228,7 @@ def test_tensor_map_adjoint_matches_simple_kernels(dtype, shape, region, every):
     grads = {}
     for variant in (1, 2):
         eps = torch.as_tensor(case["eps"]).cuda().requires_grad_(True)
-        F = ceviche_b200.fdtd(eps, case["dL"], case["npml"], dtype=dtype)
+        F = ceviche_b200.fdtd(eps, case["dL"], case["npml"], dtype=dtype, arith=arith)
         F.set_option("adjoint_variant", variant)
         F.design_region = region
         series = F.run(case["steps"], case["sources"], case["probes"], checkpoint_every=every)
