@@ -204,6 +204,9 @@ class _RunFn(torch.autograd.Function):
         ctx.sim, ctx.steps, ctx.waveforms = sim, steps, waveforms
         ctx.record = None
         box = _grad_box(sim)
+        if box is None and getattr(sim, "design_region", None) is None and getattr(sim, "record_whole_grid", True):
+            # gradient of every cell: the same trick with the whole grid as the box, where the record fits in memory
+            box = [(0, int(n)) for n in sim.grid_shape]
         if box is not None and every is None and steps > 0 and _record_fits(sim, box, steps):
             # gradients wanted inside a design box only: record D of the box after every step instead of checkpointing the
             # state -- the reverse sweep then needs no recomputation at all (cev_fdtd_adjoint_run_boxed)

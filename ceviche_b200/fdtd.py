@@ -165,6 +165,9 @@ class fdtd:
         # ((x0, x1), (y0, y1), (z0, z1)) or None: reverse-mode gradients w.r.t. eps_r are only wanted inside this box
         # (the region being optimised); outside it the adjoint sweep skips the dL/d(1/eps) accumulation and returns 0
         self.design_region = None
+        # without a design region: record D of the WHOLE grid per step when that fits in a quarter of the free memory (no
+        # checkpoints, no recomputation in the reverse sweep; the forward run pays one extra copy of D per step)
+        self.record_whole_grid = True
 
         eps_r = self._as_eps(eps_r, pad=True)
         self.Nx, self.Ny, self.Nz = self.grid_shape = tuple(eps_r.shape)
