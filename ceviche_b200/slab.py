@@ -498,7 +498,14 @@ class SlabFDTD:
             if self.path == "nccl":
                 self._wait()     # leave no message in flight; the D halo is in place for a following run()
             if self.n_probes:
-                dist.all_reduce(series, group=self.group)
+                # sum of the ranks' partial series in RANK ORDER (all-gather + a fixed-order sum): an all-reduce picks its
+                # reduction order by message size and ring / tree algorithm, so a run split into two run() calls differed
+                # from the unsplit one in the last bit on 4 ranks
+                parts = [torch.empty_like(series) for _ in range(P)]
+                dist.all_gather(parts, series.contiguous(), group=self.group)
+                series = parts[0].clone()
+                for r in range(1, P):
+                    series += parts[r]
             if self.path == "peer":
                 self._peer_check()
         return series
