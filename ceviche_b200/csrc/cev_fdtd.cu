@@ -1750,6 +1750,8 @@ int cev_fdtd_destroy(cev_fdtd* p) {
     DeviceGuard guard(p->device);
     p->drop_graphs();
     p->stage_w.release(); p->stage_p.release();
+    p->adj_stage_w.release(); p->adj_stage_g.release();
+    p->batch_tab_H.release(); p->batch_tab_D.release();
     if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
     for (auto q : p->side) cudaStreamDestroy(q);
     for (auto e : p->side_ev) cudaEventDestroy(e);
