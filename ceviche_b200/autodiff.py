@@ -76,6 +76,9 @@ def _grad_box(sim):
         lo, hi = int(lo), int(hi)
         if not (0 <= lo < hi <= n):
             raise ValueError("design_region {} outside the grid {}".format(region, sim.grid_shape))
+        if lo == 0 and hi == n:          # the whole axis (e.g. the z axis of a 2-D grid): nothing to add
+            box.append((0, n))
+            continue
         if hi + 1 > n:
             return None
         box.append((lo, hi + 1))

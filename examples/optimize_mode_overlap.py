@@ -35,17 +35,33 @@ def build(Nx=120, Ny=80, npml=10, dL=5e-8, lambda0=1.0e-6, steps=600):
     return dict(eps=eps, design=design, src=src, prb=prb, wave=wave, dL=dL, npml=npml, steps=steps)
 
 
-def make_objective(P, device="cuda"):
+def make_objective(P, device="cuda", blur_radius=0, beta=None, eta=0.5):
+    """blur_radius > 0 / beta given: the design density goes through the reference examples' parametrisation first --
+    blur inside the design region (make_rho) and tanh projection (operator_proj), examples/optimize_mode_converter.py:51-72
+    -- and torch differentiates through it on the way back."""
+    from ceviche_b200.parametrization import make_rho, operator_proj
     eps0 = torch.as_tensor(P["eps"], device=device)
     design = torch.as_tensor(P["design"], device=device)
     n_design = int(design.sum())
     F = ceviche_b200.fdtd(eps0, P["dL"], [P["npml"], P["npml"], 0])
+    # the reverse sweep only needs dL/d(1/eps) inside the design region: no recomputation where the grid allows it
+    ix, iy = torch.nonzero(design[:, :, 0], as_tuple=True)
+    F.design_region = ((int(ix.min()), int(ix.max()) + 1), (int(iy.min()), int(iy.max()) + 1), (0, 1))
 
     def objective(rho):
         """rho in [0, 1] per design cell -> (transmitted mode energy, d/d rho)"""
         rho = rho.detach().clone().requires_grad_(True)
+        dens = rho
+        if blur_radius > 0 or beta is not None:
+            full = torch.zeros(design.shape[:2], dtype=torch.float64, device=device)
+            full = full.masked_scatter(design[:, :, 0], rho)
+            if blur_radius > 0:
+                full = make_rho(full, design[:, :, 0], radius=blur_radius)
+            if beta is not None:
+                full = operator_proj(full, eta=eta, beta=beta)
+            dens = full[design[:, :, 0]]
         eps = eps0.clone()
-        eps[design] = 1.0 + 3.0 * rho
+        eps[design] = 1.0 + 3.0 * dens
         F.eps_r = eps                                                   # fields reset, new graph (fdtd.py:63-72)
         series = F.run(P["steps"], [("z", P["src"], P["wave"])], [("Ez", P["prb"])])
         val = (series ** 2).sum()

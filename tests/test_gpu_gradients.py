@@ -180,6 +180,13 @@ def test_inverse_design_loop_improves_mode_overlap():
     assert abs(float(fd) - float(g0 @ d)) <= 1e-6 * abs(float(fd))
     rho, hist = adam_optimize(objective, rho0, True, step_size=0.1, Nsteps=4, bounds=(0.0, 1.0), direction="max", verbose=False)
     assert hist[-1] > hist[0] > 0 and float(rho.min()) >= 0.0 and float(rho.max()) <= 1.0
+    # the same loop with the reference examples' parametrisation in front (blur inside the design region + tanh
+    # projection, examples/optimize_mode_converter.py:51-72): torch chains through it
+    objective2, _ = ex.make_objective(P, blur_radius=2, beta=6.0)
+    rho1 = torch.as_tensor(np.random.default_rng(1).random(n), device="cuda")
+    v1, g1 = objective2(rho1)
+    fd = (objective2(rho1 + h * d)[0] - objective2(rho1 - h * d)[0]) / (2 * h)
+    assert abs(float(fd) - float(g1 @ d)) <= 1e-6 * abs(float(fd))
 
 
 def test_hips_autograd_registration_callables():

@@ -174,6 +174,8 @@ def test_design_region_boxes():
     assert autodiff._grad_box(sim) is None
     sim.design_region = None
     assert autodiff._grad_box(sim) is None
+    sim2d = types.SimpleNamespace(design_region=((2, 5), (1, 4), (0, 1)), grid_shape=(8, 6, 1))
+    assert autodiff._grad_box(sim2d) == [(2, 6), (1, 5), (0, 1)]          # a full axis needs no extra cell
     sim.design_region = ((2, 9), (1, 4), (0, 3))
     with pytest.raises(ValueError):
         autodiff._grad_box(sim)
