@@ -184,7 +184,9 @@ def make_cpu_sim(eps, kind):
         F = reference_class()(eps, DL, NPML)
         return (lambda Jz: F.forward(Jz=Jz)), "ceviche/fdtd.py (unmodified reference, numpy, 1 thread)"
     if kind == "c":
+        from oracle import fdtd_c
         from oracle.fdtd_c import OracleFDTDC
+        fdtd_c.set_threads(os.cpu_count() or 1)      # (torchrun exports OMP_NUM_THREADS=1: use every host core anyway)
         sim = OracleFDTDC(eps, DL, NPML)
         return (lambda Jz: sim.step(Jz=Jz)), "oracle/fdtd_c.c (fused C restatement, gcc -O2 -fopenmp)"
     from oracle.fdtd_numpy import OracleFDTD

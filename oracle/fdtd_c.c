@@ -11,6 +11,21 @@
  * Arrays are C-order (Nx, Ny, Nz) doubles; v[c] = component c (x, y, z).  */
 #include <stddef.h>
 #include <stdint.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* n > 0: use n OpenMP threads from now on (launchers such as torchrun export OMP_NUM_THREADS=1).  Returns the thread
+ * count parallel regions will use. */
+int oracle_omp_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 #define IDX(i, j, k) (((size_t)(i) * Ny + (j)) * Nz + (k))
 

@@ -38,8 +38,15 @@ def load():
         P = C.POINTER(C.c_double)
         lib.oracle_fdtd_step.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double] + [P * 3] * 7 + [P * 12, P * 12, P * 3, P * 3]
         lib.oracle_fdtd_step.restype = None
+        lib.oracle_omp_threads.argtypes = [C.c_int]
+        lib.oracle_omp_threads.restype = C.c_int
         _lib = lib
     return _lib
+
+
+def set_threads(n=0):
+    """Use n OpenMP threads (0 = leave as is); returns the number parallel regions will use."""
+    return int(load().oracle_omp_threads(int(n)))
 
 
 def _p(a):
