@@ -21,6 +21,7 @@
 #include "step_v4.cuh"
 #include "step_v5.h"
 #include "adjoint_v5.h"
+#include "tan2d_fused.cuh"
 #include "adjoint.cuh"
 
 namespace {
@@ -175,6 +176,9 @@ struct cev_fdtd {
     int jvp_batch = -1;          // -1 auto / 1: the B tangent half-steps of a forward-mode sweep as ONE launch each
                                  // (k_step_{H,D}_v2_batch) wherever the marching kernels serve them; 0: one launch per tangent
     DeviceBuf batch_tab_H, batch_tab_D;     // per-tangent StepArgs of those launches
+    int jvp_fused = -1;          // -1 auto / 1: 2-D TM tangent states advance by the fused full-step kernel (tan2d_fused.cuh),
+                                 // ping-ponged between the caller's arrays and tan_shadow; 0: the batched two-kernel path
+    DeviceBuf batch_tab_F0, batch_tab_F1, tan_shadow;
     int jvp_streams = -1;        // -1 auto (2-D grids <= 2^23 cells, any grid <= 2^20 cells), 0 never, 1 always
     uint64_t epoch = 1;          // bumped whenever sources, probes or options change
     int use_graph = -1;          // -1 auto (small grids), 0 never, 1 whenever possible
@@ -991,6 +995,93 @@ int launch_tangent_batch(cev_fdtd* p, int which, int B, int n_tiles, int aux, un
     return 0;
 }
 
+// ---- forward-mode sweep on 2-D TM grids with the fused tangent step (tan2d_fused.cuh) -------------------------------
+// Per time step: ONE launch advances all B tangent states by a whole step (it reads the primal D of the previous step, so
+// it goes first), then the primal H and D half-steps.  The tangent states ping-pong between the caller's arrays (even
+// steps read them) and plan-owned shadows; after an odd number of steps the shadows are copied back.
+// Returns 1 if it ran, 0 if this plan / state is not served, -1 on error.
+template <typename T, typename AT>
+int jvp_loop_fused2d(cev_fdtd* p, const cev_state* st, int B, const cev_state* tst, const cev_tangent* tan, int64_t nsteps,
+                     const double* waveform, double* partials, double* tpartials, cudaStream_t s) {
+    constexpr int V = vec_width<T>();
+    const int64_t Nx = p->N[0];
+    if (!p->jvp_fused || p->halo.on() || p->N[1] != 1 || p->on != (unsigned)MASK_TM || nsteps < 1) return 0;
+    const int64_t stride = nsteps * p->n_slots;
+    const int Nz = p->N[2];
+    const size_t es = sizeof(T);
+    const size_t nfield = (size_t)Nx * Nz * es, nI0 = (size_t)std::max(p->nH[0], 0) * Nz * es, nI2 = (size_t)Nx * std::max(p->nH[2], 0) * es;
+    auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t per = 3 * up(nfield) + up(nI0) + up(nI2);
+    std::vector<StepArgs<T, AT>> tabA((size_t)B), tabB((size_t)B);
+    if (p->tan_shadow.bytes < per * (size_t)B) {
+        p->tan_shadow.release();
+        if (p->tan_shadow.alloc(per * (size_t)B)) return -1;
+    }
+    for (int b = 0; b < B; ++b) {
+        StepArgs<T, AT>& a = tabA[b];
+        if (fill_args(p, &tst[b], a, &tan[b])) return -1;
+        if (!can_march(p, a, true)) return 0;
+        unsigned char* base = (unsigned char*)p->tan_shadow.p + per * (size_t)b;
+        T* sD = (T*)base;
+        T* sH0 = (T*)(base + up(nfield));
+        T* sH2 = (T*)(base + 2 * up(nfield));
+        T* sI0 = (T*)(base + 3 * up(nfield));
+        T* sI2 = (T*)(base + 3 * up(nfield) + up(nI0));
+        a.ntz = (Nz + V2_BY * 32 * V - 1) / (V2_BY * 32 * V);
+        // measured on B200 (profiles/r2_tune_fused_tangent_step.log): fp32 (four cells per thread, half as many CTAs) wants
+        // shorter chunks than fp64
+        a.xchunk = p->xchunk > 0 ? p->xchunk : (sizeof(T) == 4 ? 16 : 32);
+        a.n_tiles = a.ntz * (int)((Nx + a.xchunk - 1) / a.xchunk);
+        a.aux_slot0 = 0;
+        a.partials = tpartials ? tpartials + b * stride : nullptr;
+        a.t_probe = -1;
+        StepArgs<T, AT>& bb = tabB[b];
+        bb = a;
+        // A: caller -> shadow
+        a.Hout[0] = sH0; a.Hout[2] = sH2; a.Dout[1] = sD; a.ICEout[0] = sI0; a.ICEout[2] = sI2;
+        // B: shadow -> caller
+        bb.Hin[0] = sH0; bb.Hin[2] = sH2; bb.Din[1] = sD; bb.ICE[0] = sI0; bb.ICE[2] = sI2;
+        bb.ICEout[0] = a.ICE[0]; bb.ICEout[2] = a.ICE[2];
+        if (b > 0 && a.n_tiles != tabA[0].n_tiles) return 0;
+    }
+    const size_t tbytes = (size_t)B * sizeof(StepArgs<T, AT>);
+    for (DeviceBuf* buf : {&p->batch_tab_F0, &p->batch_tab_F1})
+        if (buf->bytes < tbytes) {
+            buf->release();
+            if (buf->alloc(tbytes)) return -1;
+        }
+    CUDA_TRY(cudaMemcpyAsync(p->batch_tab_F0.p, tabA.data(), tbytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(p->batch_tab_F1.p, tabB.data(), tbytes, cudaMemcpyHostToDevice, s));
+    const int n_tiles = tabA[0].n_tiles;
+    const int aux = (tpartials && p->n_slots > 0) ? p->n_slots : 0;
+    const dim3 blk(32, V2_BY);
+    for (int64_t n = 0; n < nsteps; ++n) {
+        const StepArgs<T, AT>* tab = (const StepArgs<T, AT>*)((n & 1) ? p->batch_tab_F1.p : p->batch_tab_F0.p);
+        const unsigned g = (unsigned)(n_tiles + (n > 0 ? aux : 0)) * (unsigned)B;
+        k_tan2d_fused_batch<T, AT, V><<<g, blk, 0, s>>>(tab, B, n - 1);
+        CUDA_TRY(cudaGetLastError());
+        if (launch_H<T, AT>(p, st, nullptr, nullptr, 0, Nx, n - 1, partials, s)) return -1;
+        if (launch_D<T, AT>(p, st, nullptr, nullptr, nullptr, nullptr, nullptr, waveform ? waveform + n * p->nsrc : nullptr, 0, Nx,
+                            n, partials, s))
+            return -1;
+    }
+    if (nsteps & 1)      // the final tangent states live in the shadows
+        for (int b = 0; b < B; ++b) {
+            const StepArgs<T, AT>& a = tabA[b];
+            CUDA_TRY(cudaMemcpyAsync((void*)a.Hin[0], a.Hout[0], nfield, cudaMemcpyDeviceToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync((void*)a.Hin[2], a.Hout[2], nfield, cudaMemcpyDeviceToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync((void*)a.Din[1], a.Dout[1], nfield, cudaMemcpyDeviceToDevice, s));
+            if (nI0) CUDA_TRY(cudaMemcpyAsync(a.ICE[0], a.ICEout[0], nI0, cudaMemcpyDeviceToDevice, s));
+            if (nI2) CUDA_TRY(cudaMemcpyAsync(a.ICE[2], a.ICEout[2], nI2, cudaMemcpyDeviceToDevice, s));
+        }
+    if (launch_probe_only<T, AT>(p, st, nullptr, 0, nsteps - 1, partials, s)) return -1;
+    for (int b = 0; b < B; ++b)
+        for (int which = 0; which < 2; ++which)
+            if (launch_probe_only<T, AT>(p, &tst[b], &tan[b], which, nsteps - 1, tpartials ? tpartials + b * stride : nullptr, s))
+                return -1;
+    return 1;
+}
+
 // Primal + B tangents in one sweep.  Per step: tangent H half-steps first (they need the primal D of
 // the previous step), then the primal step, then the tangent D half-steps (same linear update, J = 0).
 template <typename T, typename AT>
@@ -998,6 +1089,10 @@ int jvp_loop(cev_fdtd* p, const cev_state* st, int B, const cev_state* tst, cons
              const double* waveform, double* partials, double* tpartials, cudaStream_t s) {
     const int64_t Nx = p->N[0];
     const int64_t stride = nsteps * p->n_slots;
+    {
+        const int rc = jvp_loop_fused2d<T, AT>(p, st, B, tst, tan, nsteps, waveform, partials, tpartials, s);
+        if (rc != 0) return rc < 0 ? -1 : 0;
+    }
     // The B tangent states are independent of each other; on grids whose single launches cannot fill the GPU they
     // run on B side streams (fork / join with events) so that their kernels overlap.  Dependencies: a tangent H
     // half-step reads the primal D of the previous step (so it waits for the primal D launch, and the next primal D
@@ -1752,6 +1847,7 @@ int cev_fdtd_destroy(cev_fdtd* p) {
     p->stage_w.release(); p->stage_p.release();
     p->adj_stage_w.release(); p->adj_stage_g.release();
     p->batch_tab_H.release(); p->batch_tab_D.release();
+    p->batch_tab_F0.release(); p->batch_tab_F1.release(); p->tan_shadow.release();
     if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
     for (auto q : p->side) cudaStreamDestroy(q);
     for (auto e : p->side_ev) cudaEventDestroy(e);
@@ -1772,7 +1868,10 @@ int cev_fdtd_destroy(cev_fdtd* p) {
 int cev_fdtd_set_option(cev_fdtd* p, const char* name, int64_t value) {
     if (!p || !name) return fail("NULL argument");
     p->epoch++;
-    if (!strcmp(name, "jvp_batch")) {
+    if (!strcmp(name, "jvp_fused")) {
+        if (value < -1 || value > 1) return fail("jvp_fused must be -1 (auto), 0 or 1");
+        p->jvp_fused = (int)value;
+    } else if (!strcmp(name, "jvp_batch")) {
         if (value < -1 || value > 1) return fail("jvp_batch must be -1 (auto), 0 or 1");
         p->jvp_batch = (int)value;
     } else if (!strcmp(name, "jvp_streams")) {

@@ -124,6 +124,9 @@ if "c5" in which:
     wave = np.exp(-(t - 400) ** 2 / (2 * 120.0 ** 2)) * np.cos(2 * np.pi * 299792458.0 / 1550e-9 * (0.5 * DL / (np.sqrt(3) * 299792458.0)) * t)
     for dtype, name in ((torch.float64, "f64"), (torch.float32, "f32")):
         F = ceviche_b200.fdtd(eps_t, DL, [20, 20, 0], dtype=dtype)
+        for kv in os.environ.get("C5_OPTS", "").split(","):
+            if kv:
+                F.set_option(kv.split("=")[0], int(kv.split("=")[1]))
         F.jvp_run(10, Vt, [("z", prof, wave[:10])], [("Ez", mask)])
         F.initialize_fields()
         s, (series, dseries) = timed(lambda: F.jvp_run(steps, Vt, [("z", prof, wave)], [("Ez", mask)]))

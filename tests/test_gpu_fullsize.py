@@ -160,8 +160,8 @@ def test_config4_full_size_gradient_properties():
 
 def test_config5_full_size_batched_tangents():
     """Config 5 at its stated grid (2-D 2048 x 2048 grating coupler, 16 fill-factor directions through the sigmoid
-    projection, examples/forwardmode_grating_coupler.py:138-162): the batched tangent launches are bit-identical to one
-    launch per tangent, and a tangent equals a central finite difference of the forward run."""
+    projection, examples/forwardmode_grating_coupler.py:138-162): the batched tangent half-steps and the fused tangent
+    step are bit-identical to one launch per tangent, and a tangent equals a central finite difference of the forward run."""
     import ceviche_b200
     from ceviche_b200.parametrization import grating_coupler
     steps, B = 260, 16
@@ -175,13 +175,17 @@ def test_config5_full_size_batched_tangents():
     wave = np.exp(-(t - 60) ** 2 / (2 * 20.0 ** 2)) * np.cos(0.3 * t)
     srcs, probes = [("z", prof, wave)], [("Ez", mask)]
     out = {}
-    for batch in (0, -1):
+    for name, opts in (("one launch per tangent", {"jvp_fused": 0, "jvp_batch": 0}), ("batched half-steps", {"jvp_fused": 0}),
+                       ("fused tangent step", {})):
         F = ceviche_b200.fdtd(eps, DL, [20, 20, 0])
-        F.set_option("jvp_batch", batch)
-        out[batch] = F.jvp_run(steps, V, srcs, probes)
+        for k, v in opts.items():
+            F.set_option(k, v)
+        out[name] = F.jvp_run(steps, V, srcs, probes)
         assert F._active == 0b011100
-    assert torch.equal(out[0][0], out[-1][0]) and torch.equal(out[0][1], out[-1][1])
-    series, dseries = out[-1]
+    ref = out["one launch per tangent"]
+    for name in ("batched half-steps", "fused tangent step"):
+        assert torch.equal(out[name][0], ref[0]) and torch.equal(out[name][1], ref[1]), name
+    series, dseries = out["fused tangent step"]
     norms = dseries.flatten(1).norm(dim=1)
     assert float(norms.max()) > 0
     b = int(norms.argmax())                                   # the tooth group under the source / probe

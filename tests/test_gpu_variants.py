@@ -315,3 +315,30 @@ def test_graph_replay_equals_plain_launches(shape, npml, comps, dtype):
         assert np.array_equal(f0[k], f1[k]), k
     for a, b in zip(p0, p1):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("dtype,arith", [(torch.float64, None), (torch.float32, None), (torch.float32, "f64")])
+@pytest.mark.parametrize("shape,npml", [((96, 128, 1), (5, 6, 0)), ((70, 264, 1), (8, 9, 0)), ((33, 40, 1), (0, 0, 0))])
+def test_fused_tangent_step_equals_the_two_kernel_path(shape, npml, dtype, arith):
+    """2-D TM forward-mode sweeps: the fused tangent step (csrc/tan2d_fused.cuh: both half-steps of all B tangent states in
+    one launch, states ping-ponged) against the batched half-step launches: probe series, tangent series and the final
+    tangent states (fields and PML integrals) bit for bit, for odd and even step counts."""
+    import ceviche_b200
+    for steps in (1, 2, 7, 30):
+        rng = np.random.default_rng(5)
+        eps = 1 + 2 * rng.random(shape)
+        V = torch.as_tensor(rng.standard_normal((3,) + shape))
+        prof = np.zeros(shape); prof[shape[0] // 2, shape[1] // 3, 0] = 1.0
+        prof2 = rng.random(shape) * (rng.random(shape) < 0.02)
+        probes = [("Ez", rng.random(shape)), ("Hx", rng.random(shape)), ("Hy", (rng.random(shape) < 0.1) * 1.0), ("Dz", rng.random(shape))]
+        t = np.arange(steps)
+        srcs = [("z", prof, np.cos(0.3 * t) + 1), ("z", prof2, np.sin(0.2 * t + 0.3))]
+        out = {}
+        for fused in (0, 1):
+            F = ceviche_b200.fdtd(eps, 5e-8, list(npml), dtype=dtype, arith=arith)
+            F.set_option("jvp_fused", fused)
+            s_, ds = F.jvp_run(steps, V, srcs, probes)
+            out[fused] = (s_, ds, [x.clone() for st in F._tangent_states for grp in st[1:] for x in grp])
+        assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]), steps
+        assert all(torch.equal(a, b) for a, b in zip(out[0][2], out[1][2])), steps
+
