@@ -12,12 +12,18 @@ Host-side set-up (dt, the six 1-D sigma profiles) is fp64 numpy following the re
 formulas; the 30 full-grid coefficient arrays of fdtd.py:265-311 are never built.
 """
 import ctypes as C
+import functools
 
 import numpy as np
 import torch
 
 from . import _lib
 from .constants import C_0, EPSILON_0
+
+
+def _base(t):
+    from .autodiff import base
+    return base(t)
 
 FIELD_KEYS = ("Ex", "Ey", "Ez", "Dx", "Dy", "Dz", "Hx", "Hy", "Hz")
 _FIELD_CODE = {k: i for i, k in enumerate(FIELD_KEYS)}
@@ -110,6 +116,19 @@ class _Plan:
                 self.handle = C.c_void_p()
         except Exception:
             pass
+
+
+def _host(method):
+    """Host-side bookkeeping of the object runs below any active torch.func transform (autodiff.plain): its tensors go to
+    the C ABI by pointer."""
+    @functools.wraps(method)
+    def wrapped(self, *args, **kwargs):
+        if torch._C._are_functorch_transforms_active():
+            from .autodiff import plain
+            with plain():
+                return method(self, *args, **kwargs)
+        return method(self, *args, **kwargs)
+    return wrapped
 
 
 def fold_probes(plan, partials, n_probes, stream):
@@ -253,8 +272,11 @@ class fdtd:
     def _compute_update_parameters(self, mu_r=1.0):
         """Only the D->E coefficients are arrays (fdtd.py:314-316); everything else lives in the
         plan's 1-D tables."""
+        from .autodiff import base, plain
         self._mE64 = [1 / e for e in (self.eps_xx, self.eps_yy, self.eps_zz)]
-        self._mE = [m.to(self.dtype).contiguous() for m in self._mE64]
+        # what the kernels read: plain tensors (under torch.func transforms _mE64 is wrapped; see autodiff.base / plain)
+        with plain():
+            self._mE = [base(m).to(self.dtype).contiguous() for m in self._mE64]
         self.mEx1, self.mEy1, self.mEz1 = self._mE
         # the reference's m*1..4 arrays freeze dt at THIS call (a later `F.dL = ...` changes dt and the curls,
         # fdtd.py:41-45, 80, but not the coefficients until eps_r is assigned again)
@@ -262,6 +284,7 @@ class fdtd:
             self._plan = None
         self._coef_dt = self.dt
 
+    @_host
     def _ensure_plan(self):
         if self._plan is None:
             self._plan = _Plan(self.device, self.dtype, self.arith_f64, self.grid_shape, self.dL, self._coef_dt,
@@ -302,6 +325,7 @@ class fdtd:
         self._shadow = None
         self._st_cache = None
 
+    @_host
     def initialize_fields(self):
         """fdtd.py:147-211: zero state, t_index = 0, a NEW fields dict."""
         self.t_index = 0
@@ -402,6 +426,15 @@ class fdtd:
             self._st_cache = None
             self._publish()
             return self.fields
+        if torch._C._are_functorch_transforms_active():     # nothing to differentiate in this step: run it below the transform
+            with autodiff.plain():
+                self._H, self._D = [_base(t) for t in self._H], [_base(t) for t in self._D]
+                if self._pml is not None:
+                    self._pml = {fam: [_base(t) for t in ts] for fam, ts in self._pml.items()}
+                return self._step_plain(plan, [None if j is None else _base(j) for j in J])
+        return self._step_plain(plan, J)
+
+    def _step_plain(self, plan, J):
         with torch.cuda.device(self.device):
             new = torch.empty((9,) + self.grid_shape, dtype=self.dtype, device=self.device).unbind(0)   # nine fresh arrays
             Hn, Dn, En = new[0:3], new[3:6], new[6:9]
@@ -422,7 +455,7 @@ class fdtd:
         """profile / mask array -> cev_points (+ tensors kept alive in `keep`)."""
         if not torch.is_tensor(arr):
             arr = torch.as_tensor(np.asarray(arr, dtype=np.float64))
-        arr = arr.to(device=self.device, dtype=torch.float64)
+        arr = _base(arr).to(device=self.device, dtype=torch.float64)
         arr = reshape_to_ND(arr, 3).expand(self.grid_shape).reshape(-1)
         pts = _lib.cev_points()
         pts.field = field_code
@@ -437,6 +470,7 @@ class fdtd:
             keep += [nz, w]
         return pts
 
+    @_host
     def set_sources(self, sources):
         """sources: [(component 'x'|'y'|'z', profile array)].  J(t) = sum_s profile_s * waveform[t, s]."""
         plan = self._ensure_plan()
@@ -450,6 +484,7 @@ class fdtd:
         self._n_sources = len(sources)
         self._source_mask = sum({1 << _COMP[comp] for comp, _ in sources})
 
+    @_host
     def set_probes(self, probes):
         """probes: [(field key 'Ex'..'Hz', mask array)].  series[t, p] = sum(field_p * mask_p)."""
         plan = self._ensure_plan()
@@ -470,6 +505,7 @@ class fdtd:
         self._n_probes = len(probes)
         self._n_slots = n_slots.value
 
+    @_host
     def set_monitors(self, monitors, freqs):
         """Running-DFT monitors: [(field key 'Ex'..'Hz', mask array)] (the non-zero cells of the mask are monitored)
         at the frequencies `freqs` (Hz).  While run() advances, F_m(f)[q] = sum_n field_q(n) exp(-2 pi i f n dt)
@@ -484,7 +520,7 @@ class fdtd:
         for m, (key, mask) in enumerate(monitors):
             if not torch.is_tensor(mask):
                 mask = torch.as_tensor(np.asarray(mask))
-            mask = reshape_to_ND(mask.to(self.device), 3).expand(self.grid_shape).reshape(-1)
+            mask = reshape_to_ND(_base(mask).to(self.device), 3).expand(self.grid_shape).reshape(-1)
             nz = torch.nonzero(mask).reshape(-1).contiguous()
             pts[m].field, pts[m].n, pts[m].idx, pts[m].cell0, pts[m].weight = _FIELD_CODE[key], nz.numel(), _ptr(nz), 0, None
             keep.append(nz)
@@ -498,6 +534,7 @@ class fdtd:
         self._mon_freqs = freqs
         self._mon_acc = torch.zeros((self._n_mon_pts, len(freqs), 2), dtype=torch.float64, device=self.device)
 
+    @_host
     def reset_monitors(self):
         if self._mon_acc is not None:
             self._mon_acc.zero_()
@@ -519,6 +556,7 @@ class fdtd:
         self.set_sources([(s[0], s[1]) for s in sources])
         self.set_probes(list(probes))
 
+    @_host
     def _prepare_run(self, steps, sources, probes, waveforms):
         self._ensure_plan()
         if sources is None and probes is None and waveforms is None and self._n_sources == 0:
@@ -541,7 +579,7 @@ class fdtd:
                 waveforms = np.zeros((steps, 0))
         if not torch.is_tensor(waveforms):
             waveforms = torch.as_tensor(np.ascontiguousarray(waveforms, dtype=np.float64))
-        waveforms = waveforms.to(device=self.device, dtype=torch.float64).contiguous()
+        waveforms = _base(waveforms).to(device=self.device, dtype=torch.float64).contiguous()
         if tuple(waveforms.shape) != (steps, n_src):
             raise ValueError("waveforms must have shape (steps, n_sources) = {}".format((steps, n_src)))
         self._drive(self._source_mask)
@@ -573,6 +611,7 @@ class fdtd:
         waveforms = self._prepare_run(steps, sources, probes, waveforms)
         return autodiff.jvp_run(self, steps, waveforms, eps_tangents)
 
+    @_host
     def _run_raw(self, steps, waveforms, refresh=True, fused=True):
         plan = self._ensure_plan()
         with torch.cuda.device(self.device):
@@ -619,6 +658,7 @@ class fdtd:
             return True
         return not any(int(p) for p in self.npml) and self.N >= (1 << 21) and min(self.grid_shape) >= 32
 
+    @_host
     def _shadow_state(self):
         if self._shadow is None:
             self._shadow = ([torch.empty_like(t) for t in self._H], [torch.empty_like(t) for t in self._D],
@@ -627,6 +667,7 @@ class fdtd:
         sh.H, sh.D, sh.ICE, sh.IH = (_ptr3(ts) for ts in self._shadow)
         return sh
 
+    @_host
     def _refresh_E(self):
         plan = self._ensure_plan()
         En = [torch.empty_like(t) for t in self._D]

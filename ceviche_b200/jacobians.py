@@ -2,13 +2,21 @@
 (ceviche/jacobians.py:16-73), over torch instead of HIPS autograd.
 
 reverse   -> torch.autograd: one backward sweep per OUTPUT element (jacobians.py:29-35)
-forward   -> torch forward-mode AD: one run per INPUT direction (jacobians.py:38-51); for FDTD
-             problems prefer `fdtd.jvp_run`, which advances a batch of directions in one sweep
+forward   -> torch forward-mode AD.  The reference runs `fun` once per INPUT direction (jacobians.py:38-51); here a
+             batch of directions goes through ONE evaluation of `fun` (torch.vmap over torch.func.jvp, in chunks of
+             `forward_chunk` directions): every fdtd.run() inside it becomes one batched tangent sweep
+             (autodiff._RunTanFn.vmap -> cev_fdtd_jvp_run with B tangent states) and every fdtd.forward() one primal
+             step plus B tangent steps.  A `fun` that torch.vmap cannot trace (in-place writes into unbatched tensors,
+             .item(), numpy round trips) falls back to one pass per direction; `last_forward_path` says which ran.
 numerical -> one-sided finite differences (jacobians.py:54-73)
 Returns an (n_out, n_in) array (torch tensor on the input's device)."""
 import numpy as np
 import torch
 import torch.autograd.forward_ad as fwAD
+
+
+forward_chunk = 16          # directions per evaluation of `fun` in mode='forward' (B tangent states live at once)
+last_forward_path = None    # 'batched' | 'per-direction: <why the batched pass was not possible>'
 
 
 def _as_tensor(x):
@@ -53,6 +61,29 @@ def _reverse(fun, x):
 
 
 def _forward(fun, x):
+    global last_forward_path
+    try:
+        J = _forward_batched(fun, x)
+        last_forward_path = "batched"
+        return J
+    except Exception as e:          # not traceable by torch.vmap: the reference's schedule, one pass per direction
+        last_forward_path = "per-direction: {}: {}".format(type(e).__name__, str(e).splitlines()[0] if str(e) else "")
+    return _forward_per_direction(fun, x)
+
+
+def _forward_batched(fun, x):
+    n = x.numel()
+    if n == 0:
+        raise ValueError("no input directions")
+    E = torch.eye(n, dtype=x.dtype, device=x.device).reshape((n,) + tuple(x.shape))
+
+    def column(t):
+        return torch.func.jvp(lambda z: _flat(fun(z)), (x,), (t,))[1]
+    cols = torch.vmap(column, chunk_size=max(1, min(int(forward_chunk), n)))(E)        # [n_in, n_out]
+    return cols.detach().transpose(0, 1).contiguous()
+
+
+def _forward_per_direction(fun, x):
     cols = []
     flat = x.reshape(-1)
     for q in range(flat.numel()):

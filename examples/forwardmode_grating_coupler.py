@@ -2,7 +2,8 @@
 examples/forwardmode_grating_coupler.py (:138-240): a grating whose teeth are the sigmoid projection of a smooth density
 around 1 - fill_factor, a pulsed source in the slab, the power through a line above the grating, and d(power)/d(fill
 factor) by forward-mode differentiation.  The reference traces one complete run per parameter (jacobians.py:38-51); here
-ALL fill factors (one per group of teeth) ride along in ONE sweep (fdtd.jvp_run: batched tangent launches).
+ALL fill factors (one per group of teeth) ride along in ONE sweep (fdtd.jvp_run: batched tangent launches), also when
+asked for through `jacobian(objective, mode='forward')` as the reference's example does (`sensitivities_by_jacobian`).
 
     python examples/forwardmode_grating_coupler.py [N] [groups] [steps]
 """
@@ -43,6 +44,20 @@ def power_and_sensitivities(P, ff, dtype=torch.float64):
     return power, dpower
 
 
+def sensitivities_by_jacobian(P, ff, dtype=torch.float64):
+    """The same numbers the way the reference's example asks for them (forwardmode_grating_coupler.py:200-240):
+    `jacobian(objective, mode='forward')` of the power as a function of the fill factors.  `objective` is evaluated ONCE
+    for all groups (torch.vmap over torch.func.jvp): the sigmoid projection is differentiated by torch, the run() inside
+    becomes one batched tangent sweep."""
+    G = P["G"]
+
+    def objective(ff):
+        F = ceviche_b200.fdtd(G.eps_r(ff.to("cuda")), P["dL"], [P["npml"], P["npml"], 0], dtype=dtype)
+        series = F.run(P["steps"], [("z", P["prof"], P["wave"])], [("Ez", P["mask"])])
+        return (series ** 2).sum()
+    return ceviche_b200.jacobian(objective, mode='forward')(np.asarray(ff, dtype=np.float64))[0]
+
+
 if __name__ == "__main__":
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 512
     groups = int(sys.argv[2]) if len(sys.argv) > 2 else 8
@@ -58,3 +73,6 @@ if __name__ == "__main__":
     e = np.zeros(groups); e[g] = h
     fd = (float(power_and_sensitivities(P, ff + e)[0]) - float(power_and_sensitivities(P, ff - e)[0])) / (2 * h)
     print("finite difference for group %d: %+.6e (forward mode: %+.6e)" % (g, fd, float(dpower[g])))
+    dj = sensitivities_by_jacobian(P, ff)
+    print("jacobian(mode='forward') [%s]: max |difference| to the sweep above %.3e" % (
+        ceviche_b200.jacobians.last_forward_path, float((dj - dpower).abs().max())))

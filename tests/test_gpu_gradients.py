@@ -71,6 +71,8 @@ def test_reference_forward_mode_tests(name, golden_dir):
         return _ref_objective(F, case, shape, array_valued=True)(F)
 
     jac = jacobian(objective, mode='forward')(2.0).cpu().numpy().reshape(shape)
+    from ceviche_b200 import jacobians
+    assert jacobians.last_forward_path == "batched", jacobians.last_forward_path      # torch.vmap over torch.func.jvp
     assert rel_l2(jac, gold["jvp_ad"]) <= 1e-10
     assert rel_l2(jac, gold["fd_one_sided"]) <= ALLOWED_RATIO
     assert rel_l2(jac, gold["fd_central"]) <= 1e-6
@@ -322,6 +324,73 @@ def test_forward_mode_through_the_fused_run():
     assert rel_l2(jf, jr) <= 1e-10
 
 
+def test_jacobian_forward_mode_is_one_batched_sweep(monkeypatch):
+    """jacobian(mode='forward') (ceviche/jacobians.py:38-51) evaluates `fun` ONCE for a batch of input directions: a
+    run()-based objective costs one primal run and one tangent sweep with B states, a forward()-loop objective one primal
+    step and B tangent steps per time step.  Same numbers as one pass per direction (the reference's schedule) and as
+    reverse mode."""
+    import ceviche_b200
+    from ceviche_b200 import autodiff, jacobian, jacobians
+    case = cases.grad_case("probe3d")
+    shape = case["eps"].shape
+    eps = torch.as_tensor(case["eps"]).cuda()
+    w = torch.as_tensor(cases.objective_weights(case["steps"], len(case["probes"]))).cuda()
+    rng = np.random.default_rng(11)
+    bumps = torch.as_tensor(rng.random((5,) + shape)).cuda()
+    sweeps, evaluations = [], []
+    real_sweep = autodiff._tangent_sweep
+    monkeypatch.setattr(autodiff, "_tangent_sweep", lambda sim, tape, batch: (sweeps.append(len(batch)), real_sweep(sim, tape, batch))[1])
+
+    def objective(c):           # five parameters in, two numbers out
+        evaluations.append(1)
+        e = eps + (c.to(eps.device).reshape(5, 1, 1, 1) * bumps).sum(0)
+        F = ceviche_b200.fdtd(e, case["dL"], case["npml"])
+        series = F.run(case["steps"], case["sources"], case["probes"])
+        return torch.stack([(series ** 2 * w).sum(), (series[-10:] * w[-10:]).sum()])
+    x = np.array([0.1, 0.0, 0.3, 0.2, 0.05])
+    jf = jacobian(objective, mode='forward')(x)
+    assert jacobians.last_forward_path == "batched", jacobians.last_forward_path
+    assert sweeps == [5] and len(evaluations) == 1
+    assert tuple(jf.shape) == (2, 5)
+    per_direction = jacobians._forward_per_direction(objective, torch.as_tensor(x))
+    assert sweeps == [5] + [1] * 5
+    assert rel_l2(jf.cpu().numpy(), per_direction.cpu().numpy()) <= 1e-13
+    jr = jacobian(objective, mode='reverse')(x)
+    assert rel_l2(jf.cpu().numpy(), jr.cpu().numpy()) <= 1e-10
+    # in chunks of two directions: three evaluations, sweeps of 2 + 2 + 1 states
+    del sweeps[:], evaluations[:]
+    monkeypatch.setattr(jacobians, "forward_chunk", 2)
+    jc = jacobian(objective, mode='forward')(x)
+    assert sweeps == [2, 2, 1] and len(evaluations) == 3 and jacobians.last_forward_path == "batched"
+    assert torch.equal(jc, jf)
+
+    # the reference-style loop over forward(): array-valued, three parameters, fp64 and fp32 storage
+    comp, prof, wave = case["sources"][0]
+    prof_t = torch.as_tensor(prof).cuda()
+    for dtype, tol in ((torch.float64, 1e-13), (torch.float32, 1e-6)):
+        def loop_objective(c):
+            e = eps + (c.to(eps.device).reshape(3, 1, 1, 1) * bumps[:3]).sum(0)
+            F = ceviche_b200.fdtd(e, case["dL"], case["npml"], dtype=dtype)
+            S = 0.0
+            for t in range(25):
+                fields = F.forward(**{"J" + comp: (prof_t * float(wave[t])).to(dtype)})
+                S = S + fields["Ez"] * fields["Hx"] + fields["Dy"]
+            return S
+        x3 = np.array([0.1, 0.2, 0.0])
+        jl = jacobian(loop_objective, mode='forward')(x3)
+        assert jacobians.last_forward_path == "batched", jacobians.last_forward_path
+        assert tuple(jl.shape) == (int(np.prod(shape)), 3)
+        ref = jacobians._forward_per_direction(loop_objective, torch.as_tensor(x3))
+        assert rel_l2(jl.double().cpu().numpy(), ref.double().cpu().numpy()) <= tol
+
+    # a `fun` torch.vmap cannot trace falls back to one pass per direction, with the same result
+    def untraceable(c):
+        return objective(c) * float(np.asarray(c.detach().cpu())[0] * 0 + 1)
+    jb = jacobian(untraceable, mode='forward')(x)
+    assert jacobians.last_forward_path.startswith("per-direction"), jacobians.last_forward_path
+    assert rel_l2(jb.cpu().numpy(), jf.cpu().numpy()) <= 1e-13
+
+
 def test_forwardmode_grating_coupler_example():
     """examples/forwardmode_grating_coupler.py (the time-domain part of the reference's example of the same name): the
     sensitivities of the coupled power to every tooth group's fill factor from ONE batched tangent sweep agree with central
@@ -340,3 +409,8 @@ def test_forwardmode_grating_coupler_example():
         e = np.zeros(4); e[g] = h
         fd = (float(ex.power_and_sensitivities(P, ff + e)[0]) - float(ex.power_and_sensitivities(P, ff - e)[0])) / (2 * h)
         assert abs(fd - float(dpower[g])) <= 1e-5 * float(dpower.abs().max()), (g, fd, float(dpower[g]))
+    # the reference's own call, jacobian(objective, mode='forward'): one evaluation, one batched sweep, same numbers
+    from ceviche_b200 import jacobians
+    dj = ex.sensitivities_by_jacobian(P, ff)
+    assert jacobians.last_forward_path == "batched", jacobians.last_forward_path
+    assert float((dj - dpower).abs().max()) <= 1e-10 * float(dpower.abs().max())

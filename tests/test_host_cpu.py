@@ -190,3 +190,82 @@ def test_design_region_boxes():
     assert boxes[2][0] >= boxes[2][1]                       # does not touch the third slab: empty x-range
     slab = types.SimpleNamespace(design_region=None, Nx=12, Ny=6, Nz=5, lo=0, hi=4)
     assert SlabFDTD._local_grad_box(slab) is None
+
+
+def test_jacobian_forward_mode_batches_directions_on_cpu():
+    """Host logic of jacobian(mode='forward') (ceviche/jacobians.py:38-51): a batch of directions through ONE evaluation of
+    `fun` (torch.vmap over torch.func.jvp), in chunks; a `fun` torch.vmap cannot trace falls back to one pass per
+    direction.  Checked on torch-only functions (the FDTD nodes need a GPU: tests/test_gpu_gradients.py)."""
+    import torch
+    from ceviche_b200 import jacobian, jacobians
+    calls = []
+
+    def fun(x):
+        calls.append(1)
+        y = torch.zeros(3, dtype=torch.float64)
+        y[0:2] = x[0:2] ** 2
+        return torch.cat([y, (x[0] * x[2]).reshape(1)])
+    x = np.array([1.0, 2.0, 3.0])
+    exact = np.array([[2.0, 0, 0], [0, 4.0, 0], [0, 0, 0], [3.0, 0, 1.0]])
+    J = jacobian(fun, mode='forward')(x)
+    assert jacobians.last_forward_path == "batched" and len(calls) == 1
+    assert np.array_equal(J.numpy(), exact)
+    assert np.array_equal(jacobian(fun, mode='reverse')(x).numpy(), exact)
+    assert np.allclose(jacobian(fun, mode='numerical')(x).numpy(), exact, atol=1e-5)
+    del calls[:]
+    old = jacobians.forward_chunk
+    try:
+        jacobians.forward_chunk = 2
+        assert np.array_equal(jacobian(fun, mode='forward')(x).numpy(), exact) and len(calls) == 2
+    finally:
+        jacobians.forward_chunk = old
+
+    def untraceable(x):
+        return fun(x) * float(np.asarray(x.detach())[0])         # a numpy round trip: no data pointer under torch.vmap
+    J = jacobian(untraceable, mode='forward')(x)
+    assert jacobians.last_forward_path.startswith("per-direction")
+    assert np.array_equal(J.numpy(), exact)
+    assert tuple(jacobian(lambda c: c * 3, mode='forward')(2.0).shape) == (1, 1)     # scalar in, scalar out
+    with pytest.raises(ValueError):
+        jacobian(fun, mode='sideways')
+
+
+def test_host_tensors_stay_plain_under_torch_func_transforms():
+    """Under torch.vmap(torch.func.jvp(.)) every op returns a wrapped tensor without a data pointer; the object's
+    bookkeeping runs inside autodiff.plain() and strips wrappers with autodiff.base(), so the C ABI gets real pointers.
+    torch.func.grad (whose wrappers do not say requires_grad) is refused instead of silently treated as a constant."""
+    import types
+    import torch
+    from torch._C._functorch import is_functorch_wrapped_tensor as wrapped
+    from ceviche_b200 import autodiff
+    x = torch.tensor([1.0, 2.0], dtype=torch.float64)
+    seen = {}
+
+    def fun(c):
+        m = 1 / (x * c)
+        seen["top_level_factory_is_wrapped"] = wrapped(torch.zeros(2))
+        with autodiff.plain():
+            z = torch.zeros(2, dtype=torch.float64)
+            seen["plain_factory_is_wrapped"] = wrapped(z)
+            seen["ptr"] = z.data_ptr() != 0 and (z.clone() * 2).data_ptr() != 0
+            b = autodiff.base(m).to(torch.float64).contiguous()
+            seen["base"] = (not wrapped(b)) and b.data_ptr() != 0 and torch.equal(b, 1 / (x * x))
+        sim = types.SimpleNamespace(_mE64=[m, m, m], _H=[z] * 3, _D=[z] * 3, _pml=None)
+        seen["needs_grad"] = autodiff.needs_grad(sim, [None, None, None])
+        return (m + z).sum()
+    t = torch.vmap(lambda d: torch.func.jvp(fun, (x,), (d,))[1])(torch.eye(2, dtype=torch.float64))
+    assert torch.allclose(t, -1 / x ** 3)        # evaluated at c = x: m = 1 / x^2
+    assert seen == {"top_level_factory_is_wrapped": True, "plain_factory_is_wrapped": False, "ptr": True, "base": True,
+                    "needs_grad": True}
+    with pytest.raises(NotImplementedError):                 # a batch of permittivities has no single plain value
+        torch.vmap(lambda e: autodiff.base(e).sum())(torch.ones(2, 3))
+
+    def through_func_grad(c):
+        m = 1 / (x * c)
+        z = torch.zeros(2, dtype=torch.float64)
+        autodiff.needs_grad(types.SimpleNamespace(_mE64=[m, m, m], _H=[z] * 3, _D=[z] * 3, _pml=None), [None, None, None])
+        return m.sum()
+    with pytest.raises(NotImplementedError):
+        torch.func.grad(through_func_grad)(x)
+    with autodiff.plain():                                   # no transform active: a no-op context
+        assert not wrapped(torch.zeros(1))
