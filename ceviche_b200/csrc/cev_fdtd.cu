@@ -1032,6 +1032,7 @@ int jvp_loop_fused2d(cev_fdtd* p, const cev_state* st, int B, const cev_state* t
         // shorter chunks than fp64
         a.xchunk = p->xchunk > 0 ? p->xchunk : (sizeof(T) == 4 ? 16 : 32);
         a.n_tiles = a.ntz * (int)((Nx + a.xchunk - 1) / a.xchunk);
+        a.pf_dist = p->pf_dist;
         a.aux_slot0 = 0;
         a.partials = tpartials ? tpartials + b * stride : nullptr;
         a.t_probe = -1;

@@ -43,8 +43,12 @@ __device__ __forceinline__ AT update_pp(AT old, AT curl, AT ua, AT ra, AT ub, AT
     return v;
 }
 
+#ifndef CEV_TAN2D_MINB
+#define CEV_TAN2D_MINB 4      // CTAs per SM the register budget is capped for (tuned: profiles/r2_tune_fused_tangent_occupancy.log)
+#endif
+
 template <typename T, typename AT, int V>
-__global__ void __launch_bounds__(32 * V2_BY, 4) k_tan2d_fused_batch(const StepArgs<T, AT>* table, int B, int64_t t_probe) {
+__global__ void __launch_bounds__(32 * V2_BY, CEV_TAN2D_MINB) k_tan2d_fused_batch(const StepArgs<T, AT>* table, int B, int64_t t_probe) {
     const StepArgs<T, AT>& a = batch_args<T, AT>(table, blockIdx.x % B, t_probe);
     const int bid = blockIdx.x / B;
     if (bid >= a.n_tiles) {       // probes of the previous step (E / D and H families) on the input state
@@ -127,8 +131,9 @@ __global__ void __launch_bounds__(32 * V2_BY, 4) k_tan2d_fused_batch(const StepA
 
     for (int i = xs; i < xe; ++i) {
         const int ip = (i + 1 == Nx) ? 0 : i + 1;
-        if ((lane & (128 / (int)(sizeof(T) * V) - 1)) == 0 && i + 2 < Nx) {      // one lane per 128-byte line: rows two ahead into L2
-            const int o2 = (i + 2) * Nz + k0;
+        const int pf = a.pf_dist + 1;      // rows ahead (prefetch_planes = 1, the default: two)
+        if ((lane & (128 / (int)(sizeof(T) * V) - 1)) == 0 && pf > 1 && i + pf < Nx) {      // one lane per 128-byte line into L2
+            const int o2 = (i + pf) * Nz + k0;
             prefetch_l2(tD + o2); prefetch_l2(dmE + o2); prefetch_l2(mE + o2); prefetch_l2(Dp + o2);
             prefetch_l2(tH0 + o2 - Nz); prefetch_l2(tH2 + o2 - Nz);
         }
