@@ -58,6 +58,50 @@ def test_config2_full_size_first_steps_against_oracle():
         assert rel_l2(F32.fields[k].cpu().numpy(), of[k]) <= 1e-5, k
 
 
+def _bounding_box(arr):
+    nz = np.nonzero(arr)
+    return tuple(slice(int(i.min()), int(i.max()) + 1) for i in nz)
+
+
+def test_config2_full_size_first_100_steps_against_c_oracle():
+    """config 2's parity at its full size over the first 100 time steps.  The reference itself needs ~3 s per
+    step here, so the CPU side is its C restatement (oracle/fdtd_c.c: bit-identical to the numpy port, which is bit-identical
+    to ceviche/fdtd.py -- tests/test_oracle_c.py, test_oracle_vs_reference.py) on all host cores; sources are written and
+    probes summed on their bounding boxes only."""
+    from oracle.fdtd_c import OracleFDTDC, set_threads
+    steps = 100
+    eps, sources, probes = _workload(steps)
+    F, series = _run(eps, sources, probes, steps, torch.float64)
+    set_threads(os.cpu_count() or 1)
+    O = OracleFDTDC(eps, DL, NPML)
+    J = {comp: np.zeros(SHAPE) for comp, _, _ in sources}
+    src = [(comp, prof, wave, _bounding_box(prof)) for comp, prof, wave in sources]
+    prb = [(key, mask, _bounding_box(mask)) for key, mask in probes]
+    o_series = np.zeros((steps, len(probes)))
+    for t in range(steps):
+        for comp, prof, wave, box in src:
+            J[comp][box] = prof[box] * wave[t]
+        f = O.step(**{"J" + comp: a for comp, a in J.items()})
+        for p, (key, mask, box) in enumerate(prb):
+            o_series[t, p] = np.sum(f[key][box] * mask[box])
+    of = O.fields()
+    for k in FIELD_KEYS:
+        assert np.linalg.norm(of[k]) > 0, k
+        assert rel_l2(F.fields[k].cpu().numpy(), of[k]) <= 1e-10, k
+    for p in range(len(probes)):
+        if np.abs(o_series[:, p]).max() > 0:          # (the arm probes at x = 226 are not reached within 100 steps)
+            assert rel_l2(series[:, p], o_series[:, p]) <= 1e-10, p
+        else:
+            assert np.abs(series[:, p]).max() == 0, p
+    assert sum(np.abs(o_series[:, p]).max() > 0 for p in range(len(probes))) >= 3
+    del F
+    F32, s32 = _run(eps, sources, probes, steps, torch.float32)
+    for k in FIELD_KEYS:
+        assert rel_l2(F32.fields[k].cpu().numpy(), of[k]) <= 1e-5, k
+    for p in range(3):
+        assert rel_l2(s32[:, p], o_series[:, p]) <= 1e-5, p
+
+
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32], ids=["f64", "f32"])
 def test_full_size_kernel_variants_bitwise(dtype):
     steps = 24
