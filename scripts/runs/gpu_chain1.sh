@@ -23,4 +23,4 @@ for t in json.load(open("gpurun_out/fp32_drift.json")):
         print("  arith %s steps %5d fields %.2e E %.2e worst %.2e series %.2e  energy/peak %.1e" % (r["arith"], r["time_steps"], r["fields_rel_l2"], r["E_rel_l2"], r["worst_field_rel_l2"], r["series_rel_l2_up_to_here"], r["E_energy_vs_peak"]))
 PY
 echo "== c5 profile"
-bash scripts/gpu_c5prof.sh
+bash scripts/runs/gpu_c5prof.sh

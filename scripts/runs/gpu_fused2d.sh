@@ -1,5 +1,4 @@
 mkdir -p gpurun_out
-timeout 600 python scripts/test_fused2d.py 2>&1 | grep -v Warn | tail -3
 timeout 1200 python -m pytest tests/test_gpu_gradients.py tests/test_gpu_scaled_configs.py tests/test_gpu_fullsize.py tests/test_gpu_variants.py -q 2>&1 | tail -3
 C5_STEPS=20000 timeout 900 python scripts/bench_configs.py c5 > gpurun_out/c5_20000_fused.log 2>&1; python - <<PY
 import json
