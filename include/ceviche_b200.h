@@ -117,7 +117,11 @@ int cev_fdtd_destroy(cev_fdtd* plan);
  * depth, "auto_tensor_map" 0|1: let variant 0 pick them on large 3-D grids); "fused_shape" 0 auto | lanes_z*100 + warps; "use_graph" / "jvp_streams" -1 auto | 0 | 1;
  * "xchunk" x-planes per CTA of the marching kernels (0 = auto); "lanes_z" 8|16|32 lanes of a warp along z;
  * "prefetch_planes" L2 prefetch distance; "split_launch" 0|1 separate launches for the PML-free interior and
- * the PML shell.  Results do not depend on them (bit-identical).
+ * the PML shell; "jvp_batch" 0|1 the tangent half-steps of a forward-mode sweep as one launch per half-step (1, default)
+ * or one per tangent state; "jvp_fused" -1 auto | 0 | 1 both tangent half-steps of all states in ONE launch on 2-D TM grids
+ * (tan2d_fused.cuh); "adjoint_variant" 0 auto | 1 one-thread-per-cell | 2 tensor-map kernels; "tma_stages_adjED" ring depth
+ * of the adjoint E/D part; "halo_pause" 0|1 suspend the peer-store halo exchange (x-slab recomputation legs).
+ * Results do not depend on them (bit-identical; the adjoint variants agree to 1e-12).
  * "active_components": 6-bit mask (bits 0-2: D/E x,y,z; bits 3-5: H x,y,z) of the components that may be non-zero;
  * the kernels neither read nor write the others (2-D TM / TE runs move 10-11 instead of 21 words per cell).  The
  * caller guarantees that the masked-out components are identically zero and are not driven. */
