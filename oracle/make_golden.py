@@ -207,9 +207,42 @@ def make_c5_scaled_golden():
           np.linalg.norm((up - dn) / (2 * h) - ds[0]) / np.linalg.norm(ds[0]))
 
 
+SPLITTER_EXAMPLE = dict(Nx=320, Ny=180, steps=4500, t0=600, sigma=100, npml=20, dL=5e-8)
+
+
+def make_splitter_example_golden():
+    """examples/simulate_splitter_fdtd.py at half size: the REFERENCE's own `measure_fields` (ceviche/utils.py:316-332)
+    over the REFERENCE's own fdtd object, called as the notebook calls it (`measure_fields(F, source, steps, J_outs)` with
+    source = t -> J_in * amp * gaussian(t)), on the example's geometry, for the straight guide and for the splitter."""
+    import contextlib
+    import importlib.util
+    import io
+    root = os.path.dirname(OUT.rstrip(os.sep).rsplit(os.sep, 1)[0])
+    spec = importlib.util.spec_from_file_location("simulate_splitter_fdtd", os.path.join(root, "examples", "simulate_splitter_fdtd.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    ref = ref_loader.load()
+    ref_utils = sys.modules["ceviche.utils"]
+    c = SPLITTER_EXAMPLE
+    eps_wg, eps_r, J_in, J_wg, J_outs = ex.geometry(c["Nx"], c["Ny"], c["npml"])
+    F = ref.fdtd(eps_r, dL=c["dL"], npml=[c["npml"], c["npml"], 0])
+    F_wg = ref.fdtd(eps_wg, dL=c["dL"], npml=[c["npml"], c["npml"], 0])
+    wave = ex.pulse(c["steps"], F.dt, c["t0"], c["sigma"])
+    source = lambda t: J_in * wave[t]
+    with contextlib.redirect_stdout(io.StringIO()):          # (the reference prints a progress line every 5 %)
+        measured_wg = ref_utils.measure_fields(F_wg, source, c["steps"], J_wg)
+        measured = ref_utils.measure_fields(F, source, c["steps"], J_outs)
+    T, f_max = ex.transmission(measured, measured_wg, F.dt)
+    np.savez_compressed(os.path.join(OUT, "example_splitter.npz"), measured_wg=measured_wg, measured=measured, T=T,
+                        f_max=np.float64(f_max), dt=np.float64(F.dt), **{k: np.float64(v) for k, v in c.items()})
+    print("example_splitter T", T, "f_max", f_max, "peak", np.abs(measured_wg).max(), np.abs(measured).max(0))
+
+
 def main(argv):
     os.makedirs(OUT, exist_ok=True)
-    which = argv[1:] or ["fields", "grads", "modes", "scaled"]
+    which = argv[1:] or ["fields", "grads", "modes", "scaled", "splitter"]
+    if "splitter" in which:
+        make_splitter_example_golden()
     if "scaled" in which:
         make_c2_scaled_golden()
         make_c5_scaled_golden()

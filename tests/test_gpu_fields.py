@@ -253,3 +253,35 @@ def test_measure_fields_and_aniplot_against_the_oracle_loop(capsys):
     assert [t for t, _ in panels] == [0, 12, 24, 36, 48]
     for t, arr in panels:
         assert rel_l2(arr, snaps[t + 1]["Ez"][:, :, 0]) <= 1e-10
+
+
+def test_splitter_example_against_the_reference(golden_dir):
+    """examples/simulate_splitter_fdtd.py (the time-domain workflow of the reference's simulate_splitter_fdtd.ipynb) at
+    half size: the probe series of the straight guide and of the two splitter arms against what the REFERENCE's own
+    measure_fields returned on the same inputs (tests/golden/example_splitter.npz, oracle/make_golden.py splitter), and
+    the derived transmission / peak frequency."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("simulate_splitter_fdtd", os.path.join(root, "examples", "simulate_splitter_fdtd.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    gold = np.load(os.path.join(golden_dir, "example_splitter.npz"))
+    kw = dict(Nx=int(gold["Nx"]), Ny=int(gold["Ny"]), steps=int(gold["steps"]), t0=int(gold["t0"]), sigma=int(gold["sigma"]),
+              npml=int(gold["npml"]), dL=float(gold["dL"]))
+    R = ex.simulate(**kw)
+    assert R["F"].dt == float(gold["dt"])
+    assert rel_l2(R["measured_wg"][:, 0], gold["measured_wg"][:, 0]) <= 1e-10
+    for arm in range(2):
+        assert rel_l2(R["measured"][:, arm], gold["measured"][:, arm]) <= 1e-10, arm
+    assert np.allclose(R["T"], gold["T"], rtol=1e-9, atol=0) and R["f_max"] == float(gold["f_max"])
+    assert 0.9 < R["T"].sum() < 1.0
+    R32 = ex.simulate(dtype=torch.float32, **kw)
+    assert rel_l2(R32["measured_wg"][:, 0], gold["measured_wg"][:, 0]) <= 1e-5
+    for arm in range(2):
+        assert rel_l2(R32["measured"][:, arm], gold["measured"][:, arm]) <= 1e-5, arm
+    assert np.allclose(R32["T"], gold["T"], rtol=1e-3, atol=0)
+    # the reference's own call form (a callable source, one forward() per step) on the first 700 steps
+    from ceviche_b200.utils import measure_fields
+    early = measure_fields(R["F_wg"], lambda t: R["J_in"] * R["wave"][t], 700, R["J_in"])
+    again = measure_fields(R["F_wg"], (R["J_in"], R["wave"][:700]), 700, R["J_in"])
+    assert np.abs(again).max() > 0 and rel_l2(early[:, 0], again[:, 0]) <= 1e-12

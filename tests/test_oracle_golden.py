@@ -31,3 +31,26 @@ def test_zero_fields_stay_zero_in_2d_tm(golden_dir):
     for k in ("Ex", "Ey", "Hz", "Dx", "Dy"):
         assert float(gold["t1000_%s_norm" % k]) == 0.0
     assert float(gold["t1000_Ez_norm"]) > 0.0
+
+
+def test_c_oracle_matches_the_reference_on_the_splitter_example(golden_dir):
+    """tests/golden/example_splitter.npz holds what the REFERENCE's own measure_fields returned on the straight guide of
+    examples/simulate_splitter_fdtd.py (320 x 180, 4500 steps): the C restatement reproduces the series bit for bit."""
+    import importlib.util
+    from oracle.fdtd_c import OracleFDTDC
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("simulate_splitter_fdtd", os.path.join(root, "examples", "simulate_splitter_fdtd.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    gold = np.load(os.path.join(golden_dir, "example_splitter.npz"))
+    Nx, Ny, steps, npml = int(gold["Nx"]), int(gold["Ny"]), int(gold["steps"]), int(gold["npml"])
+    eps_wg, _, J_in, J_wg, _ = ex.geometry(Nx, Ny, npml)
+    O = OracleFDTDC(eps_wg, float(gold["dL"]), [npml, npml, 0])
+    assert O.dt == float(gold["dt"])
+    wave = ex.pulse(steps, O.dt, int(gold["t0"]), int(gold["sigma"]))
+    series, _ = O.run(steps, [("z", J_in, wave)], [("Ez", J_wg)])
+    assert np.array_equal(series, gold["measured_wg"])
+    T, f_max = ex.transmission(gold["measured"], gold["measured_wg"], O.dt)
+    assert np.array_equal(T, gold["T"]) and f_max == float(gold["f_max"])
+    assert 0.9 < T.sum() < 1.0 and abs(T[0] - T[1]) < 0.01 * T[0]          # a working 50 / 50 splitter
+    assert abs(f_max - 299792458.0 / 2e-6) < 0.03 * 299792458.0 / 2e-6
