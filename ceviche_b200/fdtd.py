@@ -330,6 +330,7 @@ class fdtd:
         """fdtd.py:147-211: zero state, t_index = 0, a NEW fields dict."""
         self.t_index = 0
         self._st_cache = None
+        self._ptr_cache = None      # (H list, D list, their pointer structs) as stored by the last plain forward()
         # could the state / 1/eps carry an autograd graph?  (eps_r that requires grad; set again by differentiable steps)
         self._grad_state = any(bool(m.requires_grad) for m in self.__dict__.get("_mE64", ()))
         if self.__dict__.get("_mon_acc") is not None:
@@ -435,18 +436,32 @@ class fdtd:
         return self._step_plain(plan, J)
 
     def _step_plain(self, plan, J):
-        with torch.cuda.device(self.device):
-            new = torch.empty((9,) + self.grid_shape, dtype=self.dtype, device=self.device).unbind(0)   # nine fresh arrays
-            Hn, Dn, En = new[0:3], new[3:6], new[6:9]
-            lib, h, s = plan.lib, plan.handle, self._stream()
-            st = self._st_cache
-            if st is None:                  # 1/eps and PML pointers only change with eps_r / a reset
-                st = self._st_cache = self._state()
+        # (no torch.cuda.device() context: every tensor names its device, the stream is asked for by device, and the C ABI
+        # guards the device itself.)  The host work per call is what this path costs on small grids, so: one allocation
+        # for the nine fresh arrays with their pointers by arithmetic, and the pointers of the state this very function
+        # stored last time reused (`_ptr_cache` is keyed by the identity of the lists it stored).
+        block = torch.empty((9,) + self.grid_shape, dtype=self.dtype, device=self.device)
+        new = block.unbind(0)                                           # nine fresh arrays
+        Hn, Dn, En = list(new[0:3]), list(new[3:6]), list(new[6:9])
+        if self.N:
+            base, n = block.data_ptr(), self.N * block.element_size()
+            pH, pD, pE = (_lib.c_void_p3(base + (3 * f) * n, base + (3 * f + 1) * n, base + (3 * f + 2) * n) for f in range(3))
+        else:
+            pH = pD = pE = _lib.c_void_p3(None, None, None)
+        lib, h, s = plan.lib, plan.handle, self._stream()
+        st = self._st_cache
+        if st is None:                  # 1/eps and PML pointers only change with eps_r / a reset
+            st = self._st_cache = self._state()
+        cache = self._ptr_cache
+        if cache is not None and cache[0] is self._H and cache[1] is self._D:
+            st.H, st.D = cache[2], cache[3]
+        else:
             st.H, st.D = _ptr3(self._H), _ptr3(self._D)
-            _lib.check(lib.cev_fdtd_step_H(h, C.byref(st), _ptr3(Hn), 0, self.Nx, s))
-            st.H = _ptr3(Hn)
-            _lib.check(lib.cev_fdtd_step_D(h, C.byref(st), _ptr3(Dn), _ptr3(En), _ptr3(J), _ONES3, 0, self.Nx, s))
-        self._H, self._D, self._E = list(Hn), list(Dn), list(En)
+        _lib.check(lib.cev_fdtd_step_H(h, C.byref(st), pH, 0, self.Nx, s))
+        st.H = pH
+        _lib.check(lib.cev_fdtd_step_D(h, C.byref(st), pD, pE, _ptr3(J), _ONES3, 0, self.Nx, s))
+        self._H, self._D, self._E = Hn, Dn, En
+        self._ptr_cache = (Hn, Dn, pH, pD)
         self._publish()
         return self.fields
 
