@@ -66,3 +66,33 @@ def test_reference_rejects_complex_J():
     with pytest.raises(TypeError):
         F.forward(Jz=J)
 
+
+
+def test_sigma_profiles_sweep_including_overlapping_and_oversized_pml():
+    """Every (N, npml) with N = 1..11 and npml = 0..8 on one axis: the host layer's 1-D profiles equal the reference's
+    sigma arrays bit for bit where the reference builds them (also where the low and high PML ramps overlap and overwrite
+    each other), and raise the same exception type where the reference's indices run out of its doubled grid."""
+    import itertools
+    from ceviche_b200.fdtd import sigma_profiles as host_profiles
+    ref = ref_loader.load()
+    dt = time_step(5e-8)
+    agree = errors = 0
+    for N, p in itertools.product(range(1, 12), range(0, 9)):
+        shape, npml = (N, 3, 2), [p, 0, 0]
+        try:
+            F = ref.fdtd(np.ones(shape), 5e-8, npml)
+            want, want_err = (F.sigHx[:, 0, 0].copy(), F.sigDx[:, 0, 0].copy()), None
+        except Exception as e:          # noqa: BLE001 (whatever numpy raises is the reference's error convention)
+            want, want_err = None, type(e)
+        for fn in (host_profiles, sigma_profiles):           # the product's host layer and the oracle's restatement
+            try:
+                sH, sD = fn(shape, npml, dt)
+                got, got_err = (sH[0], sD[0]), None
+            except Exception as e:      # noqa: BLE001
+                got, got_err = None, type(e)
+            assert got_err == want_err, (N, p, fn.__module__, got_err, want_err)
+            if want is not None:
+                assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), (N, p, fn.__module__)
+        agree += want is not None
+        errors += want is None
+    assert agree > 60 and errors > 0
