@@ -667,8 +667,17 @@ __global__ void __launch_bounds__(32 * BY) k_step_H_v5(const StepArgs<T, AT> a, 
 // D half-step.  Plane p (p >= xs-1) -> stage (p - xs + 1) % NS; the H boxes start one vector BEFORE the tile
 // along z (own cells at column V, the -1 neighbour of lane 0 at column V-1) and the halo row j-1 is row BY of
 // each block (row 0 .. BY-1 are the own rows).
+// Register budget of the D half-step: by default the compiler's own choice under __launch_bounds__(threads) (158 registers in
+// fp64 = 3 CTAs per SM, 122 in fp32 = 4).  -DCEV_V5_D_MINB=n caps it for n CTAs per SM (4: 128 registers in fp64 without
+// spills) -- an A/B knob; note that n = 1 is NOT the default: it lets the compiler take 196 registers.
+#ifdef CEV_V5_D_MINB
+#define CEV_V5_D_BOUNDS __launch_bounds__(32 * BY, CEV_V5_D_MINB)
+#else
+#define CEV_V5_D_BOUNDS __launch_bounds__(32 * BY)
+#endif
+
 template <typename T, typename AT, int V, int BY, int NS>
-__global__ void __launch_bounds__(32 * BY) k_step_D_v5(const StepArgs<T, AT> a, const __grid_constant__ V5MapsD maps) {
+__global__ void CEV_V5_D_BOUNDS k_step_D_v5(const StepArgs<T, AT> a, const __grid_constant__ V5MapsD maps) {
     using L = V5Layout<T, V, BY>;
     constexpr int BZ = L::BZ, ROWP = L::ROWP, BLK = L::BLK, DOFF = 3 * L::BLK;
     extern __shared__ __align__(128) unsigned char v5_smem[];
